@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark: autoregressive mel frames/s at batch 32 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host CPU
+
+One "step" = one full synthesis of the workload: encoder, 1000 K/V-cached decode steps at
+B=32 / S=258 (stop disabled so every sample emits all frames), Postnet.  `value` is measured with
+the inputs already resident in HBM; `e2e` is the same job through the public API from pinned
+host buffers with the results copied back.  Multi-GPU = independent replicas (decode does not
+shard across GPUs: SURVEY.md §8e), one process per GPU, max time over ranks.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "few-shot-transformer-tts_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "mel frames/sec autoregressive @ batch 32"
+UNIT = "frames/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload + algorithmic bytes (DESIGN.md "Roofline")
+# ------------------------------------------------------------------------------------------------
+def decode_step_params(cfg):
+    """Decoder parameters streamed on every step: all of decoder.* except the six kv_transforms."""
+    D, F, P, M, L = cfg.decoder_hidden, 4 * cfg.decoder_hidden, cfg.prenet_hidden, cfg.num_mels, cfg.n_decoder_layer
+    per_layer = 3 * D * D + D * D + D * D + D * D + 2 * D * F + 6 * D
+    return P * M + P + P * P + P + D * P + 1 + L * per_layer + 2 * D + M * D + D + 1
+
+
+def decode_bytes(cfg, batch, mem_len, n_steps, elem=4):
+    """Algorithmic HBM bytes of n_steps decode steps (weights once per step, cross K/V once per step,
+    self K/V of all previous frames, the appended K/V row, frame in/out)."""
+    kv = 2 * cfg.n_decoder_layer * cfg.decoder_hidden
+    w = decode_step_params(cfg) * elem
+    total = 0
+    for t in range(n_steps):
+        total += w + batch * kv * elem * mem_len + batch * kv * elem * (t + 1) + batch * kv * elem \
+            + batch * cfg.num_mels * 4 * 2
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reduce_max_over_ranks(value, world):
+    """max over ranks of a python float (the slowest rank defines the job's time)."""
+    if world == 1:
+        return value
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_throughput(units_per_rank, seconds_this_rank, world):
+    """Whole-job throughput of `world` replicas: all units / slowest rank's time."""
+    return units_per_rank * world / reduce_max_over_ranks(seconds_this_rank, world)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference algorithm (uncached O(T^2) loop) on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(batch_size, text_len, horizon, repeats=1):
+    """The oracle's faithful restatement of synthesize.eval_batch (re-runs the decoder over all
+    frames so far each step), B x text_len, truncated to `horizon` frames.  Returns frames/s."""
+    from oracle import tts_oracle as O
+    cfg = O.ModelConfig()
+    params = O.synth_params(cfg, seed=0)
+    params["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    batch = O.synth_batch(cfg, batch=batch_size, text_len=text_len, n_frames=4, seed=1)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            out = O.eval_batch_uncached(params, cfg, batch, max_frames=horizon)
+            times.append(time.perf_counter() - t0)
+    frames = out["mel_pre"].shape[0] * out["mel_pre"].shape[1]
+    return frames / min(times), times, frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = torch.get_num_threads()
+    horizon = args.ref_horizon
+    steps_fps = []
+    for i in range(args.warmup + args.steps):
+        fps, times, frames = cpu_reference_sample(args.batch, args.text_len, horizon)
+        if i >= args.warmup:
+            steps_fps.append((fps, times[0]))
+    secs = sum(t for _, t in steps_fps)
+    value = frames * len(steps_fps) / secs
+    sample = ("oracle port of synthesize.eval_batch (uncached O(T^2) loop, transformer/*.py fp32) on host CPU, "
+              "B=%d S=%d truncated to the first %d frames of %d (frames/s falls further with the horizon)"
+              % (args.batch, args.text_len, horizon, args.frames))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(steps_fps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "autoregressive synthesize.py decode, batch=%d, %d-byte text (S=%d tokens), %d frames, "
+                        "1xB200 per replica (BASELINE.json configs[1])" % (args.batch, args.text_len - 2, args.text_len,
+                                                                           args.frames),
+            "batch": args.batch, "text_tokens": args.text_len, "frames": args.frames, "stop": "disabled (bias -1e4)",
+            "storage": "fp32 weights + fp32 K/V cache", "parallelism": "replicas x%d (decode does not shard)" % args.gpus,
+            "l2": "per-step working set (200 MB weights + >=300 MB K/V) exceeds the 126 MB L2; no explicit flush",
+            "alignments": "encdec attention rows recorded on device (not copied to host)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    from oracle import tts_oracle as O      # weights/inputs generator + cpu_baseline only
+    from tts_b200 import _native
+    from tts_b200.engine import TtsEngine
+
+    cfg = O.ModelConfig(max_generation_frames=args.frames)
+    params = O.synth_params(cfg, seed=0)
+    params["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    eng = TtsEngine.from_state_dict(params, cfg, dev)
+    host_batch = O.synth_batch(cfg, batch=args.batch, text_len=args.text_len, n_frames=4, seed=1 + rank)
+    keys = ("inputs", "input_lengths", "input_spk_ids", "input_language_vecs")
+    pinned = {k: host_batch[k].pin_memory() for k in keys}
+    dev_batch = {k: v.to(dev) for k, v in pinned.items()}
+    sess = eng.new_session(args.batch, args.text_len, args.frames, "encdec")
+    lib = _native.load()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def job_resident():
+        return eng.generate(dev_batch, max_frames=args.frames, record_align="encdec", chunk=args.chunk,
+                            impl=args.decode_impl, session=sess)
+
+    out_host = {}
+
+    def job_e2e():
+        b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        out = eng.generate(b, max_frames=args.frames, record_align="encdec", chunk=args.chunk,
+                           impl=args.decode_impl, session=sess)
+        for k in ("mel_pre", "mel_aft", "generated_lengths"):
+            if k not in out_host:
+                out_host[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+            out_host[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    def timed(job, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = job()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / 1e3, out
+
+    for _ in range(max(args.warmup, 3)):
+        job_resident()
+    lib.tts_launch_count_reset()
+    with ClockSampler(local) as clocks:
+        secs, out = timed(job_resident, args.steps)
+    launches = int(lib.tts_launch_count())
+    frames_per_job = int(out["mel_pre"].shape[0] * out["mel_pre"].shape[1])
+    assert frames_per_job == args.batch * args.frames, "stop fired unexpectedly"
+    value = aggregate_throughput(frames_per_job * args.steps, secs, world)
+
+    job_e2e()
+    secs_e2e, out = timed(job_e2e, args.steps)
+    e2e_value = aggregate_throughput(frames_per_job * args.steps, secs_e2e, world)
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    # ---- roofline of the dominant kernel: the decode steps, timed alone with CUDA events ----------
+    mem = eng.encode(dev_batch["inputs"], dev_batch["input_lengths"], dev_batch["input_spk_ids"],
+                     dev_batch["input_language_vecs"])
+    dec_times = []
+    for _ in range(3):
+        sess.begin(mem, dev_batch["input_lengths"])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done = 0
+        while done < args.frames:
+            n = min(args.chunk, args.frames - done)
+            sess.step(n, update_state=True, impl=args.decode_impl)
+            done += n
+        e1.record()
+        torch.cuda.synchronize(dev)
+        dec_times.append(e0.elapsed_time(e1) / 1e3)
+    dec_secs = min(dec_times)
+    peak, peak_src = measured_peaks()
+    alg_bytes = decode_bytes(cfg, args.batch, args.text_len, args.frames)
+    achieved = alg_bytes / dec_secs / 1e9
+    n_launch = max(1, args.frames // args.chunk) if args.decode_impl in (0, 3) else args.frames
+    roofline = {"bound": "hbm", "kernel": "decode step (all phases of %d steps)" % args.frames,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes, "decode_seconds": dec_secs,
+                "us_per_decode_step": 1e6 * dec_secs / args.frames,
+                "share_of_job": dec_secs / (secs / args.steps)}
+    del n_launch
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            fps, times, frames = cpu_reference_sample(args.batch, args.text_len, args.ref_horizon)
+            cpu = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "oracle port of synthesize.eval_batch (uncached O(T^2) loop) on host CPU, B=%d S=%d, "
+                             "first %d of %d frames, %.1f s" % (args.batch, args.text_len, args.ref_horizon,
+                                                                args.frames, times[0])}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * reduce_max_over_ranks(secs, 1) / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "decode_impl": args.decode_impl}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--text-len", type=int, default=258)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--chunk", type=int, default=50, help="decode steps per launch / host poll")
+    ap.add_argument("--decode-impl", type=int, default=0, help="0 default, 1 per-phase kernels, 2 CUDA graph, 3 fused")
+    ap.add_argument("--ref-horizon", type=int, default=6, help="frames of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,123 @@
+"""ctypes binding of libtts_b200.so (the C ABI declared in include/tts_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is
+present, every product call raises.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
+TTS_MAX_LAYERS = 16
+ABI_VERSION = 3
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+u8p = C.POINTER(C.c_uint8)
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("scale", C.c_void_p), ("shift", C.c_void_p), ("bias", C.c_void_p),
+                ("act", C.c_int32), ("residual", C.c_void_p), ("ldr", C.c_int32), ("row_len", C.c_void_p),
+                ("rows_per_batch", C.c_int32), ("valid_rows", C.c_int32), ("out_rows_per_batch", C.c_int32),
+                ("out_row_offset", C.c_int32), ("head_dim", C.c_int32), ("n_heads", C.c_int32),
+                ("head_rows", C.c_int32), ("out_v", C.c_void_p)]
+
+
+class DecLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln_self_g", "ln_self_b", "w_qkv", "w_self_out", "ln_cross_g", "ln_cross_b", "w_cross_q", "w_cross_kv",
+        "w_cross_out", "ln_ffn_g", "ln_ffn_b", "w_ffn_in", "w_ffn_out")]
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("n_layers", "d_model", "n_heads", "d_ffn", "n_mels", "prenet_hidden")] +
+                [(n, C.c_void_p) for n in ("prenet_w0", "prenet_b0", "prenet_w1", "prenet_b1", "prenet_w2", "pe_scale",
+                                           "pe_table", "ln_out_g", "ln_out_b", "w_mel", "w_stop", "b_stop")] +
+                [("layer", DecLayerWeights * TTS_MAX_LAYERS)])
+
+
+class DecodeState(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("batch", "mem_len", "t_max")] +
+                [(n, C.c_void_p) for n in ("memory", "input_lengths", "self_k", "self_v", "cross_k", "cross_v",
+                                           "lengths", "finished", "frames", "stop_logits", "align_self", "align_cross",
+                                           "step_counter", "n_unfinished", "scratch")])
+
+
+_EXPORTS = {
+    "tts_abi_version": (C.c_int, []),
+    "tts_last_error": (C.c_char_p, []),
+    "tts_launch_count": (C.c_int64, []),
+    "tts_launch_count_reset": (None, []),
+    "tts_gemm_nt": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                              C.c_int32, C.c_int32, C.POINTER(GemmEpilogue), C.c_void_p]),
+    "tts_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                C.c_void_p, C.c_int32, C.c_void_p]),
+    "tts_embed_pe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tts_shift_pe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_void_p]),
+    "tts_pad_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_void_p]),
+    "tts_cond_embed": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tts_attention": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.c_int32, C.c_void_p, C.c_void_p]),
+    "tts_decode_scratch_bytes": (C.c_size_t, [C.POINTER(DecoderWeights), C.c_int32, C.c_int32, C.c_int32]),
+    "tts_decode_begin": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecodeState), C.c_void_p]),
+    "tts_decode_steps": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecodeState), C.c_int32, C.c_void_p,
+                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(check_device: bool = True):
+    """Load the shared library (once) and bind every symbol include/tts_b200.h declares."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("tts_b200: %s is missing - run `python __graft_entry__.py` (build()) first; "
+                               "there is no CPU or eager fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _EXPORTS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.tts_abi_version() != ABI_VERSION:
+            raise RuntimeError("tts_b200: ABI mismatch (library %d, binding %d)" % (lib.tts_abi_version(), ABI_VERSION))
+        _lib = lib
+    if check_device and not torch.cuda.is_available():
+        raise RuntimeError("tts_b200: no CUDA device; the mel path has no CPU fallback")
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_EXPORTS)
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = _lib.tts_last_error().decode("utf-8", "replace") if _lib is not None else "?"
+        raise RuntimeError("tts_b200.%s failed (%d): %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, CUDA - what every kernel expects."""
+    if not t.is_cuda:
+        raise RuntimeError("tts_b200: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

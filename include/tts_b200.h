@@ -1,0 +1,196 @@
+/*
+ * tts_b200.h — C ABI of the B200-native Transformer-TTS mel path.
+ *
+ * The reference (mutiann/few-shot-transformer-tts) has no FFI: its boundary for this path is
+ * the Python class API of the `transformer/` package.  This header is the
+ * C-ABI shared-library boundary underneath our drop-in `transformer/` package: plain
+ * pointers and sizes, no torch types.  Every entry point names the reference code it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - all matrices are row-major fp32, activations are [rows][channels] (batch-first,
+ *     channels-last, transformer/tacotron.py conventions), weights are torch Linear layout
+ *     [out][in];
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - return value 0 = success, non-zero = error; tts_last_error() gives the message.
+ *     Nothing in this library aborts or allocates device memory: scratch is caller-owned.
+ */
+#ifndef TTS_B200_H
+#define TTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTS_MAX_LAYERS 16
+#define TTS_ABI_VERSION 3
+
+/* ---- library / diagnostics -------------------------------------------------------------- */
+int tts_abi_version(void);
+const char* tts_last_error(void);
+/* number of kernels this library launched since the last reset (bench.py's gpu_launches) */
+int64_t tts_launch_count(void);
+void tts_launch_count_reset(void);
+
+/* ---- dense building blocks (prefill / teacher-forced path) ------------------------------- */
+
+/* Epilogue of tts_gemm_nt.  v = alpha*acc; v = v*scale[n]+shift[n]; v += bias[n]; act;
+ * v += residual[m][n]; rows at or beyond row_len[batch] are zeroed; then stored.
+ * Rows are grouped in batches of `rows_per_batch` (0 = one batch): row m -> (b, r);
+ * rows with r >= valid_rows are not stored; the output row is b*out_rows_per_batch + r +
+ * out_row_offset.  This is how the k=5 Conv1d of the Postnet runs as a GEMM over a
+ * zero-padded [B][T+4][C] activation buffer with overlapping rows (lda = C, K = 5C). */
+typedef struct TtsGemmEpilogue {
+  float alpha;                 /* 1.0f for none */
+  const float* scale;          /* [N] or NULL */
+  const float* shift;          /* [N] or NULL */
+  const float* bias;           /* [N] or NULL */
+  int32_t act;                 /* 0 none, 1 relu, 2 tanh */
+  const float* residual;       /* [M_out][ldr] or NULL (indexed by OUTPUT row) */
+  int32_t ldr;
+  const int32_t* row_len;      /* [n_batches] or NULL */
+  int32_t rows_per_batch;      /* 0 = M */
+  int32_t valid_rows;          /* 0 = rows_per_batch */
+  int32_t out_rows_per_batch;  /* 0 = rows_per_batch */
+  int32_t out_row_offset;
+  /* head-split store (cross K/V precompute, attention.py:66-68 + split_heads :6-15):
+   * if head_dim > 0 the N axis is [2][H][head_dim] and element (m=(b,s), n=(w,h,d)) goes to
+   * (w ? out_v : c)[((b*H + h)*head_rows + s)*head_dim + d]. */
+  int32_t head_dim;
+  int32_t n_heads;
+  int32_t head_rows;
+  float* out_v;
+} TtsGemmEpilogue;
+
+/* C[M,N] = epilogue(A[M,K] * W[N,K]^T).  Replaces every nn.Linear / nn.Conv1d call of the
+ * teacher-forced path: transformer/attention.py:43-47,63-68,119; modules.py:11-19;
+ * tacotron.py:50-52,56-64,78,85,112,114.  K % 4 == 0, lda % 4 == 0, ldw % 4 == 0. */
+int tts_gemm_nt(const float* A, int32_t lda, const float* W, int32_t ldw, float* C, int32_t ldc,
+                int32_t M, int32_t N, int32_t K, const TtsGemmEpilogue* epi, void* stream);
+
+/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta, eps = 1e-6 (modules.py:36,43,47,88,95,102,106).
+ * row_len/rows_per_batch (optional) zero rows at or beyond the length (common.py:51 impute). */
+int tts_layernorm(const float* x, float* y, const float* gamma, const float* beta, int32_t rows,
+                  int32_t channels, float eps, const int32_t* row_len, int32_t rows_per_batch,
+                  void* stream);
+
+/* Encoder prologue: out[b,s,:] = embed[ids[b,s],:] * (s < len[b]) + pe[s,:] * pe_scale
+ * (tacotron.py:34, modules.py:49-55, common.py:4-29).  pe is a [>=S][C] device table.
+ * ids == NULL: `embed` is the already embedded input [B*S][C] (vocab = B*S). */
+int tts_embed_pe(const int64_t* ids, const int32_t* lengths, const float* embed, const float* pe,
+                 const float* pe_scale, float* out, int32_t batch, int32_t seq, int32_t channels,
+                 int32_t vocab, void* stream);
+
+/* Decoder prologue (teacher forced): out[b,t,:] = (t==0 ? 0 : pre[b,t-1,:] * (t-1 < len[b])
+ * [* (t-1 != T-1 if leave_one)]) + pe[t,:] * pe_scale   (modules.py:114-118, tacotron.py:109-110) */
+int tts_shift_pe(const float* pre, const int32_t* lengths, const float* pe, const float* pe_scale,
+                 float* out, int32_t batch, int32_t frames, int32_t channels, void* stream);
+
+/* out[b, pad + t, :] = t < len[b] ? x[b, t, :] : 0 for t < T; the `pad` rows before and after
+ * each sequence are zeroed.  out is [B][T + 2*pad][C].  This is the `impute` + zero padding in
+ * front of the first Postnet convolution (tacotron.py:83-84, Conv1d padding=2). */
+int tts_pad_rows(const float* x, const int32_t* lengths, float* out, int32_t batch, int32_t frames,
+                 int32_t channels, int32_t pad, void* stream);
+
+/* Speaker / language conditioning written into the tail of the encoder memory:
+ * mem[b,s,off:off+E] = softsign(W2 * h + b2) broadcast over s (tacotron.py:21-31,36-43), with
+ * h = w1[ids[b], :] (speaker: nn.Embedding table [n][E], ids != NULL) or
+ * h = w1 * vec[b]   (language: bias-free Linear [E][vec_dim] on the one-hot vector, ids == NULL). */
+int tts_cond_embed(const float* vec, int32_t vec_dim, const int64_t* ids, const float* w1, const float* w2,
+                   const float* b2, int32_t emb, float* mem, int32_t batch, int32_t seq,
+                   int32_t mem_width, int32_t col_offset, void* stream);
+
+/* Multi-head scaled dot-product attention over full sequences (attention.py:72-122 minus the
+ * projections).  q/k/v are addressed as ptr[(b*rows + r)*ld + h*head_dim + d].
+ * mask: causal != 0 -> key j allowed iff j <= i (modules.py:112); key_len != NULL -> key j
+ * allowed iff j < key_len[b] (modules.py:50-52,109-111).  Masked logits are -1e20 like
+ * common.py:32.  ctx is [B][Tq][H*head_dim]; align (optional) is [B][H][Tq][Tk] (the
+ * reference returns the transposed view, attention.py:88).  head_dim in {32, 64, 96}. */
+int tts_attention(const float* q, int32_t ldq, const float* k, int32_t ldk, const float* v,
+                  int32_t ldv, float* ctx, float* align, int32_t batch, int32_t n_heads,
+                  int32_t tq, int32_t tk, int32_t head_dim, float q_scale, int32_t causal,
+                  const int32_t* key_len, void* stream);
+
+/* ---- autoregressive decode (the hot path) ------------------------------------------------ */
+
+typedef struct TtsDecLayerWeights {
+  const float* ln_self_g;   /* decoder.decoder.attn_layer_norms.{l}.weight   [D] */
+  const float* ln_self_b;
+  const float* w_qkv;       /* ...self_attentions.{l}.qkv_transform.weight   [3D][D] */
+  const float* w_self_out;  /* ...self_attentions.{l}.output_transform.weight [D][D] */
+  const float* ln_cross_g;  /* ...encdec_layer_norms.{l} */
+  const float* ln_cross_b;
+  const float* w_cross_q;   /* ...encdec_attentions.{l}.q_transform.weight   [D][D] */
+  const float* w_cross_kv;  /* ...encdec_attentions.{l}.kv_transform.weight  [2D][D] */
+  const float* w_cross_out; /* ...encdec_attentions.{l}.output_transform.weight */
+  const float* ln_ffn_g;    /* ...ffn_layer_norms.{l} */
+  const float* ln_ffn_b;
+  const float* w_ffn_in;    /* ...ffn_layers.{l}.input_layer.weight  [4D][D] */
+  const float* w_ffn_out;   /* ...ffn_layers.{l}.output_layer.weight [D][4D] */
+} TtsDecLayerWeights;
+
+typedef struct TtsDecoderWeights {
+  int32_t n_layers, d_model, n_heads, d_ffn, n_mels, prenet_hidden;
+  const float* prenet_w0;   /* decoder.prenet.dense0.weight [P][M] */
+  const float* prenet_b0;
+  const float* prenet_w1;   /* [P][P] */
+  const float* prenet_b1;
+  const float* prenet_w2;   /* dense_final.weight [D][P] */
+  const float* pe_scale;    /* decoder.decoder.pe_scale, device scalar */
+  const float* pe_table;    /* [t_max][D] sinusoid table (common.py:4-29), built once */
+  const float* ln_out_g;    /* decoder.decoder.output_layer_norm */
+  const float* ln_out_b;
+  const float* w_mel;       /* decoder.mel_net.weight [M][D] */
+  const float* w_stop;      /* decoder.stop_net.weight [1][D] */
+  const float* b_stop;      /* decoder.stop_net.bias [1] */
+  TtsDecLayerWeights layer[TTS_MAX_LAYERS];
+} TtsDecoderWeights;
+
+/* Per-utterance-batch decode state.  All buffers are caller-owned device memory.
+ * Cache layout: [L][B][H][rows][head_dim] with K and V separate, so that the K (or V) stream
+ * of one (layer, sample, head) is one contiguous run of rows*head_dim floats. */
+typedef struct TtsDecodeState {
+  int32_t batch, mem_len, t_max;
+  const float* memory;          /* [B][S][D]  encoder outputs (tacotron.py:44) */
+  const int32_t* input_lengths; /* [B] */
+  float* self_k;                /* [L][B][H][t_max][dh] */
+  float* self_v;
+  float* cross_k;               /* [L][B][H][S][dh] */
+  float* cross_v;
+  int32_t* lengths;             /* [B] target_lengths, starts at 1 (synthesize.py:23) */
+  uint8_t* finished;            /* [B] (synthesize.py:24) */
+  float* frames;                /* [B][t_max][M]  mel_pre (synthesize.py:43) */
+  float* stop_logits;           /* [B][t_max] */
+  float* align_self;            /* NULL or [L][B][H][t_max][t_max]  rows = query step */
+  float* align_cross;           /* NULL or [L][B][H][t_max][S] */
+  int32_t* step_counter;        /* device scalar: next step index t */
+  int32_t* n_unfinished;        /* device scalar, refreshed every step */
+  float* scratch;               /* tts_decode_scratch_bytes() bytes */
+} TtsDecodeState;
+
+size_t tts_decode_scratch_bytes(const TtsDecoderWeights* w, int32_t batch, int32_t mem_len,
+                                int32_t t_max);
+
+/* Once per utterance batch: cross_k/v[l] = split_heads(kv_transform_l(memory))
+ * (attention.py:66-68, recomputed EVERY step by the reference, synthesize.py:39-41), and
+ * reset lengths=1, finished=0, step_counter=0. */
+int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void* stream);
+
+/* Run `n_steps` cached decode steps starting at *step_counter (the body
+ * of the loop synthesize.py:35-45 with transformer/tacotron.py:107-116 inside).
+ *   prev_mel / prev_mel_stride: where step t reads frame t-1 from.  NULL = st->frames.
+ *   update_state: 1 = also perform synthesize.py:42-45 on device (finished |= stop>0,
+ *                 lengths += !finished); 0 = the caller does it (unchanged eval_batch).
+ *   impl: 0 = default (fused persistent kernel when available), 1 = per-phase kernels. */
+int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32_t n_steps,
+                     const float* prev_mel, int64_t prev_mel_stride, int32_t update_state,
+                     int32_t impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTS_B200_H */

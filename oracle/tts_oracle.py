@@ -77,11 +77,11 @@ class ModelConfig:
     @classmethod
     def tiny(cls) -> "ModelConfig":
         """A small model used by fast CPU tests (same structure, small widths)."""
-        return cls(vocab_size=300, embed_size=64, encoder_hidden=64, decoder_hidden=96,
-                   n_encoder_layer=2, n_decoder_layer=2, n_attention_head=4,
+        return cls(vocab_size=300, embed_size=64, encoder_hidden=64, decoder_hidden=128,
+                   n_encoder_layer=2, n_decoder_layer=2, n_attention_head=2,
                    prenet_hidden=32, postnet_hidden=48, n_postnet_layer=3,
-                   max_num_speaker=20, speaker_embedding_size=16,
-                   max_num_language=10, language_embedding_size=16,
+                   max_num_speaker=20, speaker_embedding_size=32,
+                   max_num_language=12, language_embedding_size=32,
                    max_generation_frames=64)
 
 

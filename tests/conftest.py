@@ -33,4 +33,4 @@ def full_params():
 def tiny_params():
     from oracle import tts_oracle as O
     cfg = O.ModelConfig.tiny()
-    return cfg, O.synth_params(cfg, seed=5)
+    return cfg, O.synth_params(cfg, seed=15)

@@ -125,7 +125,7 @@ def main():
 
     # ---- G4: tiny model — forward, loss, gradients (dropout 0, batch-stat BN), long AR ----------
     tcfg = O.ModelConfig.tiny()
-    tparams = O.synth_params(tcfg, seed=5)
+    tparams = O.synth_params(tcfg, seed=15)
     thp = hp_for(tcfg)
     thp.set_hparam("transformer_dropout_rate", 0.0)
     thp.set_hparam("decoder_dropout_rate", 0.0)
@@ -151,12 +151,12 @@ def main():
     save("tiny_forward_loss_grad.npz", **arrays)
 
     tparams_ar = dict(tparams)
-    tparams_ar["decoder.stop_net.bias"] = torch.tensor([-0.85])
+    tparams_ar["decoder.stop_net.bias"] = torch.tensor([-0.7])
     tmodel_ar = ref_model(tcfg, tparams_ar).eval()
     tb = O.synth_batch(tcfg, batch=5, text_len=24, n_frames=4, seed=7, ragged=True)
     res = run_eval_batch(tcfg, tmodel_ar, tb, 60)
     print("G4 generated_lengths", res["generated_lengths"])
-    save("tiny_ar.npz", stop_bias=np.float32(-0.85), max_frames=np.int64(60),
+    save("tiny_ar.npz", stop_bias=np.float32(-0.7), max_frames=np.int64(60),
          mel_pre=res["mel_pre"], mel_aft=res["mel_aft"],
          generated_lengths=np.asarray(res["generated_lengths"], dtype=np.int32),
          stop_margin=np.float64(stop_margin(tmodel_ar, tcfg, tparams_ar, tb, 60)))

@@ -1,0 +1,116 @@
+"""CPU-side checks of the drop-in boundary: the transformer/ mirror has the reference's classes,
+state-dict schema and seed-for-seed init; the C-ABI library loads and exports every symbol the
+header declares; and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as G
+    G.build()
+    return G
+
+
+def test_header_symbols_are_exported(built):
+    from tts_b200 import _native
+    header = open(os.path.join(ROOT, "include", "tts_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(tts_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(built.LIB)
+    for name in declared:
+        assert hasattr(lib, name), "libtts_b200.so does not export %s" % name
+    assert sorted(_native.exported_symbols()) == declared  # the ctypes binding covers the whole header
+    assert _native.load(check_device=False).tts_abi_version() == _native.ABI_VERSION
+
+
+def test_library_is_sm100a_with_packed_fp32_and_no_legacy_tensor_ops(built):
+    sass = subprocess.run(["cuobjdump", "-sass", built.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "FFMA2" in sass               # packed fp32 FMA, the Blackwell fp32 peak path
+    assert "HGMMA" not in sass           # no Hopper-only wgmma
+
+
+def test_struct_layouts_match_the_header(built):
+    """sizeof() of the ctypes mirrors equals what the C compiler lays out."""
+    from tts_b200 import _native
+    src = '#include <stdio.h>\n#include "tts_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(TtsGemmEpilogue),' \
+          ' sizeof(TtsDecLayerWeights), sizeof(TtsDecoderWeights), sizeof(TtsDecodeState));return 0;}'
+    exe = os.path.join(ROOT, "few-shot-transformer-tts_b200", "build", "sizes")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
+                   check=True)
+    sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
+    mine = [ctypes.sizeof(c) for c in (_native.GemmEpilogue, _native.DecLayerWeights, _native.DecoderWeights,
+                                       _native.DecodeState)]
+    assert sizes == mine
+
+
+def test_state_dict_schema_and_seeded_init_match_the_reference(built, golden_dir):
+    from tts_b200.config import default_hparams
+    from transformer import tacotron
+    ref = json.load(open(os.path.join(golden_dir, "ref_init_seed0.json")))
+    torch.manual_seed(0)                       # train.py:33
+    m = tacotron.Tacotron(default_hparams())   # train.py:118
+    tacotron.initialize_variables(m)           # train.py:119
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref["tensors"].keys())          # same names, same order
+    assert sum(p.numel() for p in m.parameters()) == ref["n_params"]
+    for k, v in sd.items():
+        want = ref["tensors"][k]
+        assert list(v.shape) == want["shape"], k
+        np.testing.assert_allclose(float(v.double().sum()), want["sum"], rtol=1e-9, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose(float(v.double().abs().sum()), want["abs"], rtol=1e-9, atol=1e-9, err_msg=k)
+        np.testing.assert_allclose([float(x) for x in v.flatten()[:3].double()], want["head"], rtol=0, atol=0)
+    for step, want in ref["lr_factor"].items():
+        assert tacotron.learning_rate_schedule(int(step), default_hparams()) == want
+
+
+def test_strict_load_of_oracle_weights_and_l2_selection(built, tiny_params):
+    from oracle import tts_oracle as O
+    from tts_b200.config import hparams_from
+    from transformer import tacotron
+    cfg, params = tiny_params
+    m = tacotron.Tacotron(hparams_from(cfg))
+    m.load_state_dict(params, strict=True)      # utils/checkpoint.py:41-44 loads strictly
+    batch = O.synth_batch(cfg, batch=3, text_len=20, n_frames=30, seed=6, ragged=True)
+    with torch.no_grad():
+        outs = O.tacotron_forward(params, cfg, batch)
+        want = O.compute_loss(params, cfg, batch["mel_targets"], batch["target_lengths"], outs)
+        got = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], outs, hparams_from(cfg))
+    assert set(got) == {"loss", "bef_loss", "aft_loss", "aft_losses", "mse_loss", "l2", "stop_loss"}
+    for k in got:
+        np.testing.assert_allclose(got[k].numpy(), want[k].numpy(), rtol=1e-6, atol=1e-8, err_msg=k)
+
+
+def test_no_cpu_fallback(built, tiny_params):
+    """On a CPU model every forward raises instead of silently computing somewhere else."""
+    from oracle import tts_oracle as O
+    from tts_b200.config import hparams_from
+    from transformer import tacotron
+    cfg, params = tiny_params
+    m = tacotron.Tacotron(hparams_from(cfg)).eval()
+    m.load_state_dict(params)
+    batch = O.synth_batch(cfg, batch=2, text_len=8, n_frames=6, seed=1)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        m(**{k: v for k, v in batch.items() if k != "names"})
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        m.postnet(batch["mel_targets"], batch["target_lengths"])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "few-shot-transformer-tts_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(base, f)

@@ -1,0 +1,428 @@
+"""GPU parity tests: every CUDA entry point and the whole decode / teacher-forced paths against
+the CPU oracle (oracle/tts_oracle.py) and the golden vectors produced by the reference itself.
+All calls go through the C ABI (ctypes) — there is no other implementation to fall back to.
+
+Tolerances (fp32 everywhere): per-kernel <= 1e-4 max-abs on O(1) values; whole-model mel frames
+<= 1e-3 max-abs (the north-star bound); generated lengths / stop indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import tts_oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+DEV = "cuda:0"
+KERNEL_TOL = 1e-4
+MEL_TOL = 1e-3
+
+
+def _dev(t):
+    return t.to(DEV)
+
+
+def _err(a, b):
+    return float((a.detach().cpu().double() - b.detach().cpu().double()).abs().max())
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    from tts_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def tiny_engine(tiny_params, ops):
+    from tts_b200.engine import TtsEngine
+    cfg, params = tiny_params
+    return TtsEngine.from_state_dict(params, cfg, DEV)
+
+
+@pytest.fixture(scope="module")
+def full_engine(full_params, ops):
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    return TtsEngine.from_state_dict(params, cfg, DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 1, 16), (7, 5, 80), (33, 81, 768), (130, 200, 256), (300, 1536, 512),
+                                   (2100, 768, 3072), (64, 64, 4), (129, 257, 36)])
+def test_gemm_nt_plain(ops, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    got = ops.linear(_dev(a), _dev(w))
+    assert _err(got, a @ w.t()) < KERNEL_TOL
+
+
+def test_gemm_nt_epilogues(ops):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 70, 96, 128
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    got = ops.linear(_dev(a), _dev(w), bias=_dev(bias), act=ops.ACT_RELU, residual=_dev(res), alpha=0.5)
+    want = torch.relu(0.5 * (a @ w.t()) + bias) + res
+    assert _err(got, want) < KERNEL_TOL
+    lens = torch.tensor([3, 10, 0, 7, 10, 1, 9], dtype=torch.int32)   # 7 batches of 10 rows
+    got = ops.linear(_dev(a), _dev(w), row_len=_dev(lens), rows_per_batch=10)
+    mask = (torch.arange(10)[None, :] < lens[:, None]).reshape(-1, 1)
+    assert _err(got, (a @ w.t()) * mask) < KERNEL_TOL
+
+
+def test_gemm_cross_kv_head_split(ops):
+    g = torch.Generator().manual_seed(4)
+    B, S, D, H = 3, 11, 128, 2
+    mem, w = torch.randn(B * S, D, generator=g), torch.randn(2 * D, D, generator=g) / D ** 0.5
+    ok = torch.zeros(B, H, S, D // H, device=DEV)
+    ov = torch.zeros_like(ok)
+    ops.cross_kv(_dev(mem), _dev(w), B, S, H, ok, ov)
+    kv = (mem @ w.t()).view(B, S, 2, H, D // H)
+    assert _err(ok, kv[:, :, 0].permute(0, 2, 1, 3)) < KERNEL_TOL
+    assert _err(ov, kv[:, :, 1].permute(0, 2, 1, 3)) < KERNEL_TOL
+
+
+@pytest.mark.parametrize("B,T,cin,cout,last", [(2, 9, 80, 48, False), (3, 33, 48, 80, True), (1, 1, 16, 16, False)])
+def test_conv5_as_gemm(ops, B, T, cin, cout, last):
+    g = torch.Generator().manual_seed(B + T)
+    x, w = torch.randn(B, T, cin, generator=g), torch.randn(cout, cin, 5, generator=g) / (5 * cin) ** 0.5
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    lens = torch.randint(1, T + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = T
+    mask = (torch.arange(T)[None, :] < lens[:, None])[:, :, None].float()
+    y = F.conv1d((x * mask).transpose(1, 2), w, padding=2).transpose(1, 2) * scale + shift
+    xpad = ops.pad_rows(_dev(x), _dev(lens), B, T)
+    assert _err(xpad[:, 2:T + 2], x * mask) == 0 and float(xpad[:, :2].abs().max()) == 0
+    wp = _dev(w.permute(0, 2, 1).reshape(cout, -1).contiguous())
+    if last:
+        res = torch.randn(B, T, cout, generator=g)
+        out = torch.empty(B, T, cout, device=DEV)
+        ops.conv5(xpad, wp, _dev(scale), _dev(shift), ops.ACT_NONE, None, B, T, out, False, residual=_dev(res))
+        assert _err(out, y + res) < KERNEL_TOL
+    else:
+        out = torch.zeros(B, T + 4, cout, device=DEV)
+        ops.conv5(xpad, wp, _dev(scale), _dev(shift), ops.ACT_TANH, _dev(lens), B, T, out, True)
+        assert _err(out[:, 2:T + 2], torch.tanh(y) * mask) < KERNEL_TOL
+        assert float(out[:, :2].abs().max()) == 0 and float(out[:, T + 2:].abs().max()) == 0
+
+
+def test_layernorm_and_prologues(ops):
+    g = torch.Generator().manual_seed(5)
+    rows, C = 37, 768
+    x, gam, bet = torch.randn(rows, C, generator=g) * 3 + 1, torch.randn(C, generator=g), torch.randn(C, generator=g)
+    got = ops.layernorm(_dev(x), _dev(gam), _dev(bet))
+    assert _err(got, F.layer_norm(x, (C,), gam, bet, 1e-6)) < KERNEL_TOL
+    # embed + mask + PE, and shift-right + mask + PE
+    from tts_b200.engine import sinusoid_table
+    B, S, V, E = 3, 13, 50, 64
+    ids = torch.randint(0, V, (B, S), generator=g)
+    lens = torch.tensor([13, 5, 1], dtype=torch.int32)
+    table, scale = torch.randn(V, E, generator=g), torch.tensor(1.3)
+    pe = sinusoid_table(32, E)
+    assert _err(pe[:S], O.sinusoid_table(S, E)) == 0
+    got = ops.embed_pe(_dev(ids), _dev(lens), _dev(table), _dev(pe), _dev(scale), B, S)
+    want = table[ids] * (torch.arange(S)[None, :] < lens[:, None])[..., None] + pe[:S] * scale
+    assert _err(got.view(B, S, E), want) < 1e-6
+    pre = torch.randn(B * S, E, generator=g)
+    got = ops.shift_pe(_dev(pre), _dev(lens), _dev(pe), _dev(scale), B, S)
+    p3 = pre.view(B, S, E) * (torch.arange(S)[None, :] < lens[:, None])[..., None]
+    want = torch.cat([torch.zeros(B, 1, E), p3[:, :-1]], 1) + pe[:S] * scale
+    assert _err(got.view(B, S, E), want) < 1e-6
+
+
+@pytest.mark.parametrize("dh,H,B,Tq,Tk,mode", [(32, 2, 2, 5, 5, "causal"), (64, 2, 3, 70, 70, "causal"),
+                                               (96, 8, 2, 130, 41, "keys"), (64, 4, 2, 33, 33, "keys"),
+                                               (96, 2, 1, 1, 200, "none"), (32, 1, 2, 65, 64, "keys")])
+def test_attention_full_sequence(ops, dh, H, B, Tq, Tk, mode):
+    g = torch.Generator().manual_seed(dh + Tq)
+    C = H * dh
+    q, k, v = (torch.randn(B, t, C, generator=g) for t in (Tq, Tk, Tk))
+    klen = None
+    bias = None
+    if mode == "causal":
+        bias = torch.triu(torch.ones(Tq, Tk), 1)[None, None] * O.NEG_BIAS
+    elif mode == "keys":
+        klen = torch.randint(1, Tk + 1, (B,), generator=g, dtype=torch.int32)
+        klen[0] = Tk
+        if B > 1:
+            klen[1] = 0   # fully masked row: the reference's softmax over all -1e20 is uniform
+        bias = ((torch.arange(Tk)[None, :] >= klen[:, None]).float() * O.NEG_BIAS)[:, None, None, :]
+    qh, kh, vh = (O._heads(t, H) for t in (q, k, v))
+    logits = (qh * dh ** -0.5) @ kh.transpose(2, 3)
+    if bias is not None:
+        logits = logits + bias
+    wts = torch.softmax(logits, -1)
+    want = (wts @ vh).transpose(1, 2).reshape(B, Tq, C)
+    qd, kd, vd = _dev(q), _dev(k), _dev(v)
+    ctx, align = ops.attention(qd.data_ptr(), C, kd.data_ptr(), C, vd.data_ptr(), C, B, H, Tq, Tk, dh,
+                               mode == "causal", None if klen is None else _dev(klen), True, torch.device(DEV))
+    assert _err(ctx.view(B, Tq, C), want) < KERNEL_TOL
+    assert _err(align, wts) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# model paths vs oracle and golden (tiny model: exercises every mask / ragged edge quickly)
+# ---------------------------------------------------------------------------------------------
+def test_tiny_encoder_and_teacher_forced_forward(tiny_engine, tiny_params, golden_dir):
+    cfg, params = tiny_params
+    z = np.load(os.path.join(golden_dir, "tiny_forward_loss_grad.npz"))
+    batch = O.synth_batch(cfg, batch=3, text_len=20, n_frames=30, seed=6, ragged=True)
+    want = O.tacotron_forward(params, cfg, batch)
+    got = tiny_engine.forward(batch)
+    assert _err(got["memory"], want["memory"]) < KERNEL_TOL
+    for k in ("mel_bef", "mel_aft", "stop_logits"):
+        assert _err(got[k], want[k]) < KERNEL_TOL, k
+        assert _err(got[k], torch.from_numpy(z[k])) < MEL_TOL, k          # the reference's own output
+    for kind in ("self", "encdec"):
+        for a, b in zip(got["alignments"][kind], want["alignments"][kind]):
+            assert a.shape == b.shape and _err(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("impl", [1, 2, 0])
+def test_tiny_autoregressive_vs_golden(tiny_engine, tiny_params, golden_dir, impl):
+    cfg, params = tiny_params
+    z = np.load(os.path.join(golden_dir, "tiny_ar.npz"))
+    from tts_b200.engine import TtsEngine
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([float(z["stop_bias"])])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=5, text_len=24, n_frames=4, seed=7, ragged=True)
+    T = int(z["max_frames"])
+    got = eng.generate(batch, max_frames=T, record_align="all", chunk=7, impl=impl)
+    want = O.eval_batch_cached(p, cfg, batch, T)
+    assert got["generated_lengths"].cpu().tolist() == z["generated_lengths"].tolist()     # bit-exact stop indices
+    assert got["generated_lengths"].dtype == torch.int32
+    assert _err(got["stop_logits"], want["stop_logits"]) < 2e-4
+    assert _err(got["mel_pre"], torch.from_numpy(z["mel_pre"])) < MEL_TOL
+    assert _err(got["mel_aft"], torch.from_numpy(z["mel_aft"])) < MEL_TOL
+    assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4
+    # cache contents: the K/V rows written step by step equal the oracle's
+    sess = got["session"]
+    t = want["self_k"][0].shape[2]
+    for l in range(cfg.n_decoder_layer):
+        assert _err(sess.self_k[l][:, :, :t], want["self_k"][l]) < 2e-4
+        assert _err(sess.cross_v[l], want["cross_v"][l]) < KERNEL_TOL
+    # attention rows recorded per step are the softmax rows of a teacher-forced pass over the result
+    tf = O.decoder_forward(p, cfg, want["memory"], batch["input_lengths"],
+                           torch.cat([want["mel_pre"], torch.zeros(5, 1, cfg.num_mels)], 1)[:, :T],
+                           want["generated_lengths"], leave_one=True)
+    # (only rows of still-running samples are comparable: the loop's lengths change over time)
+    b = int(np.argmax(z["generated_lengths"]))
+    a_got = got["alignments"]["encdec"][-1][b].cpu()
+    assert _err(a_got, tf[2]["encdec"][-1][b]) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size model
+# ---------------------------------------------------------------------------------------------
+def test_cfg1_forward_vs_reference_golden(full_engine, full_params, golden_dir):
+    """BASELINE config 0: B=1, 120-byte text -> 400 frames, teacher forced."""
+    cfg, _ = full_params
+    z = np.load(os.path.join(golden_dir, "cfg1_forward.npz"))
+    batch = O.synth_batch(cfg, batch=1, text_len=122, n_frames=400, seed=1)
+    got = full_engine.forward(batch)
+    errs = {k: _err(got[k], torch.from_numpy(z[k])) for k in ("mel_bef", "mel_aft", "stop_logits")}
+    print("cfg1 max-abs vs reference:", errs)
+    assert max(errs.values()) < MEL_TOL
+    a = got["alignments"]
+    assert _err(a["self"][0][0, 0, ::8, ::8], torch.from_numpy(z["align_self_l0_h0"])) < 1e-5
+    assert _err(a["encdec"][5][0, 7, :, ::8], torch.from_numpy(z["align_encdec_l5_h7"])) < 1e-5
+
+
+def test_full_ragged_forward_vs_reference_golden(full_engine, full_params, golden_dir):
+    cfg, _ = full_params
+    z = np.load(os.path.join(golden_dir, "full_ragged_forward.npz"))
+    batch = O.synth_batch(cfg, batch=3, text_len=40, n_frames=64, seed=2, ragged=True)
+    got = full_engine.forward(batch, want_align=False)
+    for k in ("mel_bef", "mel_aft", "stop_logits"):
+        assert _err(got[k], torch.from_numpy(z[k])) < MEL_TOL, k
+
+
+@pytest.mark.parametrize("impl", [1, 2, 0])
+def test_full_autoregressive_vs_reference_golden(full_params, golden_dir, ops, impl):
+    """The reference's own eval_batch output (staggered stops) on the full-size model."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    z = np.load(os.path.join(golden_dir, "full_ar.npz"))
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([float(z["stop_bias"])])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=4, text_len=48, n_frames=4, seed=3, ragged=True)
+    got = eng.generate(batch, max_frames=int(z["max_frames"]), record_align="all", chunk=16, impl=impl)
+    assert got["generated_lengths"].cpu().tolist() == z["generated_lengths"].tolist()
+    e1, e2 = _err(got["mel_pre"], torch.from_numpy(z["mel_pre"])), _err(got["mel_aft"], torch.from_numpy(z["mel_aft"]))
+    print("full AR max-abs vs reference: mel_pre %.2e mel_aft %.2e (reference stop margin %.3f)" % (e1, e2, float(z["stop_margin"])))
+    assert e1 < MEL_TOL and e2 < MEL_TOL
+    T = got["mel_pre"].shape[1]
+    assert _err(got["alignments"]["encdec"][5][:, :, :, T - 1], torch.from_numpy(z["align_encdec_l5"])) < 1e-4
+    assert _err(got["alignments"]["self"][0][:, :, :, T - 1], torch.from_numpy(z["align_self_l0"])) < 1e-4
+
+
+@pytest.mark.parametrize("B,split_note", [(1, "split-KV over 32 CTAs per head"), (3, "split-KV"), (32, "one CTA per head")])
+def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_note):
+    """Decode at several batch sizes (different split-KV factors), 24 steps, vs the cached oracle."""
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    from tts_b200.engine import TtsEngine
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=B, text_len=37, n_frames=4, seed=11, ragged=B > 1)
+    want = O.eval_batch_cached(p, cfg, batch, 24)
+    got = eng.generate(batch, max_frames=24, record_align="encdec", chunk=24)
+    assert got["generated_lengths"].cpu().tolist() == want["generated_lengths"].tolist() == [25] * B
+    assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4
+    assert _err(got["mel_aft"], want["mel_aft"]) < 2e-4
+
+
+def test_decode_properties_at_baseline_shape(full_params, ops):
+    """BASELINE config 1 shape (B=32, S=258): size-independent properties — determinism, batch
+    permutation equivariance, impl agreement, zero frames after a stop, session reuse."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-5.0])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=32, text_len=258, n_frames=4, seed=21)
+    mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
+    T = 48
+    a = eng.generate(batch, max_frames=T, record_align="none", memory=mem)
+    b = eng.generate(batch, max_frames=T, record_align="none", memory=mem, session=a["session"])   # reuse buffers
+    assert torch.equal(a["mel_pre"], b["mel_pre"]) and torch.equal(a["generated_lengths"], b["generated_lengths"])
+    c = eng.generate(batch, max_frames=T, record_align="none", memory=mem, impl=1)
+    assert _err(a["mel_pre"], c["mel_pre"]) < 1e-4 and torch.equal(a["generated_lengths"], c["generated_lengths"])
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(0))
+    pb = {k: (v[perm] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    d = eng.generate(pb, max_frames=T, record_align="none", memory=mem[perm.to(DEV)].contiguous())
+    assert _err(d["mel_pre"], a["mel_pre"][perm.to(DEV)]) < 1e-4
+    assert d["generated_lengths"].cpu().tolist() == a["generated_lengths"].cpu()[perm].tolist()
+    lens = a["generated_lengths"].cpu()
+    assert len(set(lens.tolist())) > 1, "expected staggered stops at this bias"
+    for i in range(32):   # frames at or beyond the frozen length are exactly zero (modules.py:144)
+        assert float(a["mel_pre"][i, int(lens[i]):].abs().max() if int(lens[i]) < a["mel_pre"].shape[1] else 0.0) == 0.0
+    # and one oracle comparison at this shape, on the first 6 steps
+    want = O.eval_batch_cached(p, cfg, batch, 6)
+    assert _err(a["mel_pre"][:, :6], want["mel_pre"][:, :6]) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# the drop-in nn.Module API, driven the way the reference's synthesize.py / train.py drive it
+# ---------------------------------------------------------------------------------------------
+def _eval_loop_like_synthesize(model, data, max_frames, num_mels):
+    """The loop of the reference's synthesize.eval_batch (synthesize.py:17-72), restated here because the
+    reference checkout does not exist on the GPU box: same calls, same bookkeeping, same outputs."""
+    with torch.no_grad():
+        device = data["inputs"].device
+        n = data["inputs"].shape[0]
+        target_lengths = torch.ones([n], dtype=torch.int32, device=device)
+        finished = torch.zeros([n], dtype=torch.bool, device=device)
+        mels = torch.zeros([n, 0, num_mels], dtype=torch.float32, device=device)
+        enc = model.encoder(data["inputs"], data["input_lengths"], data["input_spk_ids"], data["input_language_vecs"])
+        n_calls = 0
+        while not torch.all(finished) and mels.shape[1] < max_frames:
+            dec_in = torch.cat([mels, torch.zeros([n, 1, num_mels], device=device)], dim=1)
+            mel_bef, stop_logits, align = model.decoder(enc, data["input_lengths"], dec_in, target_lengths,
+                                                        leave_one=True)
+            stop = stop_logits[:, -1] > 0
+            mels = torch.cat([mels, mel_bef[:, -1:]], dim=1)
+            finished = torch.logical_or(finished, stop)
+            target_lengths = torch.where(finished, target_lengths, target_lengths + 1)
+            n_calls += 1
+        mel_aft = mels + model.postnet(mels, target_lengths)
+        return {"mel_pre": mels, "mel_aft": mel_aft, "alignments": align, "generated_lengths": target_lengths,
+                "n_calls": n_calls}
+
+
+def test_module_api_unchanged_synthesis_loop(tiny_params, golden_dir, ops):
+    from tts_b200.config import hparams_from
+    from transformer import tacotron
+    cfg, params = tiny_params
+    z = np.load(os.path.join(golden_dir, "tiny_ar.npz"))
+    hp = hparams_from(cfg)
+    hp.max_generation_frames = int(z["max_frames"])
+    m = tacotron.Tacotron(hp)
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([float(z["stop_bias"])])
+    m.load_state_dict(p, strict=True)
+    m.to(DEV).eval()
+    batch = {k: (_dev(v) if torch.is_tensor(v) else v)
+             for k, v in O.synth_batch(cfg, batch=5, text_len=24, n_frames=4, seed=7, ragged=True).items()}
+    out = _eval_loop_like_synthesize(m, batch, hp.max_generation_frames, cfg.num_mels)
+    assert out["generated_lengths"].cpu().tolist() == z["generated_lengths"].tolist()
+    assert _err(out["mel_pre"], torch.from_numpy(z["mel_pre"])) < MEL_TOL
+    assert _err(out["mel_aft"], torch.from_numpy(z["mel_aft"])) < MEL_TOL
+    T = out["mel_pre"].shape[1]
+    assert out["alignments"]["self"][0].shape == (5, cfg.n_attention_head, T, T)
+    assert out["alignments"]["encdec"][0].shape == (5, cfg.n_attention_head, 24, T)
+    # the incremental path really was used: one cached step per call
+    assert m.decoder._inc is not None and m.decoder._inc["sess"].t == out["n_calls"]
+    # a second utterance batch through the same model restarts the cache and reproduces the result
+    out2 = _eval_loop_like_synthesize(m, batch, hp.max_generation_frames, cfg.num_mels)
+    assert torch.equal(out2["mel_pre"], out["mel_pre"])
+    # teacher-forced call through the same module (train.py:171 signature), eval mode
+    tb = {k: (_dev(v) if torch.is_tensor(v) else v)
+          for k, v in O.synth_batch(cfg, batch=3, text_len=20, n_frames=30, seed=6, ragged=True).items()}
+    with torch.no_grad():
+        o = m(**tb)
+    zf = np.load(os.path.join(golden_dir, "tiny_forward_loss_grad.npz"))
+    p0 = dict(params)
+    want = O.tacotron_forward(p, cfg, {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in tb.items()})
+    for k in ("mel_bef", "mel_aft", "stop_logits"):
+        assert _err(o[k], want[k]) < KERNEL_TOL, k
+    losses = tacotron.compute_loss(m, tb["mel_targets"], tb["target_lengths"], o, hp)
+    assert set(losses) == {"loss", "bef_loss", "aft_loss", "aft_losses", "mse_loss", "l2", "stop_loss"}
+    del p0, zf
+
+
+def test_module_api_submodules(tiny_params, ops):
+    """MultiheadAttention / FFNLayer / DecoderPrenet / Postnet / TransformerEncoder called directly."""
+    from tts_b200.config import hparams_from
+    from transformer import attention, common, modules, tacotron
+    cfg, params = tiny_params
+    hp = hparams_from(cfg)
+    g = torch.Generator().manual_seed(9)
+    mha = attention.MultiheadAttention(128, 128, True, 2).to(DEV).eval()
+    x = torch.randn(2, 9, 128, generator=g)
+    sd = {k: v.cpu() for k, v in mha.state_dict().items()}
+    bias = common.attention_bias(9, "causal")
+    with torch.no_grad():
+        out = mha(_dev(x), None, _dev(bias))
+    want, al = O.attention({"a." + k: v for k, v in sd.items()}, "a", x, None, bias, 2)
+    assert _err(out["outputs"], want) < KERNEL_TOL and _err(out["align"], al) < 1e-5
+    cross = attention.MultiheadAttention(128, 128, False, 2).to(DEV).eval()
+    mem = torch.randn(2, 6, 128, generator=g)
+    mask = torch.arange(6)[None, :] < torch.tensor([6, 2])[:, None]
+    bias = common.attention_bias(mask, "masking")
+    with torch.no_grad():
+        out = cross(_dev(x), _dev(mem), _dev(bias))
+    sd = {"a." + k: v.cpu() for k, v in cross.state_dict().items()}
+    want, al = O.attention(sd, "a", x, mem, bias, 2)
+    assert _err(out["outputs"], want) < KERNEL_TOL and _err(out["align"], al) < 1e-5
+    ffn = modules.FFNLayer(128, 512, 128).to(DEV).eval()
+    with torch.no_grad():
+        y = ffn(_dev(x))
+    sd = {"f." + k: v.cpu() for k, v in ffn.state_dict().items()}
+    assert _err(y, O.ffn(sd, "f", x)) < KERNEL_TOL
+    post = tacotron.Postnet(hp)
+    post.load_state_dict({k[len("postnet."):]: v for k, v in params.items() if k.startswith("postnet.")})
+    post.to(DEV).eval()
+    mel = torch.randn(3, 17, 80, generator=g)
+    lens = torch.tensor([17, 4, 9])
+    with torch.no_grad():
+        r = post(_dev(mel), _dev(lens))
+    assert _err(r, O.postnet_forward(params, cfg, mel, lens)) < KERNEL_TOL
+    enc = tacotron.Encoder(hp)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in params.items() if k.startswith("encoder.")})
+    enc.to(DEV).eval()
+    b = O.synth_batch(cfg, batch=3, text_len=15, n_frames=4, seed=2, ragged=True)
+    with torch.no_grad():
+        memo = enc(_dev(b["inputs"]), _dev(b["input_lengths"]), _dev(b["input_spk_ids"]), _dev(b["input_language_vecs"]))
+        emb = enc.encoder(enc.embed.weight[_dev(b["inputs"])], _dev(b["input_lengths"]))
+    want = O.encoder_forward(params, cfg, b["inputs"], b["input_lengths"], b["input_spk_ids"], b["input_language_vecs"])
+    assert _err(memo, want) < KERNEL_TOL
+    assert _err(emb, want[:, :, :cfg.encoder_hidden]) < KERNEL_TOL
