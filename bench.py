@@ -331,7 +331,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--chunk", type=int, default=50, help="decode steps per launch / host poll")
     ap.add_argument("--decode-impl", type=int, default=0, help="0 default, 1 per-phase kernels, 2 CUDA graph, 3 fused")
-    ap.add_argument("--ref-horizon", type=int, default=6, help="frames of the CPU reference sample")
+    ap.add_argument("--ref-horizon", type=int, default=40, help="frames of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -55,11 +55,16 @@ static int get_step_graph(const TtsDecoderWeights* w, const TtsDecodeState* st, 
       *kernels = e.kernels;
       return 0;
     }
+  // capture on a private stream: the caller's stream may be the legacy default stream, which
+  // cannot be captured; the instantiated graph is then launched on the caller's stream
+  static cudaStream_t cap = nullptr;
+  if (cap == nullptr) TTS_CHECK_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  (void)s;
   const long long before = g_launches.load();
-  TTS_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_step_phases(w, st, update_state, s);
+  TTS_CHECK_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_step_phases(w, st, update_state, cap);
   cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
   const int n_kernels = (int)(g_launches.load() - before);
   g_launches.store(before);  // captured launches are counted when replayed
   if (rc != 0) {
