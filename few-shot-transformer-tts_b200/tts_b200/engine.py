@@ -366,7 +366,10 @@ class TtsEngine:
             n = min(chunk, max_frames - done)
             sess.step(n, update_state=True, impl=impl)
             done += n
-            if int(sess.counters[1].item()) == 0:  # one 4-byte D2H per chunk instead of one per frame
+            left = int(sess.counters[1].item())  # one 4-byte D2H per chunk instead of one per frame
+            if left < 0:
+                raise RuntimeError("tts_b200: the fused decode kernel reported a grid-barrier timeout")
+            if left == 0:
                 all_finished = True
                 break
         lengths = sess.lengths.clone()
