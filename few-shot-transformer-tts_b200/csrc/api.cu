@@ -31,6 +31,7 @@ int launch_fused_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int
                        cudaStream_t s);
 size_t fused_scratch_floats(const TtsDecoderWeights* w, int B);
 bool fused_supported(const TtsDecoderWeights* w, const TtsDecodeState* st);
+int fused_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries);
 
 // ---- CUDA graph cache: one captured step per (weights, state, flags) -------------------------
 struct GraphEntry {
@@ -150,6 +151,12 @@ extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState
     if (rc) return rc;
   }
   return decode_reset(st, s);
+}
+
+extern "C" int tts_decode_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, int64_t* out_host,
+                                  int32_t max_entries) {
+  TTS_REQUIRE(w && st && out_host && max_entries > 0, "decode_profile: bad arguments");
+  return fused_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
 }
 
 extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32_t n_steps,

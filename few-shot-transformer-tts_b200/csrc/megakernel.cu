@@ -1,17 +1,17 @@
 // Fused persistent decode kernel (impl 3): ONE cooperative launch runs `n_steps` whole decode
 // steps.  One CTA per SM stays resident; the phases of a step are separated
-// by a software grid barrier instead of kernel launches, so a step costs ~52 barriers instead of
-// ~65 launches and every phase starts with its operands' addresses already known.
+// by a software grid barrier instead of kernel launches.  All bulk data movement is done by the
+// TMA engine (1-D cp.async.bulk, completion on mbarriers), so no phase has a chain of dependent
+// global loads:
 //
-//   GEMM phases   weight rows are split evenly over the CTAs; each CTA stages the <=32 batch rows
-//                 of the activation in shared memory (cp.async, LayerNorm applied in place from
-//                 registers), streams its weight rows once from HBM/L2 with 128-bit no-allocate
-//                 loads and multiplies with packed FFMA2.
-//   attention     the (sample, head, key) space of a phase is flattened and cut into equal
-//                 contiguous spans, one per CTA (perfect balance for any batch size / step); a
-//                 span yields at most I/G+2 partial (max, sum, weighted V) records, which the
-//                 NEXT phase (the output projection) merges while staging its input, so there is
-//                 no separate combine phase.
+//   GEMM phases   weight rows are split evenly over the CTAs.  A CTA's slice of the weight matrix
+//                 is ONE contiguous range: a single bulk copy brings it into shared memory, issued
+//                 while the CTA is still waiting on the grid barrier (weights never change).  The
+//                 <=32 activation rows arrive as 32 bulk row copies after the barrier; LayerNorm is
+//                 applied in place from registers; products run on packed FFMA2 from shared memory.
+//   attention     every warp streams its share of the K/V rows of a (sample, head) through a private
+//                 ring of bulk-copied tiles (K and V tile per slot, 3 slots in flight per warp) and
+//                 keeps an online-softmax state; warps are merged once per (sample, head).
 //   state         every CTA keeps an identical replica of lengths/finished in shared memory and
 //                 applies synthesize.py:42-45 itself after the final projection; CTA 0 publishes it.
 //
@@ -27,12 +27,18 @@ namespace fused {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
-constexpr int kKC = 768;       // K slice of the activation resident in shared memory
-constexpr int kXLd = kKC + 4;  // row stride = 4 (mod 32) words -> conflict-free 128-bit reads 4 rows apart
-constexpr int kRowBlk = 32;    // batch rows per activation tile
-constexpr int kPass = 8;       // weight rows per register pass
+constexpr int kKC = 768;        // K slice of the activation staged in shared memory at a time
+constexpr int kChunksPerWarp = kKC / 16 / kWarps;  // 16-float chunks of a slice owned by one warp (6)
+constexpr int kRowBlk = 32;     // batch rows per activation tile
+constexpr int kPass = 8;        // weight rows per register pass
+constexpr int kXFloats = (kRowBlk + 2) * (kKC + 4);     // 32 activation rows + LayerNorm gamma and beta
+constexpr int kWFloats = 19456;                         // 76 KB: <= 6 rows of K=3072, <= 25 rows of K=768
+constexpr int kTK = 8;          // keys per K/V ring tile
+constexpr int kSlots = 3;       // ring slots per warp
 constexpr int kMaxBatch = 1024;
+constexpr int kMaxSplit = 32;
 constexpr long long kSpinLimit = 1LL << 22;
+constexpr int kProfPhases = 160;
 
 enum Mode { kPlain = 0, kQkv = 1, kPrenetOut = 2, kFinal = 3 };
 enum XSrc { kXPlain = 0, kXFrames = 1, kXCombine = 2 };
@@ -40,10 +46,11 @@ enum XSrc { kXPlain = 0, kXFrames = 1, kXCombine = 2 };
 struct Args {
   TtsDecoderWeights w;
   TtsDecodeState st;
-  float *x, *q, *hid, *p0, *p1, *part;
-  int max_seg;
+  float *x, *q, *ctx, *hid, *p0, *p1, *part;
+  int n_split;          // K/V splits per (sample, head): 1 when B*H >= #CTAs
   unsigned* bar;
   int* err;
+  long long* prof;      // [kProfPhases][8] SM clock stamps of CTA 0 for the last step run (diagnostics)
   int n_steps, update_state;
 };
 
@@ -54,17 +61,113 @@ struct Gemm {
   const float* bias; int relu; int mode;
   float* Y; long long ldy; const float* R; long long ldr; float out_scale;
   float* kcache; float* vcache;
-  int comb_keys;                       // kXCombine: keys of the attention phase being merged
-  float* align; long long align_bh_stride; int align_row_len;  // kXCombine: rows to normalise (or null)
+  int comb_keys;
+  float* align; long long align_bh_stride; int align_row_len;
+};
+
+struct Attn {
+  const float* kc; const float* vc; int rows_alloc; int n_keys; const int32_t* key_len;
+  float* align; long long align_bh_stride; int align_row_len;
+};
+
+struct Phase {
+  int kind;  // 0 gemm, 1 gemm with LayerNorm prologue, 2 attention
+  Gemm g;
+  Attn at;
 };
 
 struct Smem {
-  float* xs[2];   // [32][kXLd] each
-  float* red;     // [8][8][32]
-  float* ml;      // [32*H][2]  merged (max, 1/sum) of the row block's attention items
+  float* xs;      // activation tile(s)
+  float* wb;      // weight slice
+  float* ring;    // K/V rings (aliases xs + wb during attention phases)
+  float* red;     // [8][8][32] GEMM cross-warp reduction / attention warp records
+  float* ml;      // [32*H][2]
   int* len;       // [B]
   int* fin;       // [B]
+  uint64_t* wfull;     // 1
+  uint64_t* xfull;     // 2
+  uint64_t* rfull;     // [8][kSlots]
 };
+
+struct Track {        // per-call working state of a phase (registers; never passed by reference)
+  unsigned w_par;              // parity of the weight barrier for this phase
+  unsigned issued, consumed;   // K/V ring tiles requested / used by this warp since the kernel started
+  long long* prof;             // stamp row of the current phase (CTA 0, thread 0) or null
+};
+
+__device__ __forceinline__ void stamp(const Track& tk, int k) {
+  if (tk.prof != nullptr) tk.prof[k] = clock64();
+}
+
+__device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
+  Smem sm;
+  sm.xs = base;
+  sm.wb = sm.xs + kXFloats;
+  sm.ring = base;
+  sm.red = sm.wb + kWFloats;
+  sm.ml = sm.red + kWarps * kPass * 32;
+  sm.wfull = reinterpret_cast<uint64_t*>(sm.ml + 2 * kRowBlk * a.w.n_heads);
+  sm.xfull = sm.wfull + 1;
+  sm.rfull = sm.wfull + 3;
+  sm.len = reinterpret_cast<int*>(sm.rfull + kWarps * kSlots);
+  sm.fin = sm.len + a.st.batch;
+  return sm;
+}
+
+// ---- mbarrier / bulk copy primitives ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, int* err) {
+  long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    ++spins;
+    if ((spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(err) != 0)) {
+      atomicExch(err, 2);  // never hang the GPU
+      break;
+    }
+  }
+}
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// 128-bit loads the compiler is free to hoist and batch (the asm-volatile helpers of common.cuh pin the
+// program order, which exposed the full shared-memory latency per weight row)
+__device__ __forceinline__ f32x4 ld4s(const float* p) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f32x4 r;
+  r.lo = pack2(v.x, v.y);
+  r.hi = pack2(v.z, v.w);
+  return r;
+}
+__device__ __forceinline__ f32x4 ld4cg(const float* p) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  f32x4 r;
+  r.lo = pack2(v.x, v.y);
+  r.hi = pack2(v.z, v.w);
+  return r;
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 // ---- grid barrier -----------------------------------------------------------------------------
 struct GridBar {
@@ -74,87 +177,92 @@ struct GridBar {
 };
 
 __device__ __forceinline__ void bar_arrive(GridBar& gb) {
+  fence_proxy_async();  // this thread's global writes -> visible to other CTAs' bulk (async-proxy) reads
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(gb.ctr, 1u);
-  }
+  if (threadIdx.x == 0)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
   gb.epoch++;
 }
 
 __device__ __forceinline__ void bar_wait(GridBar& gb) {
   if (threadIdx.x == 0) {
     const unsigned target = gb.epoch * gb.n;
-    if (*reinterpret_cast<volatile int*>(gb.err) == 0) {
-      long long spins = 0;
-      while (true) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
-        if (static_cast<int>(v - target) >= 0) break;
-        if (++spins > kSpinLimit) {  // never hang the GPU: flag the error and fall through
-          atomicExch(gb.err, 1);
-          break;
-        }
+    long long spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      if (static_cast<int>(v - target) >= 0) break;
+      ++spins;
+      if ((spins & 1023) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(gb.err) != 0)) {
+        atomicExch(gb.err, 1);
+        break;
       }
     }
     __threadfence();
+    fence_proxy_async();
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ void grid_sync(GridBar& gb) {
-  bar_arrive(gb);
-  bar_wait(gb);
+// ---- GEMM phase -------------------------------------------------------------------------------------
+__device__ __forceinline__ void slice_rows(const Gemm& g, int& n_lo, int& n_hi) {
+  const int G = gridDim.x, c = blockIdx.x;
+  n_lo = (int)(((long long)c * g.N) / G);
+  n_hi = (int)(((long long)(c + 1) * g.N) / G);
 }
 
-// ---- async copy helpers -------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// ---- activation staging -------------------------------------------------------------------------
-// rows b0..b0+31 (zero beyond B), columns k0..k0+kc of a [B][ldx] activation -> Xs (async)
-__device__ __forceinline__ void stage_plain(float* Xs, const float* X, long long ldx, int B, int b0, int k0, int kc,
-                                            bool zero_all) {
-  const int f4 = kc >> 2;
-  for (int i = threadIdx.x; i < kRowBlk * f4; i += kThreads) {
-    const int r = i / f4, c = (i - r * f4) << 2;
-    float* dst = Xs + r * kXLd + c;
-    if (!zero_all && b0 + r < B) cp_async16(dst, X + (size_t)(b0 + r) * ldx + k0 + c);
-    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+// one thread: bring this CTA's weight rows [n_lo, n_hi) x K into sm.wb (row r at wb + r*K)
+__device__ __forceinline__ void issue_weights(const Gemm& g, const Smem& sm) {
+  int n_lo, n_hi;
+  slice_rows(g, n_lo, n_hi);
+  if (n_hi <= n_lo) return;
+  const unsigned row_bytes = (unsigned)g.K * 4u;
+  mbar_expect_tx(sm.wfull, (unsigned)(n_hi - n_lo) * row_bytes);
+  const int a_hi = min(n_hi, g.n_w1);
+  if (n_lo < a_hi) bulk_g2s(sm.wb, g.W + (size_t)n_lo * g.K, (unsigned)(a_hi - n_lo) * row_bytes, sm.wfull);
+  if (n_hi > g.n_w1) {
+    const int b_lo = max(n_lo, g.n_w1);
+    bulk_g2s(sm.wb + (size_t)(b_lo - n_lo) * g.K, g.W2 + (size_t)(b_lo - g.n_w1) * g.K,
+             (unsigned)(n_hi - b_lo) * row_bytes, sm.wfull);
   }
 }
 
-// Merge the attention partials of the previous phase into the [32][D] context tile
-// (flash-decoding combine, fused into the staging of the output projection).
+// rows b0..b0+31 (zero beyond B), columns k0..k0+kc of a [B][ldx] activation -> Xs (row stride ld floats),
+// as 16-byte cp.async requests that are all in flight at once (one L2 latency for the whole tile).
+// 8 consecutive threads cover 128 contiguous bytes of one row; no index division in the loop.
+__device__ __forceinline__ void stage_rows(float* Xs, int ld, const float* X, long long ldx, int B, int b0, int k0,
+                                           int kc, bool zero_all) {
+  constexpr int TPR = kThreads / kRowBlk;  // threads per row (12)
+  const int r = threadIdx.x / TPR, cg = threadIdx.x - r * TPR;
+  const int nvalid = zero_all ? 0 : min(kRowBlk, B - b0);
+  float* dst = Xs + r * ld + 4 * cg;
+  if (r < nvalid) {
+    const float* src = X + (size_t)(b0 + r) * ldx + k0 + 4 * cg;
+    for (int c = 4 * cg; c < kc; c += 4 * TPR, dst += 4 * TPR, src += 4 * TPR) cp_async16(dst, src);
+  } else {
+    for (int c = 4 * cg; c < kc; c += 4 * TPR, dst += 4 * TPR)
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Merge split-K/V attention partials into the [32][D] context tile (only when n_split > 1, i.e. small batches)
 template <int DH>
-__device__ __noinline__ void stage_combined(const Args& a, const Gemm& g, const Smem& sm, float* Xs, int b0, int t) {
-  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, n = g.comb_keys;
-  const long long total = (long long)B * H * n;
-  const long long sl = (total + G - 1) / G;
-  constexpr int PS = DH + 4;  // record = o[DH], max, sum, pad (16-byte aligned)
-  // 1) merged max and 1/sum per (row, head)
+__device__ __noinline__ void stage_combined(const Args& a, const Gemm& g, const Smem& sm, float* Xs, int ld, int b0,
+                                            int t) {
+  const int B = a.st.batch, H = a.w.n_heads, ns = a.n_split, n = g.comb_keys;
+  constexpr int PS = DH + 4;
   for (int it = threadIdx.x; it < kRowBlk * H; it += kThreads) {
     const int b = b0 + it / H;
     float m = 0.f, inv = 0.f;
     if (b < B) {
-      const int item = b * H + (it % H);
-      const long long pa = (long long)item * n, pb = pa + n - 1;
-      const int c0 = (int)(pa / sl), c1 = (int)(pb / sl);
+      const float* pr = a.part + (size_t)(b * H + (it % H)) * ns * PS;
       m = -CUDART_INF_F;
-      for (int c = c0; c <= c1; ++c) {
-        const int slot = item - (int)(((long long)c * sl) / n);
-        m = fmaxf(m, __ldcg(a.part + ((size_t)c * a.max_seg + slot) * PS + DH));
-      }
+      for (int s = 0; s < ns; ++s) m = fmaxf(m, __ldcg(pr + s * PS + DH));
       float l = 0.f;
-      for (int c = c0; c <= c1; ++c) {
-        const int slot = item - (int)(((long long)c * sl) / n);
-        const float* pr = a.part + ((size_t)c * a.max_seg + slot) * PS;
-        l += __ldcg(pr + DH + 1) * expf(__ldcg(pr + DH) - m);
+      for (int s = 0; s < ns; ++s) {
+        const float pm = __ldcg(pr + s * PS + DH);
+        if (pm > -CUDART_INF_F) l += __ldcg(pr + s * PS + DH + 1) * expf(pm - m);
       }
       inv = 1.f / l;
     }
@@ -162,31 +270,30 @@ __device__ __noinline__ void stage_combined(const Args& a, const Gemm& g, const 
     sm.ml[2 * it + 1] = inv;
   }
   __syncthreads();
-  // 2) context tile
   const int D = H * DH, f4 = D >> 2;
   for (int i = threadIdx.x; i < kRowBlk * f4; i += kThreads) {
     const int r = i / f4, col = (i - r * f4) << 2;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int b = b0 + r;
     if (b < B) {
-      const int h = col / DH, d = col - h * DH, item = b * H + h;
+      const int h = col / DH, d = col - h * DH;
       const float m = sm.ml[2 * (r * H + h)], inv = sm.ml[2 * (r * H + h) + 1];
-      const long long pa = (long long)item * n, pb = pa + n - 1;
-      const int c0 = (int)(pa / sl), c1 = (int)(pb / sl);
-      for (int c = c0; c <= c1; ++c) {
-        const int slot = item - (int)(((long long)c * sl) / n);
-        const float* pr = a.part + ((size_t)c * a.max_seg + slot) * PS;
-        const float wgt = expf(__ldcg(pr + DH) - m);
-        const float4 o = __ldcg(reinterpret_cast<const float4*>(pr + d));
-        acc.x = fmaf(o.x, wgt, acc.x); acc.y = fmaf(o.y, wgt, acc.y);
-        acc.z = fmaf(o.z, wgt, acc.z); acc.w = fmaf(o.w, wgt, acc.w);
+      const float* pr = a.part + (size_t)(b * H + h) * ns * PS;
+      for (int s = 0; s < ns; ++s) {
+        const float pm = __ldcg(pr + s * PS + DH);
+        if (pm > -CUDART_INF_F) {
+          const float wgt = expf(pm - m);
+          const float4 o = __ldcg(reinterpret_cast<const float4*>(pr + s * PS + d));
+          acc.x = fmaf(o.x, wgt, acc.x); acc.y = fmaf(o.y, wgt, acc.y);
+          acc.z = fmaf(o.z, wgt, acc.z); acc.w = fmaf(o.w, wgt, acc.w);
+        }
       }
       acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     }
-    *reinterpret_cast<float4*>(Xs + r * kXLd + col) = acc;
+    *reinterpret_cast<float4*>(Xs + r * ld + col) = acc;
   }
-  // 3) normalise the recorded attention rows of this step (raw logits -> softmax weights)
-  if (g.align != nullptr) {
+  if (g.align != nullptr) {  // raw logits of this step -> softmax weights
+    const int G = gridDim.x;
     for (int it = 0; it < kRowBlk * H; ++it) {
       const int b = b0 + it / H;
       if (b >= B) break;
@@ -199,170 +306,239 @@ __device__ __noinline__ void stage_combined(const Args& a, const Gemm& g, const 
   }
 }
 
-// LayerNorm of the 32 staged rows, in place, 4 rows per warp, statistics from registers
-__device__ __forceinline__ void ln_inplace(float* Xs, int K, const float* __restrict__ gam,
-                                           const float* __restrict__ bet) {
+// LayerNorm of the 32 staged rows, in place.  gamma / beta were staged as rows 32 / 33 of the tile.  Warp w
+// normalises rows w, w+12, w+24 with their reductions interleaved.
+__device__ __forceinline__ void stage_ln_coef(float* Xs, int ld, int K, const float* gam, const float* bet) {
+  const int nf4 = K >> 2;
+  for (int i = threadIdx.x; i < 2 * nf4; i += kThreads) {
+    if (i < nf4) cp_async16(Xs + kRowBlk * ld + 4 * i, gam + 4 * i);
+    else cp_async16(Xs + (kRowBlk + 1) * ld + 4 * (i - nf4), bet + 4 * (i - nf4));
+  }
+}
+__device__ __forceinline__ void ln_inplace(float* Xs, int ld, int K) {
+  constexpr int RW = (kRowBlk + kWarps - 1) / kWarps;  // rows per warp (3)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nf4 = K >> 2;
-  float4 g4[6], b4[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int f = lane + 32 * j;
-    if (f < nf4) {
-      g4[j] = __ldg(reinterpret_cast<const float4*>(gam) + f);
-      b4[j] = __ldg(reinterpret_cast<const float4*>(bet) + f);
-    }
-  }
   const float invK = 1.f / (float)K;
-  for (int r = warp * 4; r < warp * 4 + 4; ++r) {
-    float* xr = Xs + r * kXLd;
-    float4 v[6];
+  const float* gam = Xs + kRowBlk * ld;
+  const float* bet = gam + ld;
+  float mean[RW], rstd[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int row = min(warp + kWarps * r, kRowBlk - 1);
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const int f = lane + 32 * j;
       if (f < nf4) {
-        v[j] = *reinterpret_cast<const float4*>(xr + 4 * f);
-        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        const float4 v = *reinterpret_cast<const float4*>(Xs + row * ld + 4 * f);
+        s += (v.x + v.y) + (v.z + v.w);
       }
     }
-    const float mean = warp_sum(s) * invK;
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int row = min(warp + kWarps * r, kRowBlk - 1);
+    mean[r] *= invK;
     float q = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       const int f = lane + 32 * j;
       if (f < nf4) {
-        const float dx = v[j].x - mean, dy = v[j].y - mean, dz = v[j].z - mean, dw = v[j].w - mean;
+        const float4 v = *reinterpret_cast<const float4*>(Xs + row * ld + 4 * f);
+        const float dx = v.x - mean[r], dy = v.y - mean[r], dz = v.z - mean[r], dw = v.w - mean[r];
         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) * invK + 1e-6f);
+    rstd[r] = q;
+  }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int f = lane + 32 * j;
-      if (f < nf4) {
-        float4 o;
-        o.x = (v[j].x - mean) * rstd * g4[j].x + b4[j].x;
-        o.y = (v[j].y - mean) * rstd * g4[j].y + b4[j].y;
-        o.z = (v[j].z - mean) * rstd * g4[j].z + b4[j].z;
-        o.w = (v[j].w - mean) * rstd * g4[j].w + b4[j].w;
-        *reinterpret_cast<float4*>(xr + 4 * f) = o;
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int row = warp + kWarps * r;
+    if (row < kRowBlk) {  // warp-uniform
+      const float rs = rsqrtf(rstd[r] * invK + 1e-6f);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int f = lane + 32 * j;
+        if (f < nf4) {
+          float* px = Xs + row * ld + 4 * f;
+          const float4 v = *reinterpret_cast<const float4*>(px);
+          const float4 g4 = *reinterpret_cast<const float4*>(gam + 4 * f);
+          const float4 b4 = *reinterpret_cast<const float4*>(bet + 4 * f);
+          float4 o;
+          o.x = (v.x - mean[r]) * rs * g4.x + b4.x;
+          o.y = (v.y - mean[r]) * rs * g4.y + b4.y;
+          o.z = (v.z - mean[r]) * rs * g4.z + b4.z;
+          o.w = (v.w - mean[r]) * rs * g4.w + b4.w;
+          *reinterpret_cast<float4*>(px) = o;
+        }
       }
     }
   }
 }
 
-// acc[r][i] += sum_k W[n0+r][k0+k] * Xs[4g+i][k] over this warp's 16-float chunks of the slice
-__device__ __forceinline__ void fma_slice(f32x2 (&acc)[kPass][4], const float* Xs, int kc,
-                                          const float* wbase, int K, int nrows, int k0) {
+// X-stationary product.  A warp owns the 16-float chunks {warp, warp+8, ...} of a <=768-wide slice; a lane
+// (g = lane/4, s = lane%4) keeps batch rows 4g..4g+3, floats 4s..4s+3 of each of its chunks in registers for
+// the whole phase, so the inner loop only reads weights (one 64-byte wavefront per weight row and chunk).
+struct XFrag {
+  f32x4 v[kChunksPerWarp][4];
+};
+__device__ __forceinline__ void load_xfrag(XFrag& xf, const float* Xs, int ld, int kc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, s4 = (lane & 3) * 4;
-  const int nch = kc >> 4;
-#pragma unroll 2
-  for (int c = warp; c < nch; c += kWarps) {
-    const int kk = c * 16 + s4;
-    f32x4 wv[kPass];
+  const int g = lane >> 2, s4 = (lane & 3) * 4, nch = kc >> 4;
 #pragma unroll
-    for (int r = 0; r < kPass; ++r) {
-      if (r < nrows) wv[r] = ldg_stream(wbase + (size_t)r * K + k0 + kk);
-      else wv[r].lo = wv[r].hi = 0ull;
+  for (int j = 0; j < kChunksPerWarp; ++j) {
+    const int c = warp + kWarps * j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (c < nch) xf.v[j][i] = ld4s(Xs + (4 * g + i) * ld + c * 16 + s4);
+      else xf.v[j][i].lo = xf.v[j][i].hi = 0ull;
     }
-    f32x4 xv[4];
+  }
+}
+// acc[r][i] += sum over this warp's chunks of Wb[r][k0 + ...] * X; rows r >= nrows alias the last valid row
+// (their accumulators are never stored) so the loop is branch-free; chunks beyond the slice multiply zeros.
+__device__ __forceinline__ void fma_rows(f32x2 (&acc)[kPass][4], const XFrag& xf, int kc, const float* wb, int K,
+                                         int nrows, int k0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s4 = (lane & 3) * 4, nch = kc >> 4;
+  int coff[kChunksPerWarp];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) xv[i] = lds128(Xs + (4 * g + i) * kXLd + kk);
+  for (int j = 0; j < kChunksPerWarp; ++j) coff[j] = min(warp + kWarps * j, nch - 1) * 16 + k0 + s4;
 #pragma unroll
-    for (int r = 0; r < kPass; ++r)
-      if (r < nrows) {
+  for (int r = 0; r < kPass; ++r) {
+    const float* wr = wb + (size_t)min(r, nrows - 1) * K;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[r][i] = fma2(xv[i].lo, wv[r].lo, acc[r][i]);
-          acc[r][i] = fma2(xv[i].hi, wv[r].hi, acc[r][i]);
-        }
+    for (int j = 0; j < kChunksPerWarp; ++j) {
+      const f32x4 wv = ld4s(wr + coff[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[r][i] = fma2(xf.v[j][i].lo, wv.lo, acc[r][i]);
+        acc[r][i] = fma2(xf.v[j][i].hi, wv.hi, acc[r][i]);
       }
+    }
   }
 }
 
 template <bool LN, int DH>
-__device__ __noinline__ void gemm_phase(const Args& a, const Gemm& g, const Smem& sm, int t) {
-  const int G = gridDim.x, c = blockIdx.x, B = a.st.batch;
-  const int n_lo = (int)(((long long)c * g.N) / G), n_hi = (int)(((long long)(c + 1) * g.N) / G);
+__device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* smem_base, unsigned w_par, long long* prof,
+                                        int t) {
+  const Smem sm = make_smem(a, smem_base);
+  Track tk{w_par, 0u, 0u, prof};
+  const int B = a.st.batch;
+  int n_lo, n_hi;
+  slice_rows(g, n_lo, n_hi);
   const bool has_rows = n_hi > n_lo;
   const bool owns_align = g.xsrc == kXCombine && g.align != nullptr;
   if (!has_rows && !owns_align) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2;
-  const bool single = g.K <= kKC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ld = min(g.K, kKC) + 4;
   const int n_kc = (g.K + kKC - 1) / kKC;
+  bool w_ready = !has_rows;
 
   for (int b0 = 0; b0 < B; b0 += kRowBlk) {
-    if (single) {
+    if (n_kc == 1) {  // the whole K fits one tile: stage (+ LayerNorm) once, every pass re-reads it
       if (g.xsrc == kXCombine) {
-        stage_combined<DH>(a, g, sm, sm.xs[0], b0, t);
+        stage_combined<DH>(a, g, sm, sm.xs, ld, b0, t);
       } else {
         const bool from_frames = g.xsrc == kXFrames;
         const float* X = from_frames ? a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * a.w.n_mels : g.X;
-        stage_plain(sm.xs[0], X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
-        cp_async_commit();
-        cp_async_wait<0>();
+        if (LN) stage_ln_coef(sm.xs, ld, g.K, g.ln_g, g.ln_b);
+        stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
       }
+      cp_async_wait_all();
       __syncthreads();
+      stamp(tk, 3);
       if (LN) {
-        ln_inplace(sm.xs[0], g.K, g.ln_g, g.ln_b);
+        ln_inplace(sm.xs, ld, g.K);
         __syncthreads();
       }
+      stamp(tk, 4);
     }
-    for (int n0 = n_lo, nstep = 0; n0 < n_hi; n0 += nstep) {
-      int nrows = min(kPass, n_hi - n0);
-      if (n0 < g.n_w1) nrows = min(nrows, g.n_w1 - n0);  // a pass never straddles the W / W2 boundary
-      const float* wbase = n0 < g.n_w1 ? g.W + (size_t)n0 * g.K : g.W2 + (size_t)(n0 - g.n_w1) * g.K;
+    if (!has_rows) continue;
+    if (!w_ready) {
+      mbar_wait(sm.wfull, tk.w_par, a.err);
+      w_ready = true;
+      stamp(tk, 5);
+    }
+    for (int n0 = n_lo; n0 < n_hi; n0 += kPass) {
+      const int nrows = min(kPass, n_hi - n0);
+      const float* wb = sm.wb + (size_t)(n0 - n_lo) * g.K;
+      // operands of the epilogue are requested now so that their latency hides behind the products
+      const int er = tid >> 5, eb = b0 + (tid & 31);
+      const bool e_on = er < nrows && eb < B;
+      float e_res = 0.f, e_bias = 0.f;
+      if (e_on && g.R) e_res = __ldcg(g.R + (size_t)eb * g.ldr + n0 + er);
+      if (e_on && g.bias) e_bias = __ldg(g.bias + n0 + er);
       f32x2 acc[kPass][4];
 #pragma unroll
       for (int r = 0; r < kPass; ++r)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[r][i] = 0ull;
-
-      if (single) {
-        fma_slice(acc, sm.xs[0], g.K, wbase, g.K, nrows, 0);
-      } else {  // K > 768 (FFN-out): double-buffered K slices of the activation
-        stage_plain(sm.xs[0], g.X, g.ldx, B, b0, 0, kKC, false);
-        cp_async_commit();
-        for (int ki = 0; ki < n_kc; ++ki) {
-          const int k0 = ki * kKC;
-          if (ki + 1 < n_kc) {
-            stage_plain(sm.xs[(ki + 1) & 1], g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
-            cp_async_commit();
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
+      {
+        XFrag xf;  // activation fragments live only while the products run
+        if (n_kc == 1) {
+          load_xfrag(xf, sm.xs, ld, g.K);
+          fma_rows(acc, xf, g.K, wb, g.K, nrows, 0);
+        } else {  // K > 768 (FFN-out): the next slice streams into shared memory while this one is multiplied
+          stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
+          for (int ki = 0; ki < n_kc; ++ki) {
+            const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
+            cp_async_wait_all();
+            __syncthreads();
+            load_xfrag(xf, sm.xs, ld, kc);
+            __syncthreads();  // every warp holds its fragments: the tile may be refilled
+            if (ki + 1 < n_kc) stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
+            fma_rows(acc, xf, kc, wb, g.K, nrows, k0);
           }
-          __syncthreads();
-          fma_slice(acc, sm.xs[ki & 1], min(kKC, g.K - k0), wbase, g.K, nrows, k0);
-          __syncthreads();
         }
       }
-      // reduce: packed pairs -> 4 k-split lanes -> 8 warps
+      {  // packed pairs -> reduce-scatter over the 4 k-split lanes (each ends up owning 2 weight rows x 4
+         // batch rows) -> one 128-bit store per weight row into the cross-warp buffer
+        const int ks = lane & 3, gq = lane >> 2;
+        float v32[kPass * 4];
 #pragma unroll
-      for (int r = 0; r < kPass; ++r)
+        for (int r = 0; r < kPass; ++r)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v = hsum2(acc[r][i]);
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          if ((lane & 3) == 0) sm.red[(warp * kPass + r) * 32 + 4 * gq + i] = v;
+          for (int i = 0; i < 4; ++i) v32[r * 4 + i] = hsum2(acc[r][i]);
+        float v16[16], v8[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float keep = (ks & 1) ? v32[j + 16] : v32[j], send = (ks & 1) ? v32[j] : v32[j + 16];
+          v16[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float keep = (ks & 2) ? v16[j + 8] : v16[j], send = (ks & 2) ? v16[j] : v16[j + 8];
+          v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        const int r0 = ((ks & 1) ? 4 : 0) + ((ks & 2) ? 2 : 0);  // first of the two weight rows this lane owns
+        float* dst = sm.red + (warp * kPass + r0) * 32 + 4 * gq;
+        *reinterpret_cast<float4*>(dst) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+        *reinterpret_cast<float4*>(dst + 32) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+      }
       __syncthreads();
-      const int r = tid >> 5, br = tid & 31, b = b0 + br;
-      if (r < nrows && b < B) {
+      stamp(tk, 6);
+      const int r = er, br = tid & 31, b = eb;
+      if (e_on) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) v += sm.red[(w * kPass + r) * 32 + br];
         const int n = n0 + r;
-        if (g.bias) v += __ldg(g.bias + n);
+        v += e_bias;
         if (g.relu) v = fmaxf(v, 0.f);
         switch (g.mode) {
           case kPlain: {
-            v *= g.out_scale;
-            if (g.R) v += __ldcg(g.R + (size_t)b * g.ldr + n);
-            g.Y[(size_t)b * g.ldy + n] = v;
+            g.Y[(size_t)b * g.ldy + n] = v * g.out_scale + e_res;
           } break;
           case kQkv: {
             const int H = a.w.n_heads, D = H * DH;
@@ -387,171 +563,279 @@ __device__ __noinline__ void gemm_phase(const Args& a, const Gemm& g, const Smem
         }
       }
       __syncthreads();  // red is reused by the next pass
-      nstep = nrows;
+      stamp(tk, 7);
     }
   }
 }
 
 // ---- attention phase ------------------------------------------------------------------------------
 template <int DH>
-__device__ void attn_segment(const Args& a, const float* q, const float* kbase, const float* vbase, int j0, int j1,
-                             int klen, float* part_rec, float* arow, float* sc, float* s_red, float* s_max,
-                             float* s_sum) {
-  constexpr int F4 = DH / 32;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kslot = lane >> 3, l8 = lane & 7;
-  f32x4 qv[F4];
-#pragma unroll
-  for (int i = 0; i < F4; ++i) qv[i] = ldg_cg(q + 4 * (l8 + 8 * i));
+__device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, float* smem_base, unsigned ring_count,
+                                            long long* prof, int t) {
+  const Smem sm = make_smem(a, smem_base);
+  Track tk{0u, ring_count, ring_count, prof};
+  constexpr int F4 = DH / 32;            // float4 per lane per key row (8 lanes span a row)
+  constexpr int kTile = kTK * DH;        // floats per K (or V) tile
+  constexpr int kSlotF = 2 * kTile;      // K tile then V tile
+  constexpr int kRounds = kTK / 4;       // 4 key slots per warp pass
+  constexpr int PS = DH + 4;
+  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split;
+  const int n_units = B * H * ns, n_keys = at.n_keys;
+  const int per = (n_keys + ns - 1) / ns;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kslot = lane >> 3, l8 = lane & 7;
+  float* ring = sm.ring + (size_t)warp * kSlots * kSlotF;
+  uint64_t* full = sm.rfull + warp * kSlots;
+  float* wrec = sm.red;  // [8][PS]
 
-  float lmax = -CUDART_INF_F;
-  for (int jb = j0 + warp * 4; jb < j1; jb += 32 * 4) {
-    f32x4 kv[4][F4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * 32 + kslot;
-#pragma unroll
-      for (int i = 0; i < F4; ++i) {
-        if (j < j1) kv[u][i] = ldg_cg(kbase + (size_t)j * DH + 4 * (l8 + 8 * i));
-        else kv[u][i].lo = kv[u][i].hi = 0ull;
-      }
+  // ---- producer cursor (next tile this warp will request) ----
+  int pu = blockIdx.x, pi = warp;
+  auto issue_next = [&]() {
+    int item = 0, j0 = 0, j1 = 0;
+    while (pu < n_units) {
+      item = ns == 1 ? pu : pu / ns;
+      j0 = min(n_keys, (pu - item * ns) * per);
+      j1 = min(n_keys, j0 + per);
+      if (pi * kTK < j1 - j0) break;
+      pu += G;
+      pi = warp;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * 32 + kslot;
-      f32x2 acc = 0ull;
-#pragma unroll
-      for (int i = 0; i < F4; ++i) {
-        acc = fma2(qv[i].lo, kv[u][i].lo, acc);
-        acc = fma2(qv[i].hi, kv[u][i].hi, acc);
-      }
-      float s = hsum2(acc);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (j < j1) {
-        if (j >= klen) s = kNegBias;
-        if (l8 == 0) sc[j - j0] = s;
-        lmax = fmaxf(lmax, s);
-      }
+    if (pu >= n_units) return;
+    const int key0 = j0 + pi * kTK, nk = min(kTK, j1 - key0);
+    const int slot = tk.issued % kSlots;
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)nk * DH * 4u;
+      mbar_expect_tx(&full[slot], 2u * bytes);
+      const size_t off = ((size_t)item * at.rows_alloc + key0) * DH;
+      bulk_g2s(ring + slot * kSlotF, at.kc + off, bytes, &full[slot]);
+      bulk_g2s(ring + slot * kSlotF + kTile, at.vc + off, bytes, &full[slot]);
     }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) s_max[warp] = lmax;
-  __syncthreads();
-  float m = s_max[0];
+    tk.issued++;
+    pi += kWarps;
+  };
 #pragma unroll
-  for (int w = 1; w < kWarps; ++w) m = fmaxf(m, s_max[w]);
+  for (int s = 0; s < kSlots; ++s) issue_next();
 
-  f32x2 o[F4][2];
+  for (int u = blockIdx.x; u < n_units; u += G) {
+    const int item = ns == 1 ? u : u / ns, split = u - item * ns;
+    const int j0 = min(n_keys, split * per), j1 = min(n_keys, j0 + per);
+    const int b = item / H;
+    const int klen = at.key_len ? at.key_len[b] : n_keys;
+    float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
+
+    f32x4 qv[F4];
 #pragma unroll
-  for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
-  float lsum = 0.f;
-  for (int jb = j0 + warp * 4; jb < j1; jb += 32 * 4) {
-    f32x4 vv[4][F4];
+    for (int i = 0; i < F4; ++i) qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    f32x2 o[F4][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * 32 + kslot;
+    for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
+
+    const int n_tiles = (j1 - j0 + kTK - 1) / kTK;
+    for (int ti = warp; ti < n_tiles; ti += kWarps) {
+      const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
+      const int slot = tk.consumed % kSlots;
+      mbar_wait(&full[slot], (tk.consumed / kSlots) & 1u, a.err);
+      const float* kt = ring + slot * kSlotF;
+      const float* vt = kt + kTile;
+      float s[kRounds];
+      float mt = -CUDART_INF_F;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int kl = r * 4 + kslot;
+        f32x2 acc = 0ull;
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          const f32x4 kv = ld4s(kt + kl * DH + 4 * (l8 + 8 * i));
+          acc = fma2(qv[i].lo, kv.lo, acc);
+          acc = fma2(qv[i].hi, kv.hi, acc);
+        }
+        float v = hsum2(acc);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (kl >= nk) v = -CUDART_INF_F;                 // stale smem beyond the tile's keys
+        else if (key0 + kl >= klen) v = kNegBias;        // logits + (-1e20), attention.py:84-85
+        if (kl < nk && l8 == 0 && arow != nullptr) arow[key0 + kl] = v;  // raw logit, normalised below
+        s[r] = v;
+        mt = fmaxf(mt, v);
+      }
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+      const float m_new = fmaxf(m_run, mt);
+      const float corr = expf(m_run - m_new);
+      l_run *= corr;
+      const f32x2 c2 = pack2(corr, corr);
 #pragma unroll
       for (int i = 0; i < F4; ++i) {
-        if (j < j1) vv[u][i] = ldg_cg(vbase + (size_t)j * DH + 4 * (l8 + 8 * i));
-        else vv[u][i].lo = vv[u][i].hi = 0ull;
+        o[i][0] = fma2(o[i][0], c2, 0ull);
+        o[i][1] = fma2(o[i][1], c2, 0ull);
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = jb + u * 32 + kslot;
-      const float p = j < j1 ? expf(sc[j - j0] - m) : 0.f;
-      if (l8 == 0) lsum += p;
-      const f32x2 pp = pack2(p, p);
+      for (int r = 0; r < kRounds; ++r) {
+        const int kl = r * 4 + kslot;
+        const float p = kl < nk ? expf(s[r] - m_new) : 0.f;
+        if (l8 == 0) l_run += p;
+        const f32x2 pp = pack2(p, p);
 #pragma unroll
-      for (int i = 0; i < F4; ++i) {
-        o[i][0] = fma2(pp, vv[u][i].lo, o[i][0]);
-        o[i][1] = fma2(pp, vv[u][i].hi, o[i][1]);
+        for (int i = 0; i < F4; ++i) {
+          const f32x4 vv = ld4s(vt + kl * DH + 4 * (l8 + 8 * i));
+          o[i][0] = fma2(pp, kl < nk ? vv.lo : 0ull, o[i][0]);
+          o[i][1] = fma2(pp, kl < nk ? vv.hi : 0ull, o[i][1]);
+        }
       }
+      m_run = m_new;
+      tk.consumed++;
+      __syncwarp();   // every lane is done with this slot before it is refilled
+      issue_next();
     }
-  }
+    // ---- warp record (max, sum, weighted V) -> shared ----
 #pragma unroll
-  for (int i = 0; i < F4; ++i)
+    for (int i = 0; i < F4; ++i)
 #pragma unroll
-    for (int hs = 0; hs < 2; ++hs) {
-      float x, y;
-      unpack2(o[i][hs], x, y);
-      x += __shfl_xor_sync(0xffffffffu, x, 8);  y += __shfl_xor_sync(0xffffffffu, y, 8);
-      x += __shfl_xor_sync(0xffffffffu, x, 16); y += __shfl_xor_sync(0xffffffffu, y, 16);
-      if (kslot == 0) {
-        const int d = 4 * (l8 + 8 * i) + 2 * hs;
-        s_red[warp * (DH + 1) + d] = x;
-        s_red[warp * (DH + 1) + d + 1] = y;
+      for (int hs = 0; hs < 2; ++hs) {
+        float x, y;
+        unpack2(o[i][hs], x, y);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);  y += __shfl_xor_sync(0xffffffffu, y, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16); y += __shfl_xor_sync(0xffffffffu, y, 16);
+        if (kslot == 0) {
+          const int d = 4 * (l8 + 8 * i) + 2 * hs;
+          wrec[warp * PS + d] = x;
+          wrec[warp * PS + d + 1] = y;
+        }
       }
+    const float lw = warp_sum(l_run);
+    if (lane == 0) {
+      wrec[warp * PS + DH] = m_run;
+      wrec[warp * PS + DH + 1] = lw;
     }
-  lsum = warp_sum(lsum);
-  if (lane == 0) s_sum[warp] = lsum;
-  __syncthreads();
-  if (tid < DH) {
-    float v = 0.f;
+    __syncthreads();
+    float m = -CUDART_INF_F;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) v += s_red[w * (DH + 1) + tid];
-    part_rec[tid] = v;
-  }
-  if (tid == 0) {
+    for (int w = 0; w < kWarps; ++w) m = fmaxf(m, wrec[w * PS + DH]);
     float l = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) l += s_sum[w];
-    part_rec[DH] = m;
-    part_rec[DH + 1] = l;
+    for (int w = 0; w < kWarps; ++w) {
+      const float mw = wrec[w * PS + DH];
+      if (mw > -CUDART_INF_F) l += wrec[w * PS + DH + 1] * expf(mw - m);
+    }
+    if (tid < DH) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const float mw = wrec[w * PS + DH];
+        if (mw > -CUDART_INF_F) v += wrec[w * PS + tid] * expf(mw - m);
+      }
+      if (ns == 1) a.ctx[(size_t)item * DH + tid] = v / l;
+      else a.part[(size_t)u * PS + tid] = v;
+    }
+    if (ns == 1) {
+      if (arow != nullptr) {
+        const float inv = 1.f / l;
+        for (int j = j0 + tid; j < j1; j += kThreads) arow[j] = expf(arow[j] - m) * inv;
+      }
+    } else if (tid == 0) {
+      a.part[(size_t)u * PS + DH] = m;       // -inf when the split is empty
+      a.part[(size_t)u * PS + DH + 1] = l;
+    }
+    __syncthreads();  // wrec is reused by the next unit
   }
-  if (arow != nullptr)
-    for (int j = j0 + tid; j < j1; j += kThreads) arow[j] = sc[j - j0];  // raw logits; normalised by the consumer
-  __syncthreads();  // sc / s_red are reused by the next segment
+  return tk.consumed;
 }
 
+// ---- phase table --------------------------------------------------------------------------------------
 template <int DH>
-__device__ __noinline__ void attn_phase(const Args& a, const Smem& sm, const float* kc, const float* vc, int rows_alloc,
-                           int n_keys, const int32_t* key_len, float* align, long long align_bh_stride,
-                           int align_row_len, int t) {
-  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, c = blockIdx.x;
-  const long long total = (long long)B * H * n_keys;
-  const long long sl = (total + G - 1) / G;
-  long long p = (long long)c * sl;
-  const long long p1 = min(total, p + sl);
-  float* sc = sm.xs[0];           // up to sl floats (host checks it fits)
-  float* s_red = sm.red;          // 8 * (DH+1)
-  float* s_max = sm.red + kWarps * (DH + 1);
-  float* s_sum = s_max + kWarps;
-  int seg = 0;
-  while (p < p1) {
-    const int item = (int)(p / n_keys);
-    const int j0 = (int)(p - (long long)item * n_keys);
-    const int j1 = (int)min((long long)n_keys, j0 + (p1 - p));
-    const int b = item / H;
-    const int klen = key_len ? key_len[b] : n_keys;
-    float* rec = a.part + ((size_t)c * a.max_seg + seg) * (DH + 4);
-    float* arow = align ? align + (size_t)item * align_bh_stride + (size_t)t * align_row_len : nullptr;
-    attn_segment<DH>(a, a.q + (size_t)item * DH, kc + (size_t)item * rows_alloc * DH,
-                     vc + (size_t)item * rows_alloc * DH, j0, j1, klen, rec, arow, sc, s_red, s_max, s_sum);
-    p += j1 - j0;
-    ++seg;
+__device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qscale, Phase& p) {
+  const int B = a.st.batch, D = a.w.d_model, H = a.w.n_heads, F = a.w.d_ffn, P = a.w.prenet_hidden;
+  const int M = a.w.n_mels, S = a.st.mem_len, T = a.st.t_max, L = a.w.n_layers;
+  Gemm& g = p.g;
+  memset(&g, 0, sizeof(g));
+  g.out_scale = 1.f;
+  p.kind = 0;
+  if (ph == 0) {         // prenet (tacotron.py:55-65)
+    g.xsrc = kXFrames; g.ldx = (long long)T * M; g.K = M; g.N = P; g.W = a.w.prenet_w0; g.n_w1 = P;
+    g.bias = a.w.prenet_b0; g.relu = 1; g.mode = kPlain; g.Y = a.p0; g.ldy = P;
+  } else if (ph == 1) {
+    g.X = a.p0; g.ldx = P; g.K = P; g.N = P; g.W = a.w.prenet_w1; g.n_w1 = P; g.bias = a.w.prenet_b1; g.relu = 1;
+    g.mode = kPlain; g.Y = a.p1; g.ldy = P;
+  } else if (ph == 2) {  // + shift / mask / PE (modules.py:114-118)
+    g.X = a.p1; g.ldx = P; g.K = P; g.N = D; g.W = a.w.prenet_w2; g.n_w1 = D; g.mode = kPrenetOut; g.Y = a.x; g.ldy = D;
+  } else if (ph == 3 + 8 * L) {  // final LN + mel / stop projections
+    p.kind = 1;
+    g.X = a.x; g.ldx = D; g.K = D; g.N = M + 1; g.W = a.w.w_mel; g.W2 = a.w.w_stop; g.n_w1 = M;
+    g.ln_g = a.w.ln_out_g; g.ln_b = a.w.ln_out_b; g.mode = kFinal;
+  } else {
+    const int l = (ph - 3) / 8, k = (ph - 3) % 8;
+    const TtsDecLayerWeights& lw = a.w.layer[l];
+    const size_t self_off = (size_t)l * B * H * T * DH, cross_off = (size_t)l * B * H * S * DH;
+    float* al_self = a.st.align_self ? a.st.align_self + (size_t)l * B * H * T * T : nullptr;
+    float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
+    switch (k) {
+      case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
+        p.kind = 1;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = 3 * D; g.W = lw.w_qkv; g.n_w1 = 3 * D; g.ln_g = lw.ln_self_g;
+        g.ln_b = lw.ln_self_b; g.mode = kQkv; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
+        g.kcache = a.st.self_k + self_off; g.vcache = a.st.self_v + self_off;
+        break;
+      case 1:
+        p.kind = 2;
+        p.at.kc = a.st.self_k + self_off; p.at.vc = a.st.self_v + self_off; p.at.rows_alloc = T; p.at.n_keys = t + 1;
+        p.at.key_len = nullptr; p.at.align = al_self; p.at.align_bh_stride = (long long)T * T; p.at.align_row_len = T;
+        break;
+      case 2:  // output projection + residual (attention.py:118-119, modules.py:132)
+        if (a.n_split > 1) {
+          g.xsrc = kXCombine; g.comb_keys = t + 1; g.align = al_self; g.align_bh_stride = (long long)T * T; g.align_row_len = T;
+        } else {
+          g.X = a.ctx; g.ldx = D;
+        }
+        g.K = D; g.N = D; g.W = lw.w_self_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        break;
+      case 3:  // LN + cross query
+        p.kind = 1;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = D; g.W = lw.w_cross_q; g.n_w1 = D; g.ln_g = lw.ln_cross_g;
+        g.ln_b = lw.ln_cross_b; g.mode = kPlain; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
+        break;
+      case 4:
+        p.kind = 2;
+        p.at.kc = a.st.cross_k + cross_off; p.at.vc = a.st.cross_v + cross_off; p.at.rows_alloc = S; p.at.n_keys = S;
+        p.at.key_len = a.st.input_lengths; p.at.align = al_cross; p.at.align_bh_stride = (long long)T * S; p.at.align_row_len = S;
+        break;
+      case 5:
+        if (a.n_split > 1) {
+          g.xsrc = kXCombine; g.comb_keys = S; g.align = al_cross; g.align_bh_stride = (long long)T * S; g.align_row_len = S;
+        } else {
+          g.X = a.ctx; g.ldx = D;
+        }
+        g.K = D; g.N = D; g.W = lw.w_cross_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        break;
+      case 6:  // LN + FFN-in + ReLU (modules.py:14-17)
+        p.kind = 1;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = F; g.W = lw.w_ffn_in; g.n_w1 = F; g.ln_g = lw.ln_ffn_g; g.ln_b = lw.ln_ffn_b;
+        g.relu = 1; g.mode = kPlain; g.Y = a.hid; g.ldy = F;
+        break;
+      default:  // FFN-out + residual
+        g.X = a.hid; g.ldx = F; g.K = F; g.N = D; g.W = lw.w_ffn_out; g.n_w1 = D; g.mode = kPlain;
+        g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        break;
+    }
   }
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_constant__ Args a) {
-  extern __shared__ __align__(16) float smem_raw[];
-  Smem sm;
-  sm.xs[0] = smem_raw;
-  sm.xs[1] = sm.xs[0] + kRowBlk * kXLd;
-  sm.red = sm.xs[1] + kRowBlk * kXLd;
-  sm.ml = sm.red + kWarps * kPass * 32;
-  sm.len = reinterpret_cast<int*>(sm.ml + 2 * kRowBlk * a.w.n_heads);
-  sm.fin = sm.len + a.st.batch;
+  extern __shared__ __align__(128) float smem_raw[];
+  const Smem sm = make_smem(a, smem_raw);
 
-  const int B = a.st.batch, D = a.w.d_model, H = a.w.n_heads, F = a.w.d_ffn, P = a.w.prenet_hidden;
-  const int M = a.w.n_mels, S = a.st.mem_len, T = a.st.t_max, L = a.w.n_layers;
+  const int B = a.st.batch, T = a.st.t_max;
+  const int n_phases = 3 + 8 * a.w.n_layers + 1;
   GridBar gb{a.bar, a.err, 0u, gridDim.x};
+  unsigned w_par = 0u, ring_count = 0u;
   const float qscale = (float)(1.0 / sqrt((double)DH));
 
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3 + kWarps * kSlots; ++i) mbar_init(&sm.wfull[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int b = threadIdx.x; b < B; b += kThreads) {
     sm.len[b] = a.st.lengths[b];
     sm.fin[b] = a.st.finished[b];
@@ -559,86 +843,47 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
   __syncthreads();
   const int t0 = *a.st.step_counter;
 
-  Gemm base;
-  memset(&base, 0, sizeof(base));
-  base.out_scale = 1.f;
+  // phase descriptors live in shared memory (one copy per CTA, written by thread 0): per-thread copies
+  // would sit in local memory, and with ~200 KB of shared memory in use the L1 left for it is tiny
+  __shared__ Phase ph_buf[2];
+  Phase* cur = &ph_buf[0];
+  Phase* nxt = &ph_buf[1];
+  if (threadIdx.x == 0) {
+    get_phase<DH>(a, 0, t0, qscale, *cur);
+    issue_weights(cur->g, sm);
+  }
+  __syncthreads();
 
   for (int s = 0; s < a.n_steps; ++s) {
     const int t = t0 + s;
-    {  // prenet (tacotron.py:55-65) and shift/mask/PE (modules.py:114-118)
-      Gemm g = base;
-      g.xsrc = kXFrames; g.ldx = (long long)T * M; g.K = M; g.N = P; g.W = a.w.prenet_w0; g.n_w1 = P;
-      g.bias = a.w.prenet_b0; g.relu = 1; g.mode = kPlain; g.Y = a.p0; g.ldy = P;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-      g = base;
-      g.X = a.p0; g.ldx = P; g.K = P; g.N = P; g.W = a.w.prenet_w1; g.n_w1 = P; g.bias = a.w.prenet_b1; g.relu = 1;
-      g.mode = kPlain; g.Y = a.p1; g.ldy = P;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-      g = base;
-      g.X = a.p1; g.ldx = P; g.K = P; g.N = D; g.W = a.w.prenet_w2; g.n_w1 = D; g.mode = kPrenetOut; g.Y = a.x; g.ldy = D;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-    }
-    for (int l = 0; l < L; ++l) {
-      const TtsDecLayerWeights& lw = a.w.layer[l];
-      const size_t self_off = (size_t)l * B * H * T * DH, cross_off = (size_t)l * B * H * S * DH;
-      Gemm g = base;  // LN + QKV (attention.py:63-64), k/v appended at row t
-      g.X = a.x; g.ldx = D; g.K = D; g.N = 3 * D; g.W = lw.w_qkv; g.n_w1 = 3 * D; g.ln_g = lw.ln_self_g;
-      g.ln_b = lw.ln_self_b; g.mode = kQkv; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
-      g.kcache = a.st.self_k + self_off; g.vcache = a.st.self_v + self_off;
-      gemm_phase<true, DH>(a, g, sm, t);
-      grid_sync(gb);
-
-      float* al = a.st.align_self ? a.st.align_self + (size_t)l * B * H * T * T : nullptr;
-      attn_phase<DH>(a, sm, a.st.self_k + self_off, a.st.self_v + self_off, T, t + 1, nullptr, al, (long long)T * T, T, t);
-      grid_sync(gb);
-
-      g = base;  // merge partials + output projection + residual (attention.py:118-119, modules.py:132)
-      g.xsrc = kXCombine; g.comb_keys = t + 1; g.align = al; g.align_bh_stride = (long long)T * T; g.align_row_len = T;
-      g.K = D; g.N = D; g.W = lw.w_self_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-
-      g = base;  // LN + cross query
-      g.X = a.x; g.ldx = D; g.K = D; g.N = D; g.W = lw.w_cross_q; g.n_w1 = D; g.ln_g = lw.ln_cross_g;
-      g.ln_b = lw.ln_cross_b; g.mode = kPlain; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
-      gemm_phase<true, DH>(a, g, sm, t);
-      grid_sync(gb);
-
-      al = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
-      attn_phase<DH>(a, sm, a.st.cross_k + cross_off, a.st.cross_v + cross_off, S, S, a.st.input_lengths, al,
-                     (long long)T * S, S, t);
-      grid_sync(gb);
-
-      g = base;
-      g.xsrc = kXCombine; g.comb_keys = S; g.align = al; g.align_bh_stride = (long long)T * S; g.align_row_len = S;
-      g.K = D; g.N = D; g.W = lw.w_cross_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-
-      g = base;  // LN + FFN-in + ReLU (modules.py:14-17)
-      g.X = a.x; g.ldx = D; g.K = D; g.N = F; g.W = lw.w_ffn_in; g.n_w1 = F; g.ln_g = lw.ln_ffn_g; g.ln_b = lw.ln_ffn_b;
-      g.relu = 1; g.mode = kPlain; g.Y = a.hid; g.ldy = F;
-      gemm_phase<true, DH>(a, g, sm, t);
-      grid_sync(gb);
-
-      g = base;  // FFN-out + residual
-      g.X = a.hid; g.ldx = F; g.K = F; g.N = D; g.W = lw.w_ffn_out; g.n_w1 = D; g.mode = kPlain;
-      g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
-      gemm_phase<false, DH>(a, g, sm, t);
-      grid_sync(gb);
-    }
-    {  // final LN + mel / stop projections
-      Gemm g = base;
-      g.X = a.x; g.ldx = D; g.K = D; g.N = M + 1; g.W = a.w.w_mel; g.W2 = a.w.w_stop; g.n_w1 = M;
-      g.ln_g = a.w.ln_out_g; g.ln_b = a.w.ln_out_b; g.mode = kFinal;
-      gemm_phase<true, DH>(a, g, sm, t);
-      grid_sync(gb);
+    for (int ph = 0; ph < n_phases; ++ph) {
+      long long* prof = (blockIdx.x == 0 && threadIdx.x == 0 && ph < kProfPhases) ? a.prof + 8 * ph : nullptr;
+      if (prof) prof[0] = clock64();
+      if (cur->kind == 2) {
+        ring_count = attn_phase<DH>(a, cur->at, smem_raw, ring_count, prof, t);
+      } else {
+        if (cur->kind == 1) gemm_phase<true, DH>(a, cur->g, smem_raw, w_par, prof, t);
+        else gemm_phase<false, DH>(a, cur->g, smem_raw, w_par, prof, t);
+        int n_lo, n_hi;
+        slice_rows(cur->g, n_lo, n_hi);
+        if (n_hi > n_lo) w_par ^= 1u;  // this CTA consumed one completion of the weight barrier
+      }
+      const bool last = ph == n_phases - 1;
+      if (prof) prof[1] = clock64();
+      bar_arrive(gb);
+      if (!last && threadIdx.x == 0) {  // the next phase's weights stream in while we wait for the other CTAs
+        get_phase<DH>(a, ph + 1, t, qscale, *nxt);
+        if (nxt->kind != 2) issue_weights(nxt->g, sm);
+      }
+      bar_wait(gb);
+      if (prof) prof[2] = clock64();
+      if (!last) {
+        Phase* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+      }
     }
     // synthesize.py:42-45, replicated identically in every CTA
-    int unfinished = 0;
     if (a.update_state) {
       for (int b = threadIdx.x; b < B; b += kThreads) {
         const bool fin = sm.fin[b] != 0 || __ldcg(a.st.stop_logits + (size_t)b * T + t) > 0.f;
@@ -647,6 +892,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
       }
     }
     __syncthreads();
+    int unfinished = 0;
     for (int b = 0; b < B; ++b) unfinished += sm.fin[b] ? 0 : 1;
     if (blockIdx.x == 0) {
       if (a.update_state)
@@ -659,20 +905,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
         *a.st.n_unfinished = (*reinterpret_cast<volatile int*>(a.err) != 0) ? -1 : unfinished;
       }
     }
-    if (a.update_state && unfinished == 0) break;  // uniform: every CTA holds the same replica
+    if ((a.update_state && unfinished == 0) || s + 1 == a.n_steps) break;  // uniform across CTAs
+    if (threadIdx.x == 0) {
+      get_phase<DH>(a, 0, t + 1, qscale, *cur);
+      issue_weights(cur->g, sm);
+    }
+    __syncthreads();
   }
 }
 
 static size_t smem_bytes(const TtsDecoderWeights* w, int B) {
-  return (size_t)(2 * kRowBlk * kXLd + kWarps * kPass * 32 + 2 * kRowBlk * w->n_heads) * sizeof(float) +
-         (size_t)2 * B * sizeof(int) + 16;
+  return (size_t)(kXFloats + kWFloats + kWarps * kPass * 32 + 2 * kRowBlk * w->n_heads) * sizeof(float) +
+         (size_t)(3 + kWarps * kSlots) * sizeof(uint64_t) + (size_t)2 * B * sizeof(int) + 16;
 }
 
 struct Carve {
-  float *x, *q, *hid, *p0, *p1, *part;
+  float *x, *q, *ctx, *hid, *p0, *p1, *part;
   unsigned* bar;
   int* err;
-  int max_seg;
+  long long* prof;
   size_t floats;
 };
 
@@ -687,11 +938,14 @@ static int num_sms() {
   return n;
 }
 
+static int split_for(const TtsDecoderWeights* w, int B, int G) {
+  int ns = G / (B * w->n_heads);
+  return ns < 1 ? 1 : (ns > kMaxSplit ? kMaxSplit : ns);
+}
+
 static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
   Carve c;
   const size_t D = w->d_model, F = w->d_ffn, P = w->prenet_hidden, H = w->n_heads, dh = D / H;
-  const int G = base ? num_sms() : 160;  // size for the worst case when only sizing
-  c.max_seg = (int)((size_t)B * H / (base ? G : 132)) + 2;
   size_t off = 0;
   auto take = [&](size_t n) {
     float* p = base ? base + off : nullptr;
@@ -700,44 +954,64 @@ static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
   };
   c.bar = reinterpret_cast<unsigned*>(take(32));
   c.err = reinterpret_cast<int*>(take(32));
-  c.x = take(B * D); c.q = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
-  c.part = take((size_t)G * c.max_seg * (dh + 4));
+  c.prof = reinterpret_cast<long long*>(take(2 * 8 * kProfPhases));
+  c.x = take(B * D); c.q = take(B * D); c.ctx = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
+  const size_t splits = (size_t)B * H >= 132 ? 1 : kMaxSplit;
+  c.part = take((size_t)B * H * splits * (dh + 4));
   c.floats = off;
   return c;
 }
 
 template <int DH>
-static int launch(const Args& a, size_t smem, cudaStream_t s) {
+static int launch(const Args& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    TTS_CHECK_CUDA(cudaFuncSetAttribute(fused_decode_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(fused_decode_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     int per_sm = 0;
-    TTS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_decode_kernel<DH>, kThreads, 227 * 1024));
+    TTS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_decode_kernel<DH>, kThreads, 226 * 1024));
     TTS_REQUIRE(per_sm >= 1, "fused decode kernel does not fit on an SM");
     configured = true;
   }
   void* params[] = {const_cast<Args*>(&a)};
   TTS_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fused_decode_kernel<DH>), dim3(num_sms()),
-                                             dim3(kThreads), params, smem, s));
+                                             dim3(kThreads), params, smem_bytes(&a.w, a.st.batch), s));
   count_launch();
   return 0;
 }
 
 }  // namespace fused
 
+int fused_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries) {
+  using namespace fused;
+  const Carve c = carve(w, st->batch, st->scratch);
+  const int n = max_entries < 8 * kProfPhases ? max_entries : 8 * kProfPhases;
+  TTS_CHECK_CUDA(cudaMemcpy(out_host, c.prof, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 size_t fused_scratch_floats(const TtsDecoderWeights* w, int B) { return fused::carve(w, B, nullptr).floats; }
 
 bool fused_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   using namespace fused;
-  if (w->d_model > kKC || w->d_model % 128 != 0) return false;       // LayerNorm prologue tiling
+  if (w->d_model > kKC || w->d_model % 128 != 0) return false;   // LayerNorm prologue tiling
+  if (w->d_ffn % 16 != 0) return false;
+  if (w->prenet_hidden > kKC || w->n_mels > kKC) return false;
   if (st->batch > kMaxBatch) return false;
   const int dh = w->d_model / w->n_heads;
   if (dh != 32 && dh != 64 && dh != 96) return false;
+  // the widest weight slice of any phase must fit the shared-memory weight buffer
   const int G = num_sms();
-  const long long max_keys = st->t_max > st->mem_len ? st->t_max : st->mem_len;
-  const long long span = ((long long)st->batch * w->n_heads * max_keys + G - 1) / G;
-  if (span > 2LL * kRowBlk * kXLd) return false;                      // scores of one span live in shared memory
-  if (smem_bytes(w, st->batch) > 227 * 1024) return false;
+  auto slice = [&](long long N, long long K) { return ((N + G - 1) / G) * K; };
+  const long long D = w->d_model, F = w->d_ffn, P = w->prenet_hidden, M = w->n_mels;
+  long long worst = slice(3 * D, D);
+  worst = worst > slice(F, D) ? worst : slice(F, D);
+  worst = worst > slice(D, F) ? worst : slice(D, F);
+  worst = worst > slice(P, M) ? worst : slice(P, M);
+  worst = worst > slice(P, P) ? worst : slice(P, P);
+  worst = worst > slice(D, P) ? worst : slice(D, P);
+  if (worst > kWFloats) return false;
+  if ((long long)kWarps * kSlots * 2 * kTK * dh > kXFloats + kWFloats) return false;
+  if (smem_bytes(w, st->batch) > 226 * 1024) return false;
   return true;
 }
 
@@ -750,14 +1024,14 @@ int launch_fused_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int
   Args a;
   memcpy(&a.w, w, sizeof(*w));
   memcpy(&a.st, st, sizeof(*st));
-  a.x = c.x; a.q = c.q; a.hid = c.hid; a.p0 = c.p0; a.p1 = c.p1; a.part = c.part;
-  a.max_seg = c.max_seg; a.bar = c.bar; a.err = c.err; a.n_steps = n_steps; a.update_state = update_state;
+  a.x = c.x; a.q = c.q; a.ctx = c.ctx; a.hid = c.hid; a.p0 = c.p0; a.p1 = c.p1; a.part = c.part;
+  a.n_split = split_for(w, st->batch, num_sms());
+  a.bar = c.bar; a.err = c.err; a.prof = c.prof; a.n_steps = n_steps; a.update_state = update_state;
   TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, 256, s));  // barrier counter and error flag
-  const size_t smem = smem_bytes(w, st->batch);
   switch (w->d_model / w->n_heads) {
-    case 32: return launch<32>(a, smem, s);
-    case 64: return launch<64>(a, smem, s);
-    case 96: return launch<96>(a, smem, s);
+    case 32: return launch<32>(a, s);
+    case 64: return launch<64>(a, s);
+    case 96: return launch<96>(a, s);
   }
   set_error("fused decode: unsupported head_dim");
   return 2;

@@ -71,6 +71,7 @@ _EXPORTS = {
     "tts_decode_begin": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecodeState), C.c_void_p]),
     "tts_decode_steps": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecodeState), C.c_int32, C.c_void_p,
                                    C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "tts_decode_profile": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecodeState), C.c_void_p, C.c_int32]),
 }
 
 _lib = None

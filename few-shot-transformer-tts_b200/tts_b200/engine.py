@@ -88,6 +88,16 @@ class DecodeSession:
                 "decode_steps")
         self.t += n_steps
 
+    def phase_profile(self):
+        """[n_phases, 8] SM-clock stamps of CTA 0 for the last step: 0 start, 1 compute done, 2 barrier
+        passed; GEMM phases also 3 activations staged, 4 LayerNorm done, 5 weights landed, 6 FMA +
+        reduction done (last pass), 7 epilogue done (last pass)."""
+        n = 3 + 8 * self.engine.cfg.n_decoder_layer + 1
+        buf = (C.c_int64 * (8 * n))()
+        N.check(N.load().tts_decode_profile(C.byref(self.engine.decoder_weights()), C.byref(self._st), buf, 8 * n),
+                "decode_profile")
+        return np.array(list(buf), dtype=np.int64).reshape(n, 8)
+
     def alignments(self, t):
         """Views shaped like the reference's (attention.py:88): [B,H,T_kv,T_q] per layer."""
         out = {"self": [], "encdec": []}

@@ -190,6 +190,11 @@ int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32
                      const float* prev_mel, int64_t prev_mel_stride, int32_t update_state,
                      int32_t impl, void* stream);
 
+/* Diagnostics: SM-clock stamps {phase start, compute done, barrier passed} that CTA 0 of the fused
+ * kernel recorded for every phase of the last step it ran (synchronous device-to-host copy). */
+int tts_decode_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, int64_t* out_host,
+                       int32_t max_entries);
+
 #ifdef __cplusplus
 }
 #endif
