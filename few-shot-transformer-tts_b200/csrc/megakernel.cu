@@ -31,7 +31,7 @@ constexpr int kKC = 768;        // K slice of the activation staged in shared me
 constexpr int kChunksPerWarp = kKC / 16 / kWarps;  // 16-float chunks of a slice owned by one warp (6)
 constexpr int kRowBlk = 32;     // batch rows per activation tile
 constexpr int kPass = 8;        // weight rows per register pass
-constexpr int kXFloats = (kRowBlk + 2) * (kKC + 4);     // 32 activation rows + LayerNorm gamma and beta
+constexpr int kXFloats = kRowBlk * (kKC + 4);           // 32 activation rows
 constexpr int kWFloats = 19456;                         // 76 KB: <= 6 rows of K=3072, <= 25 rows of K=768
 constexpr int kTK = 8;          // keys per K/V ring tile
 constexpr int kSlots = 3;       // ring slots per warp
@@ -47,6 +47,7 @@ struct Args {
   TtsDecoderWeights w;
   TtsDecodeState st;
   float *x, *q, *ctx, *hid, *p0, *p1, *part;
+  float* stats;         // [B][G][2] per-CTA (mean, M2) of the rows of x over the CTA's columns
   int n_split;          // K/V splits per (sample, head): 1 when B*H >= #CTAs
   unsigned* bar;
   int* err;
@@ -63,6 +64,7 @@ struct Gemm {
   float* kcache; float* vcache;
   int comb_keys;
   float* align; long long align_bh_stride; int align_row_len;
+  int emit_stats;   // the output is the residual stream x: also publish per-row (mean, M2) over this CTA's columns
 };
 
 struct Attn {
@@ -82,6 +84,8 @@ struct Smem {
   float* ring;    // K/V rings (aliases xs + wb during attention phases)
   float* red;     // [8][8][32] GEMM cross-warp reduction / attention warp records
   float* ml;      // [32*H][2]
+  float* stat;    // [32][2]  (rstd, -mean*rstd) of the staged rows
+  float* sstat;   // [8][32]  epilogue values for the per-row statistics
   int* len;       // [B]
   int* fin;       // [B]
   uint64_t* wfull;     // 1
@@ -106,7 +110,9 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.ring = base;
   sm.red = sm.wb + kWFloats;
   sm.ml = sm.red + kWarps * kPass * 32;
-  sm.wfull = reinterpret_cast<uint64_t*>(sm.ml + 2 * kRowBlk * a.w.n_heads);
+  sm.stat = sm.ml + 2 * kRowBlk * a.w.n_heads;
+  sm.sstat = sm.stat + 2 * kRowBlk;
+  sm.wfull = reinterpret_cast<uint64_t*>(sm.sstat + kPass * 32);
   sm.xfull = sm.wfull + 1;
   sm.rfull = sm.wfull + 3;
   sm.len = reinterpret_cast<int*>(sm.rfull + kWarps * kSlots);
@@ -306,82 +312,66 @@ __device__ __noinline__ void stage_combined(const Args& a, const Gemm& g, const 
   }
 }
 
-// LayerNorm of the 32 staged rows, in place.  gamma / beta were staged as rows 32 / 33 of the tile.  Warp w
-// normalises rows w, w+12, w+24 with their reductions interleaved.
-__device__ __forceinline__ void stage_ln_coef(float* Xs, int ld, int K, const float* gam, const float* bet) {
-  const int nf4 = K >> 2;
-  for (int i = threadIdx.x; i < 2 * nf4; i += kThreads) {
-    if (i < nf4) cp_async16(Xs + kRowBlk * ld + 4 * i, gam + 4 * i);
-    else cp_async16(Xs + (kRowBlk + 1) * ld + 4 * (i - nf4), bet + 4 * (i - nf4));
-  }
-}
-__device__ __forceinline__ void ln_inplace(float* Xs, int ld, int K) {
-  constexpr int RW = (kRowBlk + kWarps - 1) / kWarps;  // rows per warp (3)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nf4 = K >> 2;
-  const float invK = 1.f / (float)K;
-  const float* gam = Xs + kRowBlk * ld;
-  const float* bet = gam + ld;
-  float mean[RW], rstd[RW];
+// LayerNorm without a pass over the tile.  gamma / beta are folded into the packed weights (W_ln, c_ln); the
+// phase that produced x published, per CTA, the (mean, M2) of every row over that CTA's columns.  Here warp w
+// merges the G records of rows 4w..4w+3 (Chan's parallel variance) into (rstd, -mean * rstd); the
+// normalisation itself is applied when the fragments are loaded into registers.
+__device__ __forceinline__ void row_stats(const Args& a, const Smem& sm, int b0, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, G = gridDim.x, B = a.st.batch;
+  constexpr int E = 5;                      // records per lane (G <= 160)
+  constexpr int RW = kRowBlk / kWarps;      // rows per warp (4)
+  float cnt[E];
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    const int row = min(warp + kWarps * r, kRowBlk - 1);
+  for (int e = 0; e < E; ++e) {             // columns of x owned by CTA c = lane + 32 e (32-bit math on purpose)
+    const unsigned c = lane + 32 * e;
+    cnt[e] = c < (unsigned)G ? (float)(((c + 1u) * (unsigned)D) / (unsigned)G - (c * (unsigned)D) / (unsigned)G) : 0.f;
+  }
+  float2 rec[RW][E];
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {         // all loads first: one L2 round trip for the whole warp
+    const int b = b0 + warp * RW + rr;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      rec[rr][e] = make_float2(0.f, 0.f);
+      if (b < B && cnt[e] > 0.f)
+        rec[rr][e] = __ldcg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * G + lane + 32 * e);
+    }
+  }
+  float mean[RW], m2[RW];
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int f = lane + 32 * j;
-      if (f < nf4) {
-        const float4 v = *reinterpret_cast<const float4*>(Xs + row * ld + 4 * f);
-        s += (v.x + v.y) + (v.z + v.w);
-      }
-    }
-    mean[r] = s;
+    for (int e = 0; e < E; ++e) s += cnt[e] * rec[rr][e].x;
+    mean[rr] = s;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int r = 0; r < RW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    for (int rr = 0; rr < RW; ++rr) mean[rr] += __shfl_xor_sync(0xffffffffu, mean[rr], o);
+  const float invD = 1.f / (float)D;
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    const int row = min(warp + kWarps * r, kRowBlk - 1);
-    mean[r] *= invK;
+  for (int rr = 0; rr < RW; ++rr) {
+    mean[rr] *= invD;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int f = lane + 32 * j;
-      if (f < nf4) {
-        const float4 v = *reinterpret_cast<const float4*>(Xs + row * ld + 4 * f);
-        const float dx = v.x - mean[r], dy = v.y - mean[r], dz = v.z - mean[r], dw = v.w - mean[r];
-        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-      }
+    for (int e = 0; e < E; ++e) {
+      const float d = rec[rr][e].x - mean[rr];
+      q += rec[rr][e].y + cnt[e] * d * d;
     }
-    rstd[r] = q;
+    m2[rr] = q;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int r = 0; r < RW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    for (int rr = 0; rr < RW; ++rr) m2[rr] += __shfl_xor_sync(0xffffffffu, m2[rr], o);
+  if (lane == 0) {
 #pragma unroll
-  for (int r = 0; r < RW; ++r) {
-    const int row = warp + kWarps * r;
-    if (row < kRowBlk) {  // warp-uniform
-      const float rs = rsqrtf(rstd[r] * invK + 1e-6f);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int f = lane + 32 * j;
-        if (f < nf4) {
-          float* px = Xs + row * ld + 4 * f;
-          const float4 v = *reinterpret_cast<const float4*>(px);
-          const float4 g4 = *reinterpret_cast<const float4*>(gam + 4 * f);
-          const float4 b4 = *reinterpret_cast<const float4*>(bet + 4 * f);
-          float4 o;
-          o.x = (v.x - mean[r]) * rs * g4.x + b4.x;
-          o.y = (v.y - mean[r]) * rs * g4.y + b4.y;
-          o.z = (v.z - mean[r]) * rs * g4.z + b4.z;
-          o.w = (v.w - mean[r]) * rs * g4.w + b4.w;
-          *reinterpret_cast<float4*>(px) = o;
-        }
-      }
+    for (int rr = 0; rr < RW; ++rr) {
+      const int r = warp * RW + rr;
+      const float rstd = b0 + r < B ? rsqrtf(m2[rr] * invD + 1e-6f) : 0.f;
+      sm.stat[2 * r] = rstd;
+      sm.stat[2 * r + 1] = -mean[rr] * rstd;
     }
   }
 }
@@ -392,16 +382,33 @@ __device__ __forceinline__ void ln_inplace(float* Xs, int ld, int K) {
 struct XFrag {
   f32x4 v[kChunksPerWarp][4];
 };
-__device__ __forceinline__ void load_xfrag(XFrag& xf, const float* Xs, int ld, int kc) {
+template <bool NORM>
+__device__ __forceinline__ void load_xfrag(XFrag& xf, const float* Xs, int ld, int kc, const float* stat) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, s4 = (lane & 3) * 4, nch = kc >> 4;
+  f32x2 sc[4], sh[4];
+  if (NORM) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 st = *reinterpret_cast<const float2*>(stat + 2 * (4 * g + i));
+      sc[i] = pack2(st.x, st.x);
+      sh[i] = pack2(st.y, st.y);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < kChunksPerWarp; ++j) {
     const int c = warp + kWarps * j;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (c < nch) xf.v[j][i] = ld4s(Xs + (4 * g + i) * ld + c * 16 + s4);
-      else xf.v[j][i].lo = xf.v[j][i].hi = 0ull;
+      if (c < nch) {
+        xf.v[j][i] = ld4s(Xs + (4 * g + i) * ld + c * 16 + s4);
+        if (NORM) {  // (x - mean) * rstd
+          xf.v[j][i].lo = fma2(xf.v[j][i].lo, sc[i], sh[i]);
+          xf.v[j][i].hi = fma2(xf.v[j][i].hi, sc[i], sh[i]);
+        }
+      } else {
+        xf.v[j][i].lo = xf.v[j][i].hi = 0ull;
+      }
     }
   }
 }
@@ -452,16 +459,12 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
       } else {
         const bool from_frames = g.xsrc == kXFrames;
         const float* X = from_frames ? a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * a.w.n_mels : g.X;
-        if (LN) stage_ln_coef(sm.xs, ld, g.K, g.ln_g, g.ln_b);
         stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
       }
+      if (LN) row_stats(a, sm, b0, g.K);  // overlaps the flight of the tile
       cp_async_wait_all();
       __syncthreads();
       stamp(tk, 3);
-      if (LN) {
-        ln_inplace(sm.xs, ld, g.K);
-        __syncthreads();
-      }
       stamp(tk, 4);
     }
     if (!has_rows) continue;
@@ -487,7 +490,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
       {
         XFrag xf;  // activation fragments live only while the products run
         if (n_kc == 1) {
-          load_xfrag(xf, sm.xs, ld, g.K);
+          load_xfrag<LN>(xf, sm.xs, ld, g.K, sm.stat);
           fma_rows(acc, xf, g.K, wb, g.K, nrows, 0);
         } else {  // K > 768 (FFN-out): the next slice streams into shared memory while this one is multiplied
           stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
@@ -495,7 +498,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
             const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
             cp_async_wait_all();
             __syncthreads();
-            load_xfrag(xf, sm.xs, ld, kc);
+            load_xfrag<false>(xf, sm.xs, ld, kc, sm.stat);
             __syncthreads();  // every warp holds its fragments: the tile may be refilled
             if (ki + 1 < n_kc) stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
             fma_rows(acc, xf, kc, wb, g.K, nrows, k0);
@@ -538,7 +541,9 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
         if (g.relu) v = fmaxf(v, 0.f);
         switch (g.mode) {
           case kPlain: {
-            g.Y[(size_t)b * g.ldy + n] = v * g.out_scale + e_res;
+            v = v * g.out_scale + e_res;
+            g.Y[(size_t)b * g.ldy + n] = v;
+            if (g.emit_stats) sm.sstat[r * 32 + br] = v;
           } break;
           case kQkv: {
             const int H = a.w.n_heads, D = H * DH;
@@ -553,7 +558,9 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
           } break;
           case kPrenetOut: {  // modules.py:114-118
             const bool have = t > 0 && (t - 1) < sm.len[b];
-            g.Y[(size_t)b * g.ldy + n] = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * g.N + n) * __ldg(a.w.pe_scale);
+            v = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * g.N + n) * __ldg(a.w.pe_scale);
+            g.Y[(size_t)b * g.ldy + n] = v;
+            if (g.emit_stats) sm.sstat[r * 32 + br] = v;
           } break;
           case kFinal: {  // modules.py:144, tacotron.py:112-115
             const bool live = t < sm.len[b];
@@ -563,6 +570,17 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
         }
       }
       __syncthreads();  // red is reused by the next pass
+      if (g.emit_stats && tid < 32 && b0 + tid < B) {  // (mean, M2) of row b over this CTA's columns (one pass: N <= 8 G)
+        float m = 0.f;
+        for (int rr = 0; rr < nrows; ++rr) m += sm.sstat[rr * 32 + tid];
+        m /= (float)nrows;
+        float m2 = 0.f;
+        for (int rr = 0; rr < nrows; ++rr) {
+          const float d = sm.sstat[rr * 32 + tid] - m;
+          m2 += d * d;
+        }
+        reinterpret_cast<float2*>(a.stats)[(size_t)(b0 + tid) * gridDim.x + blockIdx.x] = make_float2(m, m2);
+      }
       stamp(tk, 7);
     }
   }
@@ -759,10 +777,11 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
     g.mode = kPlain; g.Y = a.p1; g.ldy = P;
   } else if (ph == 2) {  // + shift / mask / PE (modules.py:114-118)
     g.X = a.p1; g.ldx = P; g.K = P; g.N = D; g.W = a.w.prenet_w2; g.n_w1 = D; g.mode = kPrenetOut; g.Y = a.x; g.ldy = D;
+    g.emit_stats = 1;
   } else if (ph == 3 + 8 * L) {  // final LN + mel / stop projections
     p.kind = 1;
-    g.X = a.x; g.ldx = D; g.K = D; g.N = M + 1; g.W = a.w.w_mel; g.W2 = a.w.w_stop; g.n_w1 = M;
-    g.ln_g = a.w.ln_out_g; g.ln_b = a.w.ln_out_b; g.mode = kFinal;
+    g.X = a.x; g.ldx = D; g.K = D; g.N = M + 1; g.W = a.w.w_mel_ln; g.W2 = a.w.w_stop_ln; g.n_w1 = M;
+    g.bias = a.w.c_out_ln; g.mode = kFinal;
   } else {
     const int l = (ph - 3) / 8, k = (ph - 3) % 8;
     const TtsDecLayerWeights& lw = a.w.layer[l];
@@ -772,8 +791,8 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
     switch (k) {
       case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
         p.kind = 1;
-        g.X = a.x; g.ldx = D; g.K = D; g.N = 3 * D; g.W = lw.w_qkv; g.n_w1 = 3 * D; g.ln_g = lw.ln_self_g;
-        g.ln_b = lw.ln_self_b; g.mode = kQkv; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = 3 * D; g.W = lw.w_qkv_ln; g.n_w1 = 3 * D; g.bias = lw.c_qkv_ln;
+        g.mode = kQkv; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
         g.kcache = a.st.self_k + self_off; g.vcache = a.st.self_v + self_off;
         break;
       case 1:
@@ -788,11 +807,12 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
           g.X = a.ctx; g.ldx = D;
         }
         g.K = D; g.N = D; g.W = lw.w_self_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        g.emit_stats = 1;
         break;
       case 3:  // LN + cross query
         p.kind = 1;
-        g.X = a.x; g.ldx = D; g.K = D; g.N = D; g.W = lw.w_cross_q; g.n_w1 = D; g.ln_g = lw.ln_cross_g;
-        g.ln_b = lw.ln_cross_b; g.mode = kPlain; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = D; g.W = lw.w_cross_q_ln; g.n_w1 = D; g.bias = lw.c_cross_q_ln;
+        g.mode = kPlain; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
         break;
       case 4:
         p.kind = 2;
@@ -806,15 +826,16 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
           g.X = a.ctx; g.ldx = D;
         }
         g.K = D; g.N = D; g.W = lw.w_cross_out; g.n_w1 = D; g.mode = kPlain; g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        g.emit_stats = 1;
         break;
       case 6:  // LN + FFN-in + ReLU (modules.py:14-17)
         p.kind = 1;
-        g.X = a.x; g.ldx = D; g.K = D; g.N = F; g.W = lw.w_ffn_in; g.n_w1 = F; g.ln_g = lw.ln_ffn_g; g.ln_b = lw.ln_ffn_b;
+        g.X = a.x; g.ldx = D; g.K = D; g.N = F; g.W = lw.w_ffn_in_ln; g.n_w1 = F; g.bias = lw.c_ffn_in_ln;
         g.relu = 1; g.mode = kPlain; g.Y = a.hid; g.ldy = F;
         break;
       default:  // FFN-out + residual
         g.X = a.hid; g.ldx = F; g.K = F; g.N = D; g.W = lw.w_ffn_out; g.n_w1 = D; g.mode = kPlain;
-        g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D;
+        g.Y = a.x; g.ldy = D; g.R = a.x; g.ldr = D; g.emit_stats = 1;
         break;
     }
   }
@@ -915,12 +936,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
 }
 
 static size_t smem_bytes(const TtsDecoderWeights* w, int B) {
-  return (size_t)(kXFloats + kWFloats + kWarps * kPass * 32 + 2 * kRowBlk * w->n_heads) * sizeof(float) +
+  return (size_t)(kXFloats + kWFloats + kWarps * kPass * 32 + 2 * kRowBlk * w->n_heads + 2 * kRowBlk + kPass * 32) *
+             sizeof(float) +
          (size_t)(3 + kWarps * kSlots) * sizeof(uint64_t) + (size_t)2 * B * sizeof(int) + 16;
 }
 
 struct Carve {
-  float *x, *q, *ctx, *hid, *p0, *p1, *part;
+  float *x, *q, *ctx, *hid, *p0, *p1, *part, *stats;
   unsigned* bar;
   int* err;
   long long* prof;
@@ -958,6 +980,7 @@ static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
   c.x = take(B * D); c.q = take(B * D); c.ctx = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
   const size_t splits = (size_t)B * H >= 132 ? 1 : kMaxSplit;
   c.part = take((size_t)B * H * splits * (dh + 4));
+  c.stats = take((size_t)B * 160 * 2);
   c.floats = off;
   return c;
 }
@@ -993,7 +1016,13 @@ size_t fused_scratch_floats(const TtsDecoderWeights* w, int B) { return fused::c
 
 bool fused_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   using namespace fused;
-  if (w->d_model > kKC || w->d_model % 128 != 0) return false;   // LayerNorm prologue tiling
+  if (w->d_model > kKC || w->d_model % 16 != 0) return false;
+  if (!w->w_mel_ln || !w->w_stop_ln || !w->c_out_ln) return false;   // packed LayerNorm-folded operands required
+  for (int l = 0; l < w->n_layers; ++l)
+    if (!w->layer[l].w_qkv_ln || !w->layer[l].c_qkv_ln || !w->layer[l].w_cross_q_ln || !w->layer[l].c_cross_q_ln ||
+        !w->layer[l].w_ffn_in_ln || !w->layer[l].c_ffn_in_ln)
+      return false;
+  if (num_sms() > 160 || w->d_model > kPass * num_sms()) return false;
   if (w->d_ffn % 16 != 0) return false;
   if (w->prenet_hidden > kKC || w->n_mels > kKC) return false;
   if (st->batch > kMaxBatch) return false;
@@ -1024,7 +1053,7 @@ int launch_fused_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int
   Args a;
   memcpy(&a.w, w, sizeof(*w));
   memcpy(&a.st, st, sizeof(*st));
-  a.x = c.x; a.q = c.q; a.ctx = c.ctx; a.hid = c.hid; a.p0 = c.p0; a.p1 = c.p1; a.part = c.part;
+  a.x = c.x; a.q = c.q; a.ctx = c.ctx; a.hid = c.hid; a.p0 = c.p0; a.p1 = c.p1; a.part = c.part; a.stats = c.stats;
   a.n_split = split_for(w, st->batch, num_sms());
   a.bar = c.bar; a.err = c.err; a.prof = c.prof; a.n_steps = n_steps; a.update_state = update_state;
   TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, 256, s));  // barrier counter and error flag

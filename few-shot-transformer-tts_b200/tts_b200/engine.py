@@ -183,6 +183,34 @@ class TtsEngine:
             lw.ln_ffn_g, lw.ln_ffn_b = g(f"{p}ffn_layer_norms.{l}.weight"), g(f"{p}ffn_layer_norms.{l}.bias")
             lw.w_ffn_in = g(f"{p}ffn_layers.{l}.input_layer.weight")
             lw.w_ffn_out = g(f"{p}ffn_layers.{l}.output_layer.weight")
+        # LayerNorm folded into the projection that follows it (packed operands of the fused kernel)
+        keep = []
+
+        def fold(wname, gname, bname):
+            with torch.no_grad():
+                wt, gam, bet = w[wname].detach(), w[gname].detach(), w[bname].detach()
+                wf = (wt * gam[None, :]).contiguous()
+                cf = (wt @ bet).contiguous()
+            keep.extend([wf, cf])
+            return wf, cf
+
+        for l in range(cfg.n_decoder_layer):
+            lw = dw.layer[l]
+            wf, cf = fold(f"{p}self_attentions.{l}.qkv_transform.weight", f"{p}attn_layer_norms.{l}.weight",
+                          f"{p}attn_layer_norms.{l}.bias")
+            lw.w_qkv_ln, lw.c_qkv_ln = wf.data_ptr(), cf.data_ptr()
+            wf, cf = fold(f"{p}encdec_attentions.{l}.q_transform.weight", f"{p}encdec_layer_norms.{l}.weight",
+                          f"{p}encdec_layer_norms.{l}.bias")
+            lw.w_cross_q_ln, lw.c_cross_q_ln = wf.data_ptr(), cf.data_ptr()
+            wf, cf = fold(f"{p}ffn_layers.{l}.input_layer.weight", f"{p}ffn_layer_norms.{l}.weight",
+                          f"{p}ffn_layer_norms.{l}.bias")
+            lw.w_ffn_in_ln, lw.c_ffn_in_ln = wf.data_ptr(), cf.data_ptr()
+        wm, cm = fold("decoder.mel_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
+        ws, cs = fold("decoder.stop_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
+        cout = torch.cat([cm, cs]).contiguous()
+        keep.append(cout)
+        dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr()
+        self._dec_keep = keep  # owns the packed tensors for as long as the struct is cached
         self._dec_w, self._dec_key = dw, key
         return dw
 

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 3
+#define TTS_ABI_VERSION 4
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -131,6 +131,15 @@ typedef struct TtsDecLayerWeights {
   const float* ln_ffn_b;
   const float* w_ffn_in;    /* ...ffn_layers.{l}.input_layer.weight  [4D][D] */
   const float* w_ffn_out;   /* ...ffn_layers.{l}.output_layer.weight [D][4D] */
+  /* Derived ("packed") operands of the fused kernel: the LayerNorm in front of a projection folded into it,
+   * W_ln = W * diag(gamma) and c_ln = W * beta, so that LN(x) W^T = ((x - mean) * rstd) W_ln^T + c_ln.
+   * Rebuilt by the host whenever W / gamma / beta change; NULL = fused kernel unavailable. */
+  const float* w_qkv_ln;     /* [3D][D] */
+  const float* c_qkv_ln;     /* [3D] */
+  const float* w_cross_q_ln; /* [D][D] */
+  const float* c_cross_q_ln; /* [D] */
+  const float* w_ffn_in_ln;  /* [4D][D] */
+  const float* c_ffn_in_ln;  /* [4D] */
 } TtsDecLayerWeights;
 
 typedef struct TtsDecoderWeights {
@@ -147,6 +156,9 @@ typedef struct TtsDecoderWeights {
   const float* w_mel;       /* decoder.mel_net.weight [M][D] */
   const float* w_stop;      /* decoder.stop_net.weight [1][D] */
   const float* b_stop;      /* decoder.stop_net.bias [1] */
+  const float* w_mel_ln;    /* [M][D]  mel_net with the output LayerNorm folded in (see TtsDecLayerWeights) */
+  const float* w_stop_ln;   /* [1][D] */
+  const float* c_out_ln;    /* [M+1]   W_mel * beta_out, w_stop * beta_out */
   TtsDecLayerWeights layer[TTS_MAX_LAYERS];
 } TtsDecoderWeights;
 
