@@ -53,6 +53,13 @@ def decode_bytes(cfg, batch, mem_len, n_steps, elem=4):
     return total
 
 
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 55.06e9   # profiles/r1_fused_ncu_raw.csv (round 1)
+
+
+def decode_bytes_range(cfg, batch, mem_len, t0, t1, elem=4):
+    return decode_bytes(cfg, batch, mem_len, t1, elem) - decode_bytes(cfg, batch, mem_len, t0, elem)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -288,14 +295,18 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     alg_bytes = decode_bytes(cfg, args.batch, args.text_len, args.frames)
     achieved = alg_bytes / dec_secs / 1e9
-    n_launch = max(1, args.frames // args.chunk) if args.decode_impl in (0, 3) else args.frames
-    roofline = {"bound": "hbm", "kernel": "decode step (all phases of %d steps)" % args.frames,
+    # one launch of the fused kernel = `chunk` decode steps; report the average launch
+    n_launch = max(1, -(-args.frames // args.chunk)) if args.decode_impl in (0, 3) else args.frames
+    roofline = {"bound": "hbm", "kernel": "fused_decode_kernel (one launch = %d decode steps; %d launches per job)"
+                % (args.chunk, n_launch) if args.decode_impl in (0, 3) else "decode step (per-phase kernels)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes": alg_bytes, "decode_seconds": dec_secs,
-                "us_per_decode_step": 1e6 * dec_secs / args.frames,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (args.decode_impl in (0, 3) and args.chunk == 50
+                                                            and args.frames == 1000 and args.batch == 32) else None,
+                "traffic_note": "dram__bytes_read+write of the launch covering t=475..524 (profiles/README.md); "
+                                "algorithmic bytes of that launch: %.3e" % decode_bytes_range(cfg, args.batch, args.text_len, 475, 525),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / n_launch,
+                "launch_seconds": dec_secs / n_launch, "us_per_decode_step": 1e6 * dec_secs / args.frames,
                 "share_of_job": dec_secs / (secs / args.steps)}
-    del n_launch
 
     line = None
     if rank == 0:
@@ -331,7 +342,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--chunk", type=int, default=50, help="decode steps per launch / host poll")
     ap.add_argument("--decode-impl", type=int, default=0, help="0 default, 1 per-phase kernels, 2 CUDA graph, 3 fused")
-    ap.add_argument("--ref-horizon", type=int, default=40, help="frames of the CPU reference sample")
+    ap.add_argument("--ref-horizon", type=int, default=96, help="frames of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

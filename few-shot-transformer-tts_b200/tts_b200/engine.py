@@ -190,7 +190,7 @@ class TtsEngine:
             with torch.no_grad():
                 wt, gam, bet = w[wname].detach(), w[gname].detach(), w[bname].detach()
                 wf = (wt * gam[None, :]).contiguous()
-                cf = (wt @ bet).contiguous()
+                cf = ops.linear(bet[None, :].contiguous(), wt.contiguous()).view(-1)
             keep.extend([wf, cf])
             return wf, cf
 

@@ -12,13 +12,13 @@ from tts_b200.engine import TtsEngine  # noqa: E402
 B = int(os.environ.get("PB", "32"))
 T0 = int(os.environ.get("PT", "200"))
 NS = int(os.environ.get("PN", "2"))
-cfg = O.ModelConfig(max_generation_frames=256)
+cfg = O.ModelConfig(max_generation_frames=int(os.environ.get("PTMAX", "256")))
 params = O.synth_params(cfg, seed=0)
 params["decoder.stop_net.bias"] = torch.tensor([-1e4])
 eng = TtsEngine.from_state_dict(params, cfg, "cuda:0")
 batch = O.synth_batch(cfg, batch=B, text_len=258, n_frames=4, seed=1)
 mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
-sess = eng.new_session(B, 258, 256, "encdec")
+sess = eng.new_session(B, 258, cfg.max_generation_frames, "encdec")
 sess.begin(mem, batch["input_lengths"].cuda())
 sess.step(T0)
 torch.cuda.synchronize()
