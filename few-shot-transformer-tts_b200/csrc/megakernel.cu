@@ -72,10 +72,15 @@ struct Attn {
   float* align; long long align_bh_stride; int align_row_len;
 };
 
+struct Prefetch {   // slice [part/parts) of the first `rows` K/V rows of each item this CTA will attend over
+  const float* kc; const float* vc; int rows_alloc, rows, part, parts;
+};
+
 struct Phase {
   int kind;  // 0 gemm, 1 gemm with LayerNorm prologue, 2 attention
   Gemm g;
   Attn at;
+  Prefetch pre;
 };
 
 struct Smem {
@@ -182,8 +187,10 @@ struct GridBar {
   unsigned epoch, n;
 };
 
-__device__ __forceinline__ void bar_arrive(GridBar& gb) {
-  fence_proxy_async();  // this thread's global writes -> visible to other CTAs' bulk (async-proxy) reads
+__device__ __forceinline__ void bar_arrive(GridBar& gb, bool async_readers) {
+  // global writes of this phase that another CTA will read through the async proxy (TMA bulk copies of the
+  // freshly appended K/V row) need a cross-proxy fence; cp.async / ld readers do not
+  if (async_readers) fence_proxy_async();
   __syncthreads();
   if (threadIdx.x == 0)
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
@@ -204,10 +211,29 @@ __device__ __forceinline__ void bar_wait(GridBar& gb) {
         break;
       }
     }
-    __threadfence();
-    fence_proxy_async();
   }
   __syncthreads();
+}
+
+// Ask the memory system to pull K/V rows this CTA will stream in an upcoming attention phase into L2 while the
+// current (FMA-bound) GEMM phases leave HBM idle.  Pure hint: correctness never depends on it.
+__device__ __forceinline__ void prefetch_l2(const float* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+template <int DH>
+__device__ __forceinline__ void prefetch_kv(const Args& a, const Prefetch& pf) {
+  if (pf.kc == nullptr || a.n_split != 1 || pf.rows <= 0) return;
+  const int n_items = a.st.batch * a.w.n_heads, G = gridDim.x;
+  // keep the total under ~80 MB so that it survives in the 126 MB L2 until it is used
+  const long long cap = (80ll << 20) / ((long long)n_items * DH * 8);
+  const int r = (int)min((long long)pf.rows, cap > 1 ? cap : 1);
+  const int r0 = (int)(((long long)r * pf.part) / pf.parts), r1 = (int)(((long long)r * (pf.part + 1)) / pf.parts);
+  const int i = (int)threadIdx.x - 32;  // warp 1, lanes 0..7: (unit, K|V)
+  if (i < 0 || i >= 8 || r1 <= r0) return;
+  const int item = blockIdx.x + G * (i >> 1);
+  if (item >= n_items) return;
+  const float* base = ((i & 1) ? pf.vc : pf.kc) + ((size_t)item * pf.rows_alloc + r0) * DH;
+  prefetch_l2(base, (unsigned)(r1 - r0) * DH * 4u);
 }
 
 // ---- GEMM phase -------------------------------------------------------------------------------------
@@ -437,8 +463,8 @@ __device__ __forceinline__ void fma_rows(f32x2 (&acc)[kPass][4], const XFrag& xf
 }
 
 template <bool LN, int DH>
-__device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* smem_base, unsigned w_par, long long* prof,
-                                        int t) {
+__device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const Prefetch& pf, float* smem_base,
+                                           unsigned w_par, long long* prof, int t) {
   const Smem sm = make_smem(a, smem_base);
   Track tk{w_par, 0u, 0u, prof};
   const int B = a.st.batch;
@@ -446,7 +472,10 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
   slice_rows(g, n_lo, n_hi);
   const bool has_rows = n_hi > n_lo;
   const bool owns_align = g.xsrc == kXCombine && g.align != nullptr;
-  if (!has_rows && !owns_align) return;
+  if (!has_rows && !owns_align) {
+    prefetch_kv<DH>(a, pf);
+    return;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ld = min(g.K, kKC) + 4;
   const int n_kc = (g.K + kKC - 1) / kKC;
@@ -465,6 +494,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
       cp_async_wait_all();
       __syncthreads();
       stamp(tk, 3);
+      if (b0 == 0) prefetch_kv<DH>(a, pf);  // HBM is idle while the products run
       stamp(tk, 4);
     }
     if (!has_rows) continue;
@@ -493,6 +523,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, float* 
           load_xfrag<LN>(xf, sm.xs, ld, g.K, sm.stat);
           fma_rows(acc, xf, g.K, wb, g.K, nrows, 0);
         } else {  // K > 768 (FFN-out): the next slice streams into shared memory while this one is multiplied
+          if (b0 == 0 && n0 == n_lo) prefetch_kv<DH>(a, pf);
           stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
           for (int ki = 0; ki < n_kc; ++ki) {
             const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
@@ -769,6 +800,23 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
   memset(&g, 0, sizeof(g));
   g.out_scale = 1.f;
   p.kind = 0;
+  p.pre.kc = nullptr;
+  {  // which K/V stream to pull into L2 behind this phase's products (self: the t rows written so far)
+    const int k = ph >= 3 ? (ph - 3) % 8 : -1, l = ph >= 3 ? (ph - 3) / 8 : -1;
+    int self_layer = -1, part = 0;
+    if (ph < 3) { self_layer = 0; part = ph; }
+    else if (ph < 3 + 8 * L && k == 0) { self_layer = l; part = 3; }
+    else if (ph < 3 + 8 * L && k >= 5 && l + 1 < L) { self_layer = l + 1; part = k - 5; }
+    if (self_layer >= 0) {
+      const size_t off = (size_t)self_layer * B * H * T * DH;
+      p.pre.kc = a.st.self_k + off; p.pre.vc = a.st.self_v + off; p.pre.rows_alloc = T; p.pre.rows = t;
+      p.pre.part = part; p.pre.parts = 4;
+    } else if (ph >= 3 && ph < 3 + 8 * L && (k == 2 || k == 3)) {
+      const size_t off = (size_t)l * B * H * S * DH;
+      p.pre.kc = a.st.cross_k + off; p.pre.vc = a.st.cross_v + off; p.pre.rows_alloc = S; p.pre.rows = S;
+      p.pre.part = k - 2; p.pre.parts = 2;
+    }
+  }
   if (ph == 0) {         // prenet (tacotron.py:55-65)
     g.xsrc = kXFrames; g.ldx = (long long)T * M; g.K = M; g.N = P; g.W = a.w.prenet_w0; g.n_w1 = P;
     g.bias = a.w.prenet_b0; g.relu = 1; g.mode = kPlain; g.Y = a.p0; g.ldy = P;
@@ -883,15 +931,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
       if (cur->kind == 2) {
         ring_count = attn_phase<DH>(a, cur->at, smem_raw, ring_count, prof, t);
       } else {
-        if (cur->kind == 1) gemm_phase<true, DH>(a, cur->g, smem_raw, w_par, prof, t);
-        else gemm_phase<false, DH>(a, cur->g, smem_raw, w_par, prof, t);
+        if (cur->kind == 1) gemm_phase<true, DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
+        else gemm_phase<false, DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
         int n_lo, n_hi;
         slice_rows(cur->g, n_lo, n_hi);
         if (n_hi > n_lo) w_par ^= 1u;  // this CTA consumed one completion of the weight barrier
       }
       const bool last = ph == n_phases - 1;
       if (prof) prof[1] = clock64();
-      bar_arrive(gb);
+      bar_arrive(gb, cur->kind == 1 && cur->g.mode == kQkv);
       if (!last && threadIdx.x == 0) {  // the next phase's weights stream in while we wait for the other CTAs
         get_phase<DH>(a, ph + 1, t, qscale, *nxt);
         if (nxt->kind != 2) issue_weights(nxt->g, sm);
