@@ -64,6 +64,7 @@ struct Gemm {
   float* kcache; float* vcache;
   int comb_keys;
   float* align; long long align_bh_stride; int align_row_len;
+  int ln;           // input rows are normalised with the statistics published by the producing phase
   int emit_stats;   // the output is the residual stream x: also publish per-row (mean, M2) over this CTA's columns
 };
 
@@ -408,12 +409,14 @@ __device__ __forceinline__ void row_stats(const Args& a, const Smem& sm, int b0,
 struct XFrag {
   f32x4 v[kChunksPerWarp][4];
 };
-template <bool NORM>
+// `stat` holds (scale, shift) per row: (rstd, -mean * rstd) for a LayerNorm-folded phase, (1, 0) otherwise
+// (a runtime choice keeps a single copy of this code: the kernel is instruction-fetch sensitive).
 __device__ __forceinline__ void load_xfrag(XFrag& xf, const float* Xs, int ld, int kc, const float* stat) {
+  constexpr bool NORM = true;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, s4 = (lane & 3) * 4, nch = kc >> 4;
   f32x2 sc[4], sh[4];
-  if (NORM) {
+  {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 st = *reinterpret_cast<const float2*>(stat + 2 * (4 * g + i));
@@ -462,7 +465,7 @@ __device__ __forceinline__ void fma_rows(f32x2 (&acc)[kPass][4], const XFrag& xf
   }
 }
 
-template <bool LN, int DH>
+template <int DH>
 __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const Prefetch& pf, float* smem_base,
                                            unsigned w_par, long long* prof, int t) {
   const Smem sm = make_smem(a, smem_base);
@@ -477,6 +480,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
     return;
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool LN = g.ln != 0;
   const int ld = min(g.K, kKC) + 4;
   const int n_kc = (g.K + kKC - 1) / kKC;
   bool w_ready = !has_rows;
@@ -490,7 +494,12 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
         const float* X = from_frames ? a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * a.w.n_mels : g.X;
         stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
       }
-      if (LN) row_stats(a, sm, b0, g.K);  // overlaps the flight of the tile
+      if (LN) {
+        row_stats(a, sm, b0, g.K);  // overlaps the flight of the tile
+      } else if (tid < kRowBlk) {
+        sm.stat[2 * tid] = 1.f;
+        sm.stat[2 * tid + 1] = 0.f;
+      }
       cp_async_wait_all();
       __syncthreads();
       stamp(tk, 3);
@@ -519,21 +528,26 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
         for (int i = 0; i < 4; ++i) acc[r][i] = 0ull;
       {
         XFrag xf;  // activation fragments live only while the products run
-        if (n_kc == 1) {
-          load_xfrag<LN>(xf, sm.xs, ld, g.K, sm.stat);
-          fma_rows(acc, xf, g.K, wb, g.K, nrows, 0);
-        } else {  // K > 768 (FFN-out): the next slice streams into shared memory while this one is multiplied
+        if (n_kc > 1) {  // K > 768 (FFN-out): slices stream through the tile, starting here
           if (b0 == 0 && n0 == n_lo) prefetch_kv<DH>(a, pf);
+          if (tid < kRowBlk) {
+            sm.stat[2 * tid] = 1.f;
+            sm.stat[2 * tid + 1] = 0.f;
+          }
           stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
-          for (int ki = 0; ki < n_kc; ++ki) {
-            const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
+        }
+        for (int ki = 0; ki < n_kc; ++ki) {
+          const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
+          if (n_kc > 1) {
             cp_async_wait_all();
             __syncthreads();
-            load_xfrag<false>(xf, sm.xs, ld, kc, sm.stat);
-            __syncthreads();  // every warp holds its fragments: the tile may be refilled
-            if (ki + 1 < n_kc) stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
-            fma_rows(acc, xf, kc, wb, g.K, nrows, k0);
           }
+          load_xfrag(xf, sm.xs, ld, kc, sm.stat);
+          if (n_kc > 1) {
+            __syncthreads();  // every warp holds its fragments: the tile may be refilled while they are multiplied
+            if (ki + 1 < n_kc) stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
+          }
+          fma_rows(acc, xf, kc, wb, g.K, nrows, k0);
         }
       }
       {  // packed pairs -> reduce-scatter over the 4 k-split lanes (each ends up owning 2 weight rows x 4
@@ -635,6 +649,9 @@ __device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, fl
   float* ring = sm.ring + (size_t)warp * kSlots * kSlotF;
   uint64_t* full = sm.rfull + warp * kSlots;
   float* wrec = sm.red;  // [8][PS]
+  float* sc = sm.ring + (size_t)kWarps * kSlots * kSlotF;            // raw logits of the current unit
+  constexpr int kScCap = kXFloats + kWFloats - kWarps * kSlots * kSlotF;
+  const bool sc_ok = per <= kScCap;                                   // else fall back to read-modify-write in HBM
 
   // ---- producer cursor (next tile this warp will request) ----
   int pu = blockIdx.x, pi = warp;
@@ -664,6 +681,9 @@ __device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, fl
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) issue_next();
 
+  f32x4 qnext[F4];
+#pragma unroll
+  for (int i = 0; i < F4; ++i) qnext[i].lo = qnext[i].hi = 0ull;
   for (int u = blockIdx.x; u < n_units; u += G) {
     const int item = ns == 1 ? u : u / ns, split = u - item * ns;
     const int j0 = min(n_keys, split * per), j1 = min(n_keys, j0 + per);
@@ -672,8 +692,18 @@ __device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, fl
     float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
 
     f32x4 qv[F4];
+    if (u == (int)blockIdx.x) {
 #pragma unroll
-    for (int i = 0; i < F4; ++i) qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+      for (int i = 0; i < F4; ++i) qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < F4; ++i) qv[i] = qnext[i];
+    }
+    if (u + G < n_units) {  // latency of the next unit's query hides behind this unit's stream
+      const int nitem = ns == 1 ? u + G : (u + G) / ns;
+#pragma unroll
+      for (int i = 0; i < F4; ++i) qnext[i] = ld4cg(a.q + (size_t)nitem * DH + 4 * (l8 + 8 * i));
+    }
     float m_run = -CUDART_INF_F, l_run = 0.f;
     f32x2 o[F4][2];
 #pragma unroll
@@ -704,7 +734,10 @@ __device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, fl
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         if (kl >= nk) v = -CUDART_INF_F;                 // stale smem beyond the tile's keys
         else if (key0 + kl >= klen) v = kNegBias;        // logits + (-1e20), attention.py:84-85
-        if (kl < nk && l8 == 0 && arow != nullptr) arow[key0 + kl] = v;  // raw logit, normalised below
+        if (kl < nk && l8 == 0 && arow != nullptr) {  // raw logit, normalised once the unit's (max, sum) is known
+          if (ns == 1 && sc_ok) sc[key0 + kl - j0] = v;
+          else arow[key0 + kl] = v;
+        }
         s[r] = v;
         mt = fmaxf(mt, v);
       }
@@ -780,7 +813,8 @@ __device__ __forceinline__ unsigned attn_phase(const Args& a, const Attn& at, fl
     if (ns == 1) {
       if (arow != nullptr) {
         const float inv = 1.f / l;
-        for (int j = j0 + tid; j < j1; j += kThreads) arow[j] = expf(arow[j] - m) * inv;
+        if (sc_ok) for (int j = j0 + tid; j < j1; j += kThreads) arow[j] = expf(sc[j - j0] - m) * inv;
+        else for (int j = j0 + tid; j < j1; j += kThreads) arow[j] = expf(arow[j] - m) * inv;
       }
     } else if (tid == 0) {
       a.part[(size_t)u * PS + DH] = m;       // -inf when the split is empty
@@ -827,7 +861,7 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
     g.X = a.p1; g.ldx = P; g.K = P; g.N = D; g.W = a.w.prenet_w2; g.n_w1 = D; g.mode = kPrenetOut; g.Y = a.x; g.ldy = D;
     g.emit_stats = 1;
   } else if (ph == 3 + 8 * L) {  // final LN + mel / stop projections
-    p.kind = 1;
+    p.kind = 1; g.ln = 1;
     g.X = a.x; g.ldx = D; g.K = D; g.N = M + 1; g.W = a.w.w_mel_ln; g.W2 = a.w.w_stop_ln; g.n_w1 = M;
     g.bias = a.w.c_out_ln; g.mode = kFinal;
   } else {
@@ -838,7 +872,7 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
     float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
     switch (k) {
       case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
-        p.kind = 1;
+        p.kind = 1; g.ln = 1;
         g.X = a.x; g.ldx = D; g.K = D; g.N = 3 * D; g.W = lw.w_qkv_ln; g.n_w1 = 3 * D; g.bias = lw.c_qkv_ln;
         g.mode = kQkv; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
         g.kcache = a.st.self_k + self_off; g.vcache = a.st.self_v + self_off;
@@ -858,7 +892,7 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
         g.emit_stats = 1;
         break;
       case 3:  // LN + cross query
-        p.kind = 1;
+        p.kind = 1; g.ln = 1;
         g.X = a.x; g.ldx = D; g.K = D; g.N = D; g.W = lw.w_cross_q_ln; g.n_w1 = D; g.bias = lw.c_cross_q_ln;
         g.mode = kPlain; g.Y = a.q; g.ldy = D; g.out_scale = qscale;
         break;
@@ -877,7 +911,7 @@ __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qs
         g.emit_stats = 1;
         break;
       case 6:  // LN + FFN-in + ReLU (modules.py:14-17)
-        p.kind = 1;
+        p.kind = 1; g.ln = 1;
         g.X = a.x; g.ldx = D; g.K = D; g.N = F; g.W = lw.w_ffn_in_ln; g.n_w1 = F; g.bias = lw.c_ffn_in_ln;
         g.relu = 1; g.mode = kPlain; g.Y = a.hid; g.ldy = F;
         break;
@@ -931,8 +965,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
       if (cur->kind == 2) {
         ring_count = attn_phase<DH>(a, cur->at, smem_raw, ring_count, prof, t);
       } else {
-        if (cur->kind == 1) gemm_phase<true, DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
-        else gemm_phase<false, DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
+        gemm_phase<DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
         int n_lo, n_hi;
         slice_rows(cur->g, n_lo, n_hi);
         if (n_hi > n_lo) w_par ^= 1u;  // this CTA consumed one completion of the weight barrier
