@@ -18,6 +18,7 @@
 // Reference semantics: transformer/tacotron.py:107-116, transformer/modules.py:108-145,
 // transformer/attention.py:53-122, synthesize.py:35-45.
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -53,6 +54,7 @@ struct Args {
   int* err;
   long long* prof;      // [kProfPhases][8] SM clock stamps of CTA 0 for the last step run (diagnostics)
   int n_steps, update_state;
+  int cluster2;         // launched as 2-CTA clusters: activation tiles are TMA-multicast to both CTAs of a pair
 };
 
 struct Gemm {
@@ -157,6 +159,19 @@ __device__ __forceinline__ void bulk_g2s(float* dst, const float* src, unsigned 
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// same, delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(float* dst, const float* src, unsigned bytes, uint64_t* bar, unsigned short mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // 128-bit loads the compiler is free to hoist and batch (the asm-volatile helpers of common.cuh pin the
 // program order, which exposed the full shared-memory latency per weight row)
@@ -277,6 +292,28 @@ __device__ __forceinline__ void stage_rows(float* Xs, int ld, const float* X, lo
       *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Cluster variant: the two CTAs of a pair need the same tile, so each fetches half of the rows ONCE from L2 and
+// the TMA engine multicasts them into both CTAs' shared memory (halves the L2 broadcast traffic of a GEMM phase).
+// Completion is counted on each CTA's own `bar`, which expects the whole tile.
+__device__ __forceinline__ void stage_rows_mc(float* Xs, int ld, const float* X, long long ldx, int B, int b0, int kc,
+                                              uint64_t* bar, bool zero_all) {
+  const int nvalid = zero_all ? 0 : min(kRowBlk, B - b0);
+  if (nvalid < kRowBlk) {
+    const int f4 = kc >> 2;
+    for (int i = threadIdx.x; i < (kRowBlk - nvalid) * f4; i += kThreads) {
+      const int r = nvalid + i / f4, c = (i % f4) << 2;
+      *reinterpret_cast<float4*>(Xs + r * ld + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)nvalid * (unsigned)kc * 4u);
+    __syncwarp();
+    const int r = (int)cluster_ctarank() * (kRowBlk / 2) + (int)threadIdx.x;  // lanes 0..15: this CTA's half
+    if (threadIdx.x < kRowBlk / 2 && r < nvalid)
+      bulk_g2s_mc(Xs + r * ld, X + (size_t)(b0 + r) * ldx, (unsigned)kc * 4u, bar, (unsigned short)0x3);
+  }
 }
 
 // Merge split-K/V attention partials into the [32][D] context tile (only when n_split > 1, i.e. small batches)
@@ -467,7 +504,7 @@ __device__ __forceinline__ void fma_rows(f32x2 (&acc)[kPass][4], const XFrag& xf
 
 template <int DH>
 __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const Prefetch& pf, float* smem_base,
-                                           unsigned w_par, long long* prof, int t) {
+                                           unsigned w_par, unsigned x_par, long long* prof, int t) {
   const Smem sm = make_smem(a, smem_base);
   Track tk{w_par, 0u, 0u, prof};
   const int B = a.st.batch;
@@ -484,6 +521,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
   const int ld = min(g.K, kKC) + 4;
   const int n_kc = (g.K + kKC - 1) / kKC;
   bool w_ready = !has_rows;
+  bool mc = false;
 
   for (int b0 = 0; b0 < B; b0 += kRowBlk) {
     if (n_kc == 1) {  // the whole K fits one tile: stage (+ LayerNorm) once, every pass re-reads it
@@ -492,7 +530,12 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
       } else {
         const bool from_frames = g.xsrc == kXFrames;
         const float* X = from_frames ? a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * a.w.n_mels : g.X;
-        stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
+        if (a.cluster2 && g.N >= (int)gridDim.x && B <= kRowBlk) {
+          stage_rows_mc(sm.xs, ld, X, g.ldx, B, b0, g.K, &sm.xfull[0], from_frames && t == 0);
+          mc = true;
+        } else {
+          stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
+        }
       }
       if (LN) {
         row_stats(a, sm, b0, g.K);  // overlaps the flight of the tile
@@ -500,7 +543,8 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
         sm.stat[2 * tid] = 1.f;
         sm.stat[2 * tid + 1] = 0.f;
       }
-      cp_async_wait_all();
+      if (mc) mbar_wait(&sm.xfull[0], x_par, a.err);
+      else cp_async_wait_all();
       __syncthreads();
       stamp(tk, 3);
       if (b0 == 0) prefetch_kv<DH>(a, pf);  // HBM is idle while the products run
@@ -932,7 +976,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
   const int B = a.st.batch, T = a.st.t_max;
   const int n_phases = 3 + 8 * a.w.n_layers + 1;
   GridBar gb{a.bar, a.err, 0u, gridDim.x};
-  unsigned w_par = 0u, ring_count = 0u;
+  unsigned w_par = 0u, ring_count = 0u, x_par = 0u;
   const float qscale = (float)(1.0 / sqrt((double)DH));
 
   if (threadIdx.x == 0) {
@@ -944,6 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
     sm.fin[b] = a.st.finished[b];
   }
   __syncthreads();
+  if (a.cluster2) cluster_sync_all();  // the partner's mbarriers exist before anything is multicast into them
   const int t0 = *a.st.step_counter;
 
   // phase descriptors live in shared memory (one copy per CTA, written by thread 0): per-thread copies
@@ -965,10 +1010,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
       if (cur->kind == 2) {
         ring_count = attn_phase<DH>(a, cur->at, smem_raw, ring_count, prof, t);
       } else {
-        gemm_phase<DH>(a, cur->g, cur->pre, smem_raw, w_par, prof, t);
+        gemm_phase<DH>(a, cur->g, cur->pre, smem_raw, w_par, x_par, prof, t);
         int n_lo, n_hi;
         slice_rows(cur->g, n_lo, n_hi);
         if (n_hi > n_lo) w_par ^= 1u;  // this CTA consumed one completion of the weight barrier
+        if (a.cluster2 && cur->g.N >= (int)gridDim.x && B <= kRowBlk && cur->g.K <= kKC && cur->g.xsrc != kXCombine)
+          x_par ^= 1u;                 // ... and one of the multicast tile barrier
       }
       const bool last = ph == n_phases - 1;
       if (prof) prof[1] = clock64();
@@ -1014,6 +1061,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
     }
     __syncthreads();
   }
+  if (a.cluster2) cluster_sync_all();  // nobody leaves while the partner could still write into its shared memory
 }
 
 static size_t smem_bytes(const TtsDecoderWeights* w, int B) {
@@ -1076,9 +1124,43 @@ static int launch(const Args& a, cudaStream_t s) {
     TTS_REQUIRE(per_sm >= 1, "fused decode kernel does not fit on an SM");
     configured = true;
   }
-  void* params[] = {const_cast<Args*>(&a)};
+  static int cluster_ok = -1;  // -1 unknown, 0 no, 1 yes
+  Args args = a;
+  const size_t smem = smem_bytes(&a.w, a.st.batch);
+  if (cluster_ok != 0 && num_sms() % 2 == 0 && getenv("TTS_NO_CLUSTER") == nullptr) {
+    args.cluster2 = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(num_sms());
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = 2;
+    attrs[1].val.clusterDim.y = 1;
+    attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, fused_decode_kernel<DH>, args);
+    if (e == cudaSuccess) {
+      cluster_ok = 1;
+      count_launch();
+      return 0;
+    }
+    if (cluster_ok == 1) {
+      set_error("fused decode: cluster launch failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    (void)cudaGetLastError();  // first attempt failed: this device/driver cannot co-schedule 2-CTA clusters cooperatively
+    cluster_ok = 0;
+  }
+  args.cluster2 = 0;
+  void* params[] = {&args};
   TTS_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(fused_decode_kernel<DH>), dim3(num_sms()),
-                                             dim3(kThreads), params, smem_bytes(&a.w, a.st.batch), s));
+                                             dim3(kThreads), params, smem, s));
   count_launch();
   return 0;
 }
