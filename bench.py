@@ -141,6 +141,8 @@ def cpu_reference_sample(batch_size, text_len, horizon, repeats=1):
     """The oracle's faithful restatement of synthesize.eval_batch (re-runs the decoder over all
     frames so far each step), B x text_len, truncated to `horizon` frames.  Returns frames/s."""
     from oracle import tts_oracle as O
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     cfg = O.ModelConfig()
     params = O.synth_params(cfg, seed=0)
     params["decoder.stop_net.bias"] = torch.tensor([-1e4])
@@ -159,6 +161,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     threads = torch.get_num_threads()
     horizon = args.ref_horizon
     steps_fps = []

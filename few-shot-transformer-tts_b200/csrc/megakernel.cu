@@ -297,8 +297,8 @@ __device__ __forceinline__ void stage_rows(float* Xs, int ld, const float* X, lo
 // Cluster variant: the two CTAs of a pair need the same tile, so each fetches half of the rows ONCE from L2 and
 // the TMA engine multicasts them into both CTAs' shared memory (halves the L2 broadcast traffic of a GEMM phase).
 // Completion is counted on each CTA's own `bar`, which expects the whole tile.
-__device__ __forceinline__ void stage_rows_mc(float* Xs, int ld, const float* X, long long ldx, int B, int b0, int kc,
-                                              uint64_t* bar, bool zero_all) {
+__device__ __forceinline__ void stage_rows_mc(float* Xs, int ld, const float* X, long long ldx, int B, int b0, int k0,
+                                              int kc, uint64_t* bar, bool zero_all) {
   const int nvalid = zero_all ? 0 : min(kRowBlk, B - b0);
   if (nvalid < kRowBlk) {
     const int f4 = kc >> 2;
@@ -312,7 +312,7 @@ __device__ __forceinline__ void stage_rows_mc(float* Xs, int ld, const float* X,
     __syncwarp();
     const int r = (int)cluster_ctarank() * (kRowBlk / 2) + (int)threadIdx.x;  // lanes 0..15: this CTA's half
     if (threadIdx.x < kRowBlk / 2 && r < nvalid)
-      bulk_g2s_mc(Xs + r * ld, X + (size_t)(b0 + r) * ldx, (unsigned)kc * 4u, bar, (unsigned short)0x3);
+      bulk_g2s_mc(Xs + r * ld, X + (size_t)(b0 + r) * ldx + k0, (unsigned)kc * 4u, bar, (unsigned short)0x3);
   }
 }
 
@@ -531,7 +531,7 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
         const bool from_frames = g.xsrc == kXFrames;
         const float* X = from_frames ? a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * a.w.n_mels : g.X;
         if (a.cluster2 && g.N >= (int)gridDim.x && B <= kRowBlk) {
-          stage_rows_mc(sm.xs, ld, X, g.ldx, B, b0, g.K, &sm.xfull[0], from_frames && t == 0);
+          stage_rows_mc(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, &sm.xfull[0], from_frames && t == 0);
           mc = true;
         } else {
           stage_rows(sm.xs, ld, X, g.ldx, B, b0, 0, g.K, from_frames && t == 0);
@@ -572,24 +572,39 @@ __device__ __forceinline__ void gemm_phase(const Args& a, const Gemm& g, const P
         for (int i = 0; i < 4; ++i) acc[r][i] = 0ull;
       {
         XFrag xf;  // activation fragments live only while the products run
+        const bool mcs = a.cluster2 && g.N >= (int)gridDim.x && B <= kRowBlk;  // multicast the slices to the CTA pair
+        unsigned xp = x_par;
         if (n_kc > 1) {  // K > 768 (FFN-out): slices stream through the tile, starting here
           if (b0 == 0 && n0 == n_lo) prefetch_kv<DH>(a, pf);
           if (tid < kRowBlk) {
             sm.stat[2 * tid] = 1.f;
             sm.stat[2 * tid + 1] = 0.f;
           }
-          stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
+          if (mcs) stage_rows_mc(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, &sm.xfull[0], false);
+          else stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, 0, kKC, false);
         }
         for (int ki = 0; ki < n_kc; ++ki) {
           const int k0 = ki * kKC, kc = min(kKC, g.K - k0);
           if (n_kc > 1) {
-            cp_async_wait_all();
+            if (mcs) {
+              mbar_wait(&sm.xfull[0], xp, a.err);
+              xp ^= 1u;
+            } else {
+              cp_async_wait_all();
+            }
             __syncthreads();
           }
           load_xfrag(xf, sm.xs, ld, kc, sm.stat);
           if (n_kc > 1) {
-            __syncthreads();  // every warp holds its fragments: the tile may be refilled while they are multiplied
-            if (ki + 1 < n_kc) stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, min(kKC, g.K - k0 - kKC), false);
+            // every warp (of both CTAs when multicasting) holds its fragments: the tile may be refilled while
+            // they are multiplied
+            if (mcs) cluster_sync_all();
+            else __syncthreads();
+            if (ki + 1 < n_kc) {
+              const int kn = min(kKC, g.K - k0 - kKC);
+              if (mcs) stage_rows_mc(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, kn, &sm.xfull[0], false);
+              else stage_rows(sm.xs, ld, g.X, g.ldx, B, b0, k0 + kKC, kn, false);
+            }
           }
           fma_rows(acc, xf, kc, wb, g.K, nrows, k0);
         }
@@ -1014,8 +1029,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_decode_kernel(const __grid_
         int n_lo, n_hi;
         slice_rows(cur->g, n_lo, n_hi);
         if (n_hi > n_lo) w_par ^= 1u;  // this CTA consumed one completion of the weight barrier
-        if (a.cluster2 && cur->g.N >= (int)gridDim.x && B <= kRowBlk && cur->g.K <= kKC && cur->g.xsrc != kXCombine)
-          x_par ^= 1u;                 // ... and one of the multicast tile barrier
+        if (a.cluster2 && cur->g.N >= (int)gridDim.x && B <= kRowBlk && cur->g.xsrc != kXCombine) {
+          // ... and completions of the multicast tile barrier: one per K slice and pass
+          const int slices = (cur->g.K + kKC - 1) / kKC;
+          const int passes = slices > 1 ? (n_hi - n_lo + kPass - 1) / kPass : 1;
+          if ((slices * passes) & 1) x_par ^= 1u;
+        }
       }
       const bool last = ph == n_phases - 1;
       if (prof) prof[1] = clock64();

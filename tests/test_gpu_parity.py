@@ -264,7 +264,8 @@ def test_full_autoregressive_vs_reference_golden(full_params, golden_dir, ops, i
     assert _err(got["alignments"]["self"][0][:, :, :, T - 1], torch.from_numpy(z["align_self_l0"])) < 1e-4
 
 
-@pytest.mark.parametrize("B,split_note", [(1, "split-KV over 32 CTAs per head"), (3, "split-KV"), (32, "one CTA per head")])
+@pytest.mark.parametrize("B,split_note", [(1, "split-KV over 18 CTAs per head"), (3, "split-KV"), (32, "one CTA per head"),
+                                          (40, "two row blocks, second one partial"), (64, "two full row blocks")])
 def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_note):
     """Decode at several batch sizes (different split-KV factors), 24 steps, vs the cached oracle."""
     cfg, params = full_params
