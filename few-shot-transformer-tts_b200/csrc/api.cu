@@ -13,6 +13,7 @@ namespace tts {
 
 static thread_local char g_error[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_last_impl{0};   // implementation the last tts_decode_steps call ran (tts_decode_profile reads its stamps)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -32,6 +33,12 @@ int launch_fused_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int
 size_t fused_scratch_floats(const TtsDecoderWeights* w, int B);
 bool fused_supported(const TtsDecoderWeights* w, const TtsDecodeState* st);
 int fused_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries);
+// pipelined.cu
+int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
+                           cudaStream_t s);
+size_t pipelined_scratch_floats(const TtsDecoderWeights* w, int B);
+bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st);
+int pipelined_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries);
 
 // ---- CUDA graph cache: one captured step per (weights, state, flags) -------------------------
 struct GraphEntry {
@@ -127,8 +134,10 @@ extern "C" size_t tts_decode_scratch_bytes(const TtsDecoderWeights* w, int32_t b
   (void)mem_len;
   (void)t_max;
   if (!w || batch <= 0) return 0;
-  const size_t a = decode_scratch_floats(w, batch), b = fused_scratch_floats(w, batch);
-  return (a > b ? a : b) * sizeof(float) + 256;
+  const size_t a = decode_scratch_floats(w, batch), b = fused_scratch_floats(w, batch),
+               c = pipelined_scratch_floats(w, batch);
+  const size_t m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+  return m * sizeof(float) + 256;
 }
 
 extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void* stream) {
@@ -156,6 +165,7 @@ extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState
 extern "C" int tts_decode_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, int64_t* out_host,
                                   int32_t max_entries) {
   TTS_REQUIRE(w && st && out_host && max_entries > 0, "decode_profile: bad arguments");
+  if (g_last_impl == 4) return pipelined_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
   return fused_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
 }
 
@@ -168,7 +178,9 @@ extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState
   TTS_REQUIRE(prev_mel == nullptr, "decode_steps: external prev_mel is not supported; copy the frame into st->frames");
   (void)prev_mel_stride;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 0) impl = fused_supported(w, st) ? 3 : 2;
+  if (impl == 0) impl = pipelined_supported(w, st) ? 4 : (fused_supported(w, st) ? 3 : 2);
+  g_last_impl = impl;
+  if (impl == 4) return launch_pipelined_steps(w, st, n_steps, update_state, s);
   if (impl == 3) return launch_fused_steps(w, st, n_steps, update_state, s);
   if (impl == 1) {
     for (int i = 0; i < n_steps; ++i)

@@ -1,0 +1,1081 @@
+// Pipelined persistent decode kernel (impl 4, the default): ONE cooperative launch runs `n_steps` whole decode
+// steps with one CTA per SM, like megakernel.cu, but the step is software-pipelined over ROW GROUPS of the batch
+// so that the latency of the grid-wide dependency between phases (barrier + activation broadcast, ~2 us measured,
+// profiles/r2_microbench.txt) hides behind the work of the other group(s):
+//
+//   * the batch is cut into groups of <= 16 rows (one m16 MMA tile).  Every (phase, group) pair has its own
+//     grid-barrier counter: group g of phase p only waits for group g of phase p-1, so while the last CTAs
+//     finish (p, g) everybody else already works on (p, g+1) or (p+1, g-1).
+//   * warp specialisation: 8 consumer warps compute; a 9th producer warp polls the barrier counters, stages the
+//     next activation tile with 1-D TMA bulk copies (one mbarrier, one slot: the consumers pull the tile into
+//     registers and release the slot at once) and streams the NEXT phase's weight slice into the half of the
+//     weight region the current phase does not use.
+//   * products run on the legacy tensor-core path: mma.sync m16n8k8 TF32 with the 3-term split
+//     (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate) which keeps fp32-class accuracy (parity 1e-3 on mel
+//     frames needs it; a single TF32 pass does not).  tcgen05 needs M >= 64 per CTA; a CTA owns 5-21 weight
+//     rows here, so the 128-row tensor-memory path would waste > 80 % of every instruction.
+//   * LayerNorm is applied in the epilogue: y = rstd * (W_ln x) - rstd * mean * rowsum(W_ln) + c_ln, the row
+//     statistics are computed by the consumers from the fragments they already hold (no pass over the tile).
+//   * FFN-out (K = 3072) is split 4-way along K across CTAs (each CTA then stages the same 16 x 768 tile shape as
+//     every other phase instead of 16 x 3072) and a short reduce phase adds the four partials to the residual.
+//   * attention phases are megakernel.cu's per-warp TMA rings over the K/V streams (online softmax), per group.
+//
+// Reference semantics: transformer/tacotron.py:107-116, transformer/modules.py:108-145,
+// transformer/attention.py:53-122, synthesize.py:35-45.
+#include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tts {
+namespace pipe {
+
+constexpr int kCWarps = 8;                 // consumer warps
+constexpr int kConsumers = kCWarps * 32;   // 256
+constexpr int kThreads = kConsumers + 32;  // + producer warp
+constexpr int kGroupRows = 16;             // batch rows per group (one m16 tile)
+constexpr int kKC = 768;                   // widest K slice of an activation tile / weight row in shared memory
+constexpr int kPad = 16;                   // floats of padding per shared-memory row (bank spread of LDS.128)
+constexpr int kLdMax = kKC + kPad;
+constexpr int kMaxRows = 24;               // weight rows per CTA and phase (3 n-tiles of 8)
+constexpr int kChunks = kKC / 16 / kCWarps;             // 16-float K chunks per warp (6)
+constexpr int kXsFloats = kGroupRows * kLdMax;          // activation slot
+constexpr int kWFloats = 2 * kMaxRows * kLdMax;         // weight region: two phases in flight
+constexpr int kRedFloats = kCWarps * kGroupRows * kMaxRows;
+constexpr int kTK = 8;                     // keys per K/V ring tile
+constexpr int kSlots = 2;                  // ring slots per warp
+constexpr int kMaxBatch = 1024;
+constexpr int kMaxGroups = 64;
+constexpr int kMaxSplit = 32;
+constexpr int kDescRing = 4;
+constexpr long long kSpinLimit = 1LL << 22;
+constexpr int kProfPhases = 160;
+
+enum Kind { kGemm = 0, kAttn = 1, kReduce = 2, kCombine = 3 };
+enum Mode { kPlain = 0, kQkv = 1, kPrenetOut = 2, kFinal = 3, kPartial = 4 };
+
+struct Args {
+  TtsDecoderWeights w;
+  TtsDecodeState st;
+  float *x, *q, *ctx, *hid, *p0, *p1, *part, *fpart;
+  unsigned* bar;        // [kMaxGroups] counters, 32 words apart
+  int* err;
+  long long* prof;
+  int n_steps, update_state;
+  int group_rows, n_groups, n_split, ksplit;
+};
+
+struct Desc {
+  int kind;
+  // ---- GEMM: Y[b][n] = epilogue(sum_k X[b][k] W[n][k]) for the rows of one group
+  const float* X; long long ldx; int K, N, ksplit;
+  const float* W; const float* W2; int n_w1; int ldw;   // W2: rows >= n_w1 come from a second matrix (mel | stop)
+  const float* bias; const float* lnsum;
+  int ln, relu, mode, hi, zero_x;
+  float* Y; long long ldy; const float* R; long long ldr; float out_scale;
+  float* kcache; float* vcache;
+  // ---- attention over a K/V stream
+  const float* kc; const float* vc; int rows_alloc, n_keys; const int32_t* key_len;
+  float* align; long long align_bh_stride; int align_row_len;
+  int ring_floats;      // shared memory the rings + logits may use (the next phase's weights sit above it)
+  // ---- reduce: Y[b][n] += sum_s part[s][b][n]
+  const float* part; int n_parts;
+};
+
+struct Smem {
+  float* xs;       // activation slot [16][ld]
+  float* wreg;     // weight region; K/V rings + logits during attention phases
+  float* red;      // [8][16][24] cross-warp reduction / attention warp records
+  float* spart;    // [8][16][2] LayerNorm partial (sum, sum of squares) about the row's first element
+  float* sshift;   // [16]
+  int* len;        // [B]
+  int* fin;        // [B]
+  uint64_t* x_full;   // 1: producer -> consumers, tile landed / group may start
+  uint64_t* x_empty;  // 1: consumers -> producer, slot free (8 arrivals)
+  uint64_t* w_full;   // 2: weight slice landed (low / high placement)
+  uint64_t* pdone;    // 1: consumers finished a phase
+  uint64_t* rfull;    // [8][kSlots] ring slots
+  Desc* desc;         // [kDescRing]
+};
+
+__host__ __device__ inline size_t smem_floats_fixed() {
+  return (size_t)kXsFloats + kWFloats + kRedFloats + kCWarps * kGroupRows * 2 + kGroupRows;
+}
+static size_t smem_bytes(int B) {
+  return smem_floats_fixed() * sizeof(float) + (size_t)2 * B * sizeof(int) + (5 + kCWarps * kSlots) * sizeof(uint64_t) +
+         kDescRing * sizeof(Desc) + 64;
+}
+
+__device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
+  Smem sm;
+  sm.xs = base;
+  sm.wreg = sm.xs + kXsFloats;
+  sm.red = sm.wreg + kWFloats;
+  sm.spart = sm.red + kRedFloats;
+  sm.sshift = sm.spart + kCWarps * kGroupRows * 2;
+  sm.len = reinterpret_cast<int*>(sm.sshift + kGroupRows);
+  sm.fin = sm.len + a.st.batch;
+  uintptr_t p = reinterpret_cast<uintptr_t>(sm.fin + a.st.batch);
+  p = (p + 15) & ~(uintptr_t)15;
+  sm.x_full = reinterpret_cast<uint64_t*>(p);
+  sm.x_empty = sm.x_full + 1;
+  sm.w_full = sm.x_full + 2;
+  sm.pdone = sm.x_full + 4;
+  sm.rfull = sm.x_full + 5;
+  sm.desc = reinterpret_cast<Desc*>(sm.rfull + kCWarps * kSlots + 1);
+  return sm;
+}
+
+// ---- primitives -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, int* err) {
+  long long spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    ++spins;
+    if ((spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(err) != 0)) {
+      atomicExch(err, 2);  // never hang the GPU
+      break;
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ f32x4 ld4s(const float* p) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f32x4 r;
+  r.lo = pack2(v.x, v.y);
+  r.hi = pack2(v.z, v.w);
+  return r;
+}
+__device__ __forceinline__ f32x4 ld4cg(const float* p) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  f32x4 r;
+  r.lo = pack2(v.x, v.y);
+  r.hi = pack2(v.z, v.w);
+  return r;
+}
+
+// TF32 split: x = hi + lo with hi, lo representable in TF32 (10-bit mantissa); hi*hi + hi*lo + lo*hi recovers
+// the fp32 product to ~2^-21 relative
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- per-group grid barrier ---------------------------------------------------------------------------
+__device__ __forceinline__ void grid_arrive(const Args& a, int g) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar + 32 * g) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const Args& a, int g, unsigned target) {
+  const unsigned* ctr = a.bar + 32 * g;
+  long long spins = 0;
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (static_cast<int>(v - target) >= 0) break;
+    ++spins;
+    if ((spins & 1023) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+      atomicExch(a.err, 1);
+      break;
+    }
+  }
+}
+
+// ---- work split of a GEMM phase over the CTAs -----------------------------------------------------------
+struct Slice {
+  int n_lo, n_hi, k_lo, kc, ks;
+};
+__device__ __forceinline__ Slice slice_of(const Desc& d, int c, int G) {
+  Slice s;
+  if (d.ksplit <= 1) {
+    s.ks = 0;
+    s.n_lo = (int)(((long long)c * d.N) / G);
+    s.n_hi = (int)(((long long)(c + 1) * d.N) / G);
+    s.k_lo = 0;
+    s.kc = d.K;
+  } else {  // CTA c works on K slice c % ksplit; the CTAs of one slice share the N rows
+    s.ks = c % d.ksplit;
+    const int i = c / d.ksplit, nc = (G - s.ks + d.ksplit - 1) / d.ksplit;
+    s.n_lo = (int)(((long long)i * d.N) / nc);
+    s.n_hi = (int)(((long long)(i + 1) * d.N) / nc);
+    s.kc = d.K / d.ksplit;
+    s.k_lo = s.ks * s.kc;
+  }
+  return s;
+}
+__device__ __forceinline__ float* weight_base(const Smem& sm, const Desc& d, const Slice& s) {
+  const int ld = s.kc + kPad;
+  const int tiles = (s.n_hi - s.n_lo + 7) >> 3;
+  return d.hi ? sm.wreg + kWFloats - tiles * 8 * ld : sm.wreg;
+}
+
+// ---- producer side ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void issue_weights(const Smem& sm, const Desc& d) {
+  const Slice s = slice_of(d, blockIdx.x, gridDim.x);
+  if (s.n_hi <= s.n_lo) return;
+  const int ld = s.kc + kPad;
+  float* dst = weight_base(sm, d, s);
+  const unsigned row_bytes = (unsigned)s.kc * 4u;
+  uint64_t* bar = &sm.w_full[d.hi];
+  mbar_expect_tx(bar, (unsigned)(s.n_hi - s.n_lo) * row_bytes);
+  for (int n = s.n_lo; n < s.n_hi; ++n) {
+    const float* src = (n < d.n_w1 ? d.W + (size_t)n * d.ldw : d.W2 + (size_t)(n - d.n_w1) * d.ldw) + s.k_lo;
+    bulk_g2s(dst + (size_t)(n - s.n_lo) * ld, src, row_bytes, bar);
+  }
+}
+
+__device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const Desc& d, int g) {
+  const Slice s = slice_of(d, blockIdx.x, gridDim.x);
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, a.st.batch - b0);
+  if (d.kind != kGemm || d.zero_x || s.n_hi <= s.n_lo || rows <= 0) {
+    mbar_arrive(sm.x_full);
+    return;
+  }
+  const int ld = s.kc + kPad;
+  const unsigned row_bytes = (unsigned)s.kc * 4u;
+  mbar_expect_tx(sm.x_full, (unsigned)rows * row_bytes);
+  for (int r = 0; r < rows; ++r)
+    bulk_g2s(sm.xs + r * ld, d.X + (size_t)(b0 + r) * d.ldx + s.k_lo, row_bytes, sm.x_full);
+}
+
+// ---- GEMM group-phase (consumers) --------------------------------------------------------------------------
+struct CState {
+  unsigned gp;            // group-phases consumed so far (parity of x_full)
+  unsigned wpar[2];       // parity of the two weight barriers
+  unsigned issued, consumed;  // K/V ring tiles of this warp
+};
+
+template <int DH>
+__device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const Smem& sm, CState& cs, int g, int t,
+                                           bool first_group) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int B = a.st.batch;
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
+  const Slice s = slice_of(d, blockIdx.x, gridDim.x);
+  const bool has_rows = s.n_hi > s.n_lo;
+  const int ld = s.kc + kPad, nch = s.kc >> 4;
+  const int ncols = s.n_hi - s.n_lo, NT = (ncols + 7) >> 3;
+
+  // ---- activation fragments: rows gq and gq+8, floats 4tq..4tq+3 of the 16-float chunks {warp, warp+8, ...}
+  float4 xa[kChunks][2];
+  float sh0 = 0.f, sh1 = 0.f;
+  const bool live = has_rows && !d.zero_x;
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int c = warp + kCWarps * j;
+    if (live && c < nch) {
+      xa[j][0] = lds4(sm.xs + gq * ld + c * 16 + 4 * tq);
+      xa[j][1] = lds4(sm.xs + (gq + 8) * ld + c * 16 + 4 * tq);
+    } else {
+      xa[j][0] = xa[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (live && d.ln) {
+    sh0 = sm.xs[gq * ld];
+    sh1 = sm.xs[(gq + 8) * ld];
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sm.x_empty);   // the tile lives in registers now: the producer may refill the slot
+  if (!has_rows) return;
+
+  // operands of the epilogue are requested now so that their latency hides behind the products
+  float e_res[2], e_bias[2], e_lns[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = tid + kConsumers * k, row = idx / kMaxRows, nl = idx - row * kMaxRows;
+    const bool on = row < rows && nl < ncols;
+    e_res[k] = (on && d.R) ? __ldcg(d.R + (size_t)(b0 + row) * d.ldr + s.n_lo + nl) : 0.f;
+    e_bias[k] = (on && d.bias) ? __ldg(d.bias + s.n_lo + nl) : 0.f;
+    e_lns[k] = (on && d.ln) ? __ldg(d.lnsum + s.n_lo + nl) : 0.f;
+  }
+
+  if (d.ln) {  // partial row statistics about the row's first element (plain sums merge exactly like the products)
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+      if (warp + kCWarps * j < nch) {
+        const float v0[4] = {xa[j][0].x, xa[j][0].y, xa[j][0].z, xa[j][0].w};
+        const float v1[4] = {xa[j][1].x, xa[j][1].y, xa[j][1].z, xa[j][1].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d0 = v0[e] - sh0, d1 = v1[e] - sh1;
+          s0 += d0; q0 = fmaf(d0, d0, q0);
+          s1 += d1; q1 = fmaf(d1, d1, q1);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    if (tq == 0) {
+      *reinterpret_cast<float2*>(sm.spart + (warp * kGroupRows + gq) * 2) = make_float2(s0, q0);
+      *reinterpret_cast<float2*>(sm.spart + (warp * kGroupRows + gq + 8) * 2) = make_float2(s1, q1);
+      if (warp == 0) {
+        sm.sshift[gq] = sh0;
+        sm.sshift[gq + 8] = sh1;
+      }
+    }
+  }
+
+  if (first_group) {
+    mbar_wait(&sm.w_full[d.hi], cs.wpar[d.hi], a.err);
+    cs.wpar[d.hi] ^= 1u;
+  }
+
+  // ---- products: C[16 rows][8 NT cols] += A (activations) x B (weight rows), 3 x TF32
+  float acc[3][2][4];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][h][i] = 0.f;
+  const float* wb = weight_base(sm, d, s) + gq * ld + 4 * tq;
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int c = warp + kCWarps * j;
+    if (c < nch) {
+      uint32_t ah[8], al[8];
+      // logical k = tq <-> float 4tq (+2 for the second MMA), k = tq+4 <-> float 4tq+1 (+2); A and B agree
+      split_tf32(xa[j][0].x, ah[0], al[0]); split_tf32(xa[j][1].x, ah[1], al[1]);
+      split_tf32(xa[j][0].y, ah[2], al[2]); split_tf32(xa[j][1].y, ah[3], al[3]);
+      split_tf32(xa[j][0].z, ah[4], al[4]); split_tf32(xa[j][1].z, ah[5], al[5]);
+      split_tf32(xa[j][0].w, ah[6], al[6]); split_tf32(xa[j][1].w, ah[7], al[7]);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        if (nt < NT) {
+          const float4 wv = lds4(wb + nt * 8 * ld + c * 16);
+          uint32_t bh[4], bl[4];
+          split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
+          split_tf32(wv.z, bh[2], bl[2]); split_tf32(wv.w, bh[3], bl[3]);
+          mma_tf32(acc[nt][0], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], al[4], al[5], al[6], al[7], bh[2], bh[3]);
+          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
+          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
+        }
+      }
+    }
+  }
+  {  // fragments -> cross-warp buffer [warp][row][24]
+    float* rw = sm.red + warp * (kGroupRows * kMaxRows);
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      if (nt < NT) {
+        *reinterpret_cast<float2*>(rw + gq * kMaxRows + nt * 8 + 2 * tq) =
+            make_float2(acc[nt][0][0] + acc[nt][1][0], acc[nt][0][1] + acc[nt][1][1]);
+        *reinterpret_cast<float2*>(rw + (gq + 8) * kMaxRows + nt * 8 + 2 * tq) =
+            make_float2(acc[nt][0][2] + acc[nt][1][2], acc[nt][0][3] + acc[nt][1][3]);
+      }
+    }
+  }
+  consumer_bar();
+
+  // ---- epilogue: one output per thread and round
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = tid + kConsumers * k, row = idx / kMaxRows, nl = idx - row * kMaxRows;
+    if (row >= rows || nl >= ncols || row >= kGroupRows) continue;
+    const int b = b0 + row, n = s.n_lo + nl;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) v += sm.red[w * (kGroupRows * kMaxRows) + row * kMaxRows + nl];
+    if (d.ln) {  // LayerNorm (eps 1e-6, modules.py:88) applied to the finished product
+      float S = 0.f, Q = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) {
+        const float2 p = *reinterpret_cast<const float2*>(sm.spart + (w * kGroupRows + row) * 2);
+        S += p.x;
+        Q += p.y;
+      }
+      const float invK = 1.f / (float)d.K;
+      const float ms = S * invK;
+      const float var = fmaxf(Q * invK - ms * ms, 0.f);
+      const float rstd = rsqrtf(var + 1e-6f);
+      const float mean = sm.sshift[row] + ms;
+      v = rstd * v - rstd * mean * e_lns[k];
+    }
+    v += e_bias[k];
+    if (d.relu) v = fmaxf(v, 0.f);
+    switch (d.mode) {
+      case kPlain:
+        d.Y[(size_t)b * d.ldy + n] = v * d.out_scale + e_res[k];
+        break;
+      case kPartial:
+        d.Y[((size_t)s.ks * B + b) * d.ldy + n] = v;
+        break;
+      case kQkv: {
+        const int H = a.w.n_heads, D = H * DH;
+        const int which = n / D, cc = n - which * D;
+        if (which == 0) {
+          d.Y[(size_t)b * d.ldy + cc] = v * d.out_scale;
+        } else {
+          const int h = cc / DH, dd = cc - h * DH;
+          float* dst = which == 1 ? d.kcache : d.vcache;
+          dst[(((size_t)b * H + h) * a.st.t_max + t) * DH + dd] = v;
+        }
+      } break;
+      case kPrenetOut: {  // modules.py:114-118
+        const bool have = t > 0 && (t - 1) < sm.len[b];
+        d.Y[(size_t)b * d.ldy + n] = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * d.N + n) * __ldg(a.w.pe_scale);
+      } break;
+      case kFinal: {  // modules.py:144, tacotron.py:112-115
+        const bool on = t < sm.len[b];
+        if (n < a.w.n_mels) a.st.frames[((size_t)b * a.st.t_max + t) * a.w.n_mels + n] = on ? v : 0.f;
+        else a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
+      } break;
+    }
+  }
+}
+
+// ---- reduce group-phase: x[b][n] += sum_s part[s][b][n] (FFN-out partials + residual) ------------------------
+__device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g) {
+  const int B = a.st.batch, G = gridDim.x, c = blockIdx.x;
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
+  const int n_lo = (int)(((long long)c * d.N) / G), n_hi = (int)(((long long)(c + 1) * d.N) / G), ncols = n_hi - n_lo;
+  for (int idx = threadIdx.x; idx < rows * ncols; idx += kConsumers) {
+    const int row = idx / ncols, n = n_lo + idx - row * ncols, b = b0 + row;
+    float v = __ldcg(d.Y + (size_t)b * d.ldy + n);
+    for (int sidx = 0; sidx < d.n_parts; ++sidx) v += __ldcg(d.part + ((size_t)sidx * B + b) * d.N + n);
+    d.Y[(size_t)b * d.ldy + n] = v;
+  }
+}
+
+// ---- attention group-phase -----------------------------------------------------------------------------------
+template <int DH>
+__device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const Smem& sm, CState& cs, int g, int t) {
+  constexpr int F4 = DH / 32;            // float4 per lane per key row (8 lanes span a row)
+  constexpr int kTile = kTK * DH;        // floats per K (or V) tile
+  constexpr int kSlotF = 2 * kTile;      // K tile then V tile
+  constexpr int kRounds = kTK / 4;       // 4 key slots per warp pass
+  constexpr int PS = DH + 4;
+  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split;
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
+  const int item0 = b0 * H, n_units = rows * H * ns, n_keys = at.n_keys;
+  const int per = (n_keys + ns - 1) / ns;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kslot = lane >> 3, l8 = lane & 7;
+  float* ring = sm.wreg + (size_t)warp * kSlots * kSlotF;
+  uint64_t* full = sm.rfull + warp * kSlots;
+  float* wrec = sm.red;  // [8][PS]
+  float* sc = sm.wreg + (size_t)kCWarps * kSlots * kSlotF;            // raw logits of the current unit
+  const int sc_cap = at.ring_floats - kCWarps * kSlots * kSlotF;
+  const bool sc_ok = per <= sc_cap;                                   // else fall back to read-modify-write in HBM
+
+  // ---- producer cursor (next tile this warp will request) ----
+  int pu = blockIdx.x, pi = warp;
+  auto issue_next = [&]() {
+    int item = 0, j0 = 0, j1 = 0;
+    while (pu < n_units) {
+      item = ns == 1 ? pu : pu / ns;
+      j0 = min(n_keys, (pu - item * ns) * per);
+      j1 = min(n_keys, j0 + per);
+      if (pi * kTK < j1 - j0) break;
+      pu += G;
+      pi = warp;
+    }
+    if (pu >= n_units) return;
+    const int key0 = j0 + pi * kTK, nk = min(kTK, j1 - key0);
+    const int slot = cs.issued % kSlots;
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)nk * DH * 4u;
+      mbar_expect_tx(&full[slot], 2u * bytes);
+      const size_t off = ((size_t)(item0 + item) * at.rows_alloc + key0) * DH;
+      bulk_g2s(ring + slot * kSlotF, at.kc + off, bytes, &full[slot]);
+      bulk_g2s(ring + slot * kSlotF + kTile, at.vc + off, bytes, &full[slot]);
+    }
+    cs.issued++;
+    pi += kCWarps;
+  };
+  fence_proxy_async();  // the K/V row appended by other CTAs in the previous phase is read through the async proxy
+#pragma unroll
+  for (int sl = 0; sl < kSlots; ++sl) issue_next();
+
+  f32x4 qnext[F4];
+#pragma unroll
+  for (int i = 0; i < F4; ++i) qnext[i].lo = qnext[i].hi = 0ull;
+  for (int u = blockIdx.x; u < n_units; u += G) {
+    const int litem = ns == 1 ? u : u / ns, split = u - litem * ns, item = item0 + litem;
+    const int j0 = min(n_keys, split * per), j1 = min(n_keys, j0 + per);
+    const int b = item / H;
+    const int klen = at.key_len ? at.key_len[b] : n_keys;
+    float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
+
+    f32x4 qv[F4];
+    if (u == (int)blockIdx.x) {
+#pragma unroll
+      for (int i = 0; i < F4; ++i) qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+    } else {
+#pragma unroll
+      for (int i = 0; i < F4; ++i) qv[i] = qnext[i];
+    }
+    if (u + G < n_units) {  // latency of the next unit's query hides behind this unit's stream
+      const int nitem = item0 + (ns == 1 ? u + G : (u + G) / ns);
+#pragma unroll
+      for (int i = 0; i < F4; ++i) qnext[i] = ld4cg(a.q + (size_t)nitem * DH + 4 * (l8 + 8 * i));
+    }
+    float m_run = -CUDART_INF_F, l_run = 0.f;
+    f32x2 o[F4][2];
+#pragma unroll
+    for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
+
+    const int n_tiles = (j1 - j0 + kTK - 1) / kTK;
+    for (int ti = warp; ti < n_tiles; ti += kCWarps) {
+      const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
+      const int slot = cs.consumed % kSlots;
+      mbar_wait(&full[slot], (cs.consumed / kSlots) & 1u, a.err);
+      const float* kt = ring + slot * kSlotF;
+      const float* vt = kt + kTile;
+      float sv[kRounds];
+      float mt = -CUDART_INF_F;
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int kl = r * 4 + kslot;
+        f32x2 accq = 0ull;
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          const f32x4 kv = ld4s(kt + kl * DH + 4 * (l8 + 8 * i));
+          accq = fma2(qv[i].lo, kv.lo, accq);
+          accq = fma2(qv[i].hi, kv.hi, accq);
+        }
+        float v = hsum2(accq);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (kl >= nk) v = -CUDART_INF_F;                 // stale smem beyond the tile's keys
+        else if (key0 + kl >= klen) v = kNegBias;        // logits + (-1e20), attention.py:84-85
+        if (kl < nk && l8 == 0 && arow != nullptr) {     // raw logit, normalised once the unit's (max, sum) is known
+          if (ns == 1 && sc_ok) sc[key0 + kl - j0] = v;
+          else arow[key0 + kl] = v;
+        }
+        sv[r] = v;
+        mt = fmaxf(mt, v);
+      }
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+      const float m_new = fmaxf(m_run, mt);
+      const float corr = expf(m_run - m_new);
+      l_run *= corr;
+      const f32x2 c2 = pack2(corr, corr);
+#pragma unroll
+      for (int i = 0; i < F4; ++i) {
+        o[i][0] = fma2(o[i][0], c2, 0ull);
+        o[i][1] = fma2(o[i][1], c2, 0ull);
+      }
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int kl = r * 4 + kslot;
+        const float p = kl < nk ? expf(sv[r] - m_new) : 0.f;
+        if (l8 == 0) l_run += p;
+        const f32x2 pp = pack2(p, p);
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          const f32x4 vv = ld4s(vt + kl * DH + 4 * (l8 + 8 * i));
+          o[i][0] = fma2(pp, kl < nk ? vv.lo : 0ull, o[i][0]);
+          o[i][1] = fma2(pp, kl < nk ? vv.hi : 0ull, o[i][1]);
+        }
+      }
+      m_run = m_new;
+      cs.consumed++;
+      __syncwarp();   // every lane is done with this slot before it is refilled
+      issue_next();
+    }
+    // ---- warp record (max, sum, weighted V) -> shared ----
+#pragma unroll
+    for (int i = 0; i < F4; ++i)
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs) {
+        float x, y;
+        unpack2(o[i][hs], x, y);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);  y += __shfl_xor_sync(0xffffffffu, y, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16); y += __shfl_xor_sync(0xffffffffu, y, 16);
+        if (kslot == 0) {
+          const int dd = 4 * (l8 + 8 * i) + 2 * hs;
+          wrec[warp * PS + dd] = x;
+          wrec[warp * PS + dd + 1] = y;
+        }
+      }
+    const float lw = warp_sum(l_run);
+    if (lane == 0) {
+      wrec[warp * PS + DH] = m_run;
+      wrec[warp * PS + DH + 1] = lw;
+    }
+    consumer_bar();
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) m = fmaxf(m, wrec[w * PS + DH]);
+    float l = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) {
+      const float mw = wrec[w * PS + DH];
+      if (mw > -CUDART_INF_F) l += wrec[w * PS + DH + 1] * expf(mw - m);
+    }
+    if (tid < DH) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) {
+        const float mw = wrec[w * PS + DH];
+        if (mw > -CUDART_INF_F) v += wrec[w * PS + tid] * expf(mw - m);
+      }
+      if (ns == 1) a.ctx[(size_t)item * DH + tid] = v / l;
+      else a.fpart[((size_t)item * ns + split) * PS + tid] = v;
+    }
+    if (ns == 1) {
+      if (arow != nullptr) {
+        const float inv = 1.f / l;
+        if (sc_ok) for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = expf(sc[j - j0] - m) * inv;
+        else for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = expf(arow[j] - m) * inv;
+      }
+    } else if (tid == 0) {
+      a.fpart[((size_t)item * ns + split) * PS + DH] = m;       // -inf when the split is empty
+      a.fpart[((size_t)item * ns + split) * PS + DH + 1] = l;
+    }
+    consumer_bar();  // wrec / sc are reused by the next unit
+  }
+}
+
+// ---- combine group-phase (only when the K/V streams were split, i.e. small batches): partials -> ctx, align rows
+template <int DH>
+__device__ __forceinline__ void combine_group(const Args& a, const Desc& d, const Smem& sm, int g, int t) {
+  constexpr int PS = DH + 4;
+  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split;
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
+  const int tid = threadIdx.x;
+  float* ml = sm.red;
+  for (int li = blockIdx.x; li < rows * H; li += G) {
+    const int item = b0 * H + li;
+    const float* pr = a.fpart + (size_t)item * ns * PS;
+    if (tid == 0) {
+      float m = -CUDART_INF_F;
+      for (int sidx = 0; sidx < ns; ++sidx) m = fmaxf(m, __ldcg(pr + sidx * PS + DH));
+      float l = 0.f;
+      for (int sidx = 0; sidx < ns; ++sidx) {
+        const float pm = __ldcg(pr + sidx * PS + DH);
+        if (pm > -CUDART_INF_F) l += __ldcg(pr + sidx * PS + DH + 1) * expf(pm - m);
+      }
+      ml[0] = m;
+      ml[1] = 1.f / l;
+    }
+    consumer_bar();
+    const float m = ml[0], inv = ml[1];
+    if (tid < DH) {
+      float acc = 0.f;
+      for (int sidx = 0; sidx < ns; ++sidx) {
+        const float pm = __ldcg(pr + sidx * PS + DH);
+        if (pm > -CUDART_INF_F) acc = fmaf(__ldcg(pr + sidx * PS + tid), expf(pm - m), acc);
+      }
+      a.ctx[(size_t)item * DH + tid] = acc * inv;
+    }
+    if (d.align != nullptr) {  // raw logits of this step -> softmax weights
+      float* row = d.align + (size_t)item * d.align_bh_stride + (size_t)t * d.align_row_len;
+      for (int j = tid; j < d.n_keys; j += kConsumers) row[j] = expf(__ldcg(row + j) - m) * inv;
+    }
+    consumer_bar();
+  }
+}
+
+// ---- phase table ---------------------------------------------------------------------------------------------
+// per step: 3 prenet GEMMs, per layer {qkv, self, [combine], oproj, cq, cross, [combine], coproj, ffn1, ffn2, [reduce]},
+// final projection.  `comb` = attention streams are split (n_split > 1), `red` = FFN-out is K-split.
+__device__ __forceinline__ int phases_per_layer(const Args& a) { return 8 + (a.n_split > 1 ? 2 : 0) + (a.ksplit > 1 ? 1 : 0); }
+__device__ __forceinline__ int n_phases(const Args& a) { return 3 + phases_per_layer(a) * a.w.n_layers + 1; }
+
+template <int DH>
+__device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qscale, Desc& d) {
+  const int B = a.st.batch, D = a.w.d_model, H = a.w.n_heads, F = a.w.d_ffn, P = a.w.prenet_hidden;
+  const int M = a.w.n_mels, S = a.st.mem_len, T = a.st.t_max, L = a.w.n_layers;
+  const int ppl = phases_per_layer(a);
+  const bool comb = a.n_split > 1, red = a.ksplit > 1;
+  memset(&d, 0, sizeof(d));
+  d.out_scale = 1.f;
+  d.kind = kGemm;
+  d.ksplit = 1;
+  if (ph == 0) {         // prenet (tacotron.py:55-65)
+    d.X = a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * M; d.ldx = (long long)T * M; d.zero_x = t == 0;
+    d.K = M; d.N = P; d.W = a.w.prenet_w0; d.n_w1 = P; d.ldw = M; d.bias = a.w.prenet_b0; d.relu = 1;
+    d.mode = kPlain; d.Y = a.p0; d.ldy = P; d.hi = 1;
+    return;
+  }
+  if (ph == 1) {
+    d.X = a.p0; d.ldx = P; d.K = P; d.N = P; d.W = a.w.prenet_w1; d.n_w1 = P; d.ldw = P; d.bias = a.w.prenet_b1;
+    d.relu = 1; d.mode = kPlain; d.Y = a.p1; d.ldy = P; d.hi = 0;
+    return;
+  }
+  if (ph == 2) {         // + shift / mask / PE (modules.py:114-118)
+    d.X = a.p1; d.ldx = P; d.K = P; d.N = D; d.W = a.w.prenet_w2; d.n_w1 = D; d.ldw = P; d.mode = kPrenetOut;
+    d.Y = a.x; d.ldy = D; d.hi = 1;
+    return;
+  }
+  if (ph == 3 + ppl * L) {  // final LN + mel / stop projections
+    d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = M + 1; d.W = a.w.w_mel_ln; d.W2 = a.w.w_stop_ln; d.n_w1 = M;
+    d.ldw = D; d.bias = a.w.c_out_ln; d.lnsum = a.w.s_out_ln; d.mode = kFinal; d.hi = 0;
+    return;
+  }
+  const int l = (ph - 3) / ppl;
+  int k = (ph - 3) % ppl;
+  // canonical phase ids: 0 qkv, 1 self, 2 comb, 3 oproj, 4 cq, 5 cross, 6 comb, 7 coproj, 8 ffn1, 9 ffn2, 10 reduce
+  int id;
+  if (comb) id = k;
+  else id = k < 2 ? k : (k < 5 ? k + 1 : k + 2);
+  const TtsDecLayerWeights& lw = a.w.layer[l];
+  const size_t self_off = (size_t)l * B * H * T * DH, cross_off = (size_t)l * B * H * S * DH;
+  float* al_self = a.st.align_self ? a.st.align_self + (size_t)l * B * H * T * T : nullptr;
+  float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
+  // attention phases: the next GEMM (an output projection, high placement) owns the top n-tiles of the weight region
+  const int oproj_rows = (D + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ring_floats = kWFloats - ((oproj_rows + 7) / 8) * 8 * (D + kPad);
+  switch (id) {
+    case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = 3 * D; d.W = lw.w_qkv_ln; d.n_w1 = 3 * D; d.ldw = D;
+      d.bias = lw.c_qkv_ln; d.lnsum = lw.s_qkv_ln; d.mode = kQkv; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
+      d.kcache = a.st.self_k + self_off; d.vcache = a.st.self_v + self_off; d.hi = 0;
+      break;
+    case 1:
+      d.kind = kAttn;
+      d.kc = a.st.self_k + self_off; d.vc = a.st.self_v + self_off; d.rows_alloc = T; d.n_keys = t + 1;
+      d.key_len = nullptr; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
+      d.ring_floats = ring_floats;
+      break;
+    case 2:
+      d.kind = kCombine; d.n_keys = t + 1; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
+      break;
+    case 3:  // output projection + residual (attention.py:118-119, modules.py:132)
+      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_self_out; d.n_w1 = D; d.ldw = D; d.mode = kPlain;
+      d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
+      break;
+    case 4:  // LN + cross query
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_cross_q_ln; d.n_w1 = D; d.ldw = D;
+      d.bias = lw.c_cross_q_ln; d.lnsum = lw.s_cross_q_ln; d.mode = kPlain; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
+      d.hi = 0;
+      break;
+    case 5:
+      d.kind = kAttn;
+      d.kc = a.st.cross_k + cross_off; d.vc = a.st.cross_v + cross_off; d.rows_alloc = S; d.n_keys = S;
+      d.key_len = a.st.input_lengths; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
+      d.ring_floats = ring_floats;
+      break;
+    case 6:
+      d.kind = kCombine; d.n_keys = S; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
+      break;
+    case 7:
+      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_cross_out; d.n_w1 = D; d.ldw = D; d.mode = kPlain;
+      d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
+      break;
+    case 8:  // LN + FFN-in + ReLU (modules.py:14-17)
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = F; d.W = lw.w_ffn_in_ln; d.n_w1 = F; d.ldw = D;
+      d.bias = lw.c_ffn_in_ln; d.lnsum = lw.s_ffn_in_ln; d.relu = 1; d.mode = kPlain; d.Y = a.hid; d.ldy = F; d.hi = 0;
+      break;
+    case 9:  // FFN-out: K-split partials, or + residual directly
+      d.X = a.hid; d.ldx = F; d.K = F; d.N = D; d.W = lw.w_ffn_out; d.n_w1 = D; d.ldw = F; d.hi = 1;
+      if (red) {
+        d.ksplit = a.ksplit; d.mode = kPartial; d.Y = a.part; d.ldy = D;
+      } else {
+        d.mode = kPlain; d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D;
+      }
+      break;
+    default:
+      d.kind = kReduce; d.Y = a.x; d.ldy = D; d.N = D; d.part = a.part; d.n_parts = a.ksplit;
+      break;
+  }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(128) float smem_raw[];
+  const Smem sm = make_smem(a, smem_raw);
+  const int B = a.st.batch, T = a.st.t_max, G = gridDim.x, NG = a.n_groups;
+  const int n_ph = n_phases(a);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float qscale = (float)(1.0 / sqrt((double)DH));
+
+  if (tid == 0) {
+    mbar_init(sm.x_full, 1);
+    mbar_init(sm.x_empty, kCWarps);
+    mbar_init(&sm.w_full[0], 1);
+    mbar_init(&sm.w_full[1], 1);
+    mbar_init(sm.pdone, 1);
+    for (int i = 0; i < kCWarps * kSlots; ++i) mbar_init(&sm.rfull[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int b = tid; b < B; b += kThreads) {
+    sm.len[b] = a.st.lengths[b];
+    sm.fin[b] = a.st.finished[b];
+  }
+  __syncthreads();
+  const int t0 = *a.st.step_counter;
+
+  CState cs{0u, {0u, 0u}, 0u, 0u};
+  unsigned p_gp = 0u, p_done = 0u;      // producer: group-phases staged, phase completions consumed
+  unsigned epoch = 0u;                  // phases completed per group since the kernel started
+
+  for (int s = 0; s < a.n_steps; ++s) {
+    const int t = t0 + s;
+    if (warp == kCWarps) {
+      // =========================== producer warp (one elected lane) ===========================
+      if (lane == 0) {
+        fence_proxy_async();  // frames / activations written by other CTAs in the previous step are read by TMA
+        get_phase<DH>(a, 0, t, qscale, sm.desc[0]);
+        if (sm.desc[0].kind == kGemm) issue_weights(sm, sm.desc[0]);
+        for (int ph = 0; ph < n_ph; ++ph) {
+          const Desc& d = sm.desc[ph % kDescRing];
+          for (int g = 0; g < NG; ++g) {
+            if (ph > 0) {
+              grid_wait(a, g, (epoch + ph) * G);      // (ph-1, g) is complete everywhere
+              fence_proxy_async();
+            }
+            mbar_wait(sm.x_empty, (p_gp & 1u) ^ 1u, a.err);
+            stage_tile(a, sm, d, g);
+            ++p_gp;
+            if (g == 0 && ph + 1 < n_ph) {
+              Desc& dn = sm.desc[(ph + 1) % kDescRing];
+              get_phase<DH>(a, ph + 1, t, qscale, dn);
+              if (ph >= 1) {                            // the consumers are done with phase ph-1: its weight half
+                mbar_wait(sm.pdone, p_done & 1u, a.err);  // (and the K/V rings) may be overwritten
+                ++p_done;
+              }
+              if (dn.kind == kGemm) issue_weights(sm, dn);
+            }
+          }
+        }
+        // completions of the last two phases of this step (keeps the parity in lock-step)
+        const int left = n_ph >= 2 ? 2 : 1;
+        for (int i = 0; i < left; ++i) {
+          mbar_wait(sm.pdone, p_done & 1u, a.err);
+          ++p_done;
+        }
+      }
+      __syncwarp();
+    } else {
+      // =========================== consumer warps ===========================
+      for (int ph = 0; ph < n_ph; ++ph) {
+        long long* prof = (blockIdx.x == 0 && tid == 0 && ph < kProfPhases) ? a.prof + 8 * ph : nullptr;
+        for (int g = 0; g < NG; ++g) {
+          if (prof && g < 2) prof[3 * g] = clock64();
+          mbar_wait(sm.x_full, cs.gp & 1u, a.err);
+          ++cs.gp;
+          if (prof && g < 2) prof[3 * g + 1] = clock64();
+          const Desc& d = sm.desc[ph % kDescRing];
+          if (d.kind == kGemm) {
+            gemm_group<DH>(a, d, sm, cs, g, t, g == 0);
+          } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sm.x_empty);
+            if (d.kind == kAttn) attn_group<DH>(a, d, sm, cs, g, t);
+            else if (d.kind == kReduce) reduce_group(a, d, g);
+            else combine_group<DH>(a, d, sm, g, t);
+          }
+          // writes of this group-phase that another CTA reads through the async proxy (TMA) need the cross-proxy fence
+          fence_proxy_async();
+          consumer_bar();
+          if (tid == 0) grid_arrive(a, g);
+          if (prof && g < 2) prof[3 * g + 2] = clock64();
+        }
+        if (tid == 0) mbar_arrive(sm.pdone);
+      }
+      if (tid == 0)
+        for (int g = 0; g < NG; ++g) grid_wait(a, g, (epoch + n_ph) * G);   // the step is complete everywhere
+    }
+    epoch += n_ph;
+    __syncthreads();
+    // synthesize.py:42-45, replicated identically in every CTA
+    if (a.update_state) {
+      for (int b = tid; b < B; b += kThreads) {
+        const bool fin = sm.fin[b] != 0 || __ldcg(a.st.stop_logits + (size_t)b * T + t) > 0.f;
+        sm.fin[b] = fin ? 1 : 0;
+        if (!fin) sm.len[b] += 1;
+      }
+    }
+    __syncthreads();
+    int unfinished = 0;
+    for (int b = 0; b < B; ++b) unfinished += sm.fin[b] ? 0 : 1;
+    if (blockIdx.x == 0) {
+      if (a.update_state)
+        for (int b = tid; b < B; b += kThreads) {
+          a.st.lengths[b] = sm.len[b];
+          a.st.finished[b] = (uint8_t)sm.fin[b];
+        }
+      if (tid == 0) {
+        *a.st.step_counter = t + 1;
+        *a.st.n_unfinished = (*reinterpret_cast<volatile int*>(a.err) != 0) ? -1 : unfinished;
+      }
+    }
+    if ((a.update_state && unfinished == 0) || s + 1 == a.n_steps) break;  // uniform across CTAs
+    if (*reinterpret_cast<volatile int*>(a.err) != 0) break;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+struct Carve {
+  float *x, *q, *ctx, *hid, *p0, *p1, *part, *fpart;
+  unsigned* bar;
+  int* err;
+  long long* prof;
+  size_t floats;
+};
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int ksplit_for(const TtsDecoderWeights* w) { return (w->d_ffn + kKC - 1) / kKC; }
+
+static int group_rows_for(int B) {
+  const char* e = getenv("TTS_GROUP_ROWS");
+  int r = e ? atoi(e) : 0;
+  if (r <= 0) r = B > kGroupRows ? kGroupRows : (B + 1) / 2;   // at least two groups when there are >= 2 rows
+  if (r > kGroupRows) r = kGroupRows;
+  if (r < 1) r = 1;
+  while ((B + r - 1) / r > kMaxGroups) ++r;
+  return r;
+}
+
+static int split_for(const TtsDecoderWeights* w, int group_rows, int G) {
+  int ns = G / (group_rows * w->n_heads);
+  return ns < 1 ? 1 : (ns > kMaxSplit ? kMaxSplit : ns);
+}
+
+static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
+  Carve c;
+  const size_t D = w->d_model, F = w->d_ffn, P = w->prenet_hidden, H = w->n_heads, dh = D / H;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += (n + 31) / 32 * 32;
+    return p;
+  };
+  c.bar = reinterpret_cast<unsigned*>(take(32 * kMaxGroups));
+  c.err = reinterpret_cast<int*>(take(32));
+  c.prof = reinterpret_cast<long long*>(take(2 * 8 * kProfPhases));
+  c.x = take(B * D); c.q = take(B * D); c.ctx = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
+  c.part = take((size_t)ksplit_for(w) * B * D);
+  c.fpart = take((size_t)B * H * kMaxSplit * (dh + 4));
+  c.floats = off;
+  return c;
+}
+
+template <int DH>
+static int launch(const Args& a, cudaStream_t s) {
+  static bool configured = false;
+  const size_t smem = smem_bytes(a.st.batch);
+  if (!configured) {
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(pipelined_decode_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int per_sm = 0;
+    TTS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipelined_decode_kernel<DH>, kThreads, smem));
+    TTS_REQUIRE(per_sm >= 1, "pipelined decode kernel does not fit on an SM");
+    configured = true;
+  }
+  Args args = a;
+  void* params[] = {&args};
+  TTS_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pipelined_decode_kernel<DH>), dim3(num_sms()),
+                                             dim3(kThreads), params, smem, s));
+  count_launch();
+  return 0;
+}
+
+}  // namespace pipe
+
+int pipelined_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries) {
+  using namespace pipe;
+  const Carve c = carve(w, st->batch, st->scratch);
+  const int n = max_entries < 8 * kProfPhases ? max_entries : 8 * kProfPhases;
+  TTS_CHECK_CUDA(cudaMemcpy(out_host, c.prof, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+size_t pipelined_scratch_floats(const TtsDecoderWeights* w, int B) { return pipe::carve(w, B, nullptr).floats; }
+
+bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
+  using namespace pipe;
+  const int G = num_sms();
+  const int D = w->d_model, F = w->d_ffn, P = w->prenet_hidden, M = w->n_mels;
+  if (D > kKC || D % 16 != 0 || P > kKC || P % 16 != 0 || M > kKC || M % 16 != 0 || F % 16 != 0) return false;
+  if (!w->w_mel_ln || !w->w_stop_ln || !w->c_out_ln || !w->s_out_ln) return false;   // packed operands required
+  for (int l = 0; l < w->n_layers; ++l) {
+    const TtsDecLayerWeights& lw = w->layer[l];
+    if (!lw.w_qkv_ln || !lw.c_qkv_ln || !lw.s_qkv_ln || !lw.w_cross_q_ln || !lw.c_cross_q_ln || !lw.s_cross_q_ln ||
+        !lw.w_ffn_in_ln || !lw.c_ffn_in_ln || !lw.s_ffn_in_ln)
+      return false;
+  }
+  const int ks = ksplit_for(w);
+  if (F % ks != 0 || (F / ks) % 16 != 0 || F / ks > kKC || ks > G) return false;
+  if (st->batch > kMaxBatch) return false;
+  const int dh = D / w->n_heads;
+  if (dh != 32 && dh != 64 && dh != 96) return false;
+  auto rows = [&](long long N, int parts) { return (int)((N + parts - 1) / parts); };
+  int worst = rows(3 * D, G);
+  worst = worst > rows(F, G) ? worst : rows(F, G);
+  worst = worst > rows(D, G / ks) ? worst : rows(D, G / ks);
+  worst = worst > rows(P, G) ? worst : rows(P, G);
+  worst = worst > rows(M + 1, G) ? worst : rows(M + 1, G);
+  if (worst > kMaxRows) return false;
+  // K/V rings (+ at least a few logits) must fit below the output projection's weight tiles
+  const int oproj_tiles = (rows(D, G) + 7) / 8;
+  if (kCWarps * kSlots * 2 * kTK * dh + 64 > kWFloats - oproj_tiles * 8 * (D + kPad)) return false;
+  if (smem_bytes(st->batch) > 227 * 1024) return false;
+  return true;
+}
+
+int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
+                           cudaStream_t s) {
+  using namespace pipe;
+  TTS_REQUIRE(pipelined_supported(w, st), "pipelined decode kernel does not support this shape");
+  if (n_steps == 0) return 0;
+  const Carve c = carve(w, st->batch, st->scratch);
+  Args a;
+  memcpy(&a.w, w, sizeof(*w));
+  memcpy(&a.st, st, sizeof(*st));
+  a.x = c.x; a.q = c.q; a.ctx = c.ctx; a.hid = c.hid; a.p0 = c.p0; a.p1 = c.p1; a.part = c.part; a.fpart = c.fpart;
+  a.bar = c.bar; a.err = c.err; a.prof = c.prof; a.n_steps = n_steps; a.update_state = update_state;
+  a.group_rows = group_rows_for(st->batch);
+  a.n_groups = (st->batch + a.group_rows - 1) / a.group_rows;
+  a.n_split = split_for(w, a.group_rows, num_sms());
+  a.ksplit = ksplit_for(w);
+  TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, (32 * kMaxGroups + 32) * sizeof(unsigned), s));  // counters + error flag
+  switch (w->d_model / w->n_heads) {
+    case 32: return launch<32>(a, s);
+    case 64: return launch<64>(a, s);
+    case 96: return launch<96>(a, s);
+  }
+  set_error("pipelined decode: unsupported head_dim");
+  return 2;
+}
+
+}  // namespace tts

@@ -191,25 +191,27 @@ class TtsEngine:
                 wt, gam, bet = w[wname].detach(), w[gname].detach(), w[bname].detach()
                 wf = (wt * gam[None, :]).contiguous()
                 cf = ops.linear(bet[None, :].contiguous(), wt.contiguous()).view(-1)
-            keep.extend([wf, cf])
-            return wf, cf
+                sf = wf.double().sum(dim=1).float().contiguous()   # row sums: LayerNorm applied after the product
+            keep.extend([wf, cf, sf])
+            return wf, cf, sf
 
         for l in range(cfg.n_decoder_layer):
             lw = dw.layer[l]
-            wf, cf = fold(f"{p}self_attentions.{l}.qkv_transform.weight", f"{p}attn_layer_norms.{l}.weight",
-                          f"{p}attn_layer_norms.{l}.bias")
-            lw.w_qkv_ln, lw.c_qkv_ln = wf.data_ptr(), cf.data_ptr()
-            wf, cf = fold(f"{p}encdec_attentions.{l}.q_transform.weight", f"{p}encdec_layer_norms.{l}.weight",
-                          f"{p}encdec_layer_norms.{l}.bias")
-            lw.w_cross_q_ln, lw.c_cross_q_ln = wf.data_ptr(), cf.data_ptr()
-            wf, cf = fold(f"{p}ffn_layers.{l}.input_layer.weight", f"{p}ffn_layer_norms.{l}.weight",
-                          f"{p}ffn_layer_norms.{l}.bias")
-            lw.w_ffn_in_ln, lw.c_ffn_in_ln = wf.data_ptr(), cf.data_ptr()
-        wm, cm = fold("decoder.mel_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
-        ws, cs = fold("decoder.stop_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
+            wf, cf, sf = fold(f"{p}self_attentions.{l}.qkv_transform.weight", f"{p}attn_layer_norms.{l}.weight",
+                              f"{p}attn_layer_norms.{l}.bias")
+            lw.w_qkv_ln, lw.c_qkv_ln, lw.s_qkv_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+            wf, cf, sf = fold(f"{p}encdec_attentions.{l}.q_transform.weight", f"{p}encdec_layer_norms.{l}.weight",
+                              f"{p}encdec_layer_norms.{l}.bias")
+            lw.w_cross_q_ln, lw.c_cross_q_ln, lw.s_cross_q_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+            wf, cf, sf = fold(f"{p}ffn_layers.{l}.input_layer.weight", f"{p}ffn_layer_norms.{l}.weight",
+                              f"{p}ffn_layer_norms.{l}.bias")
+            lw.w_ffn_in_ln, lw.c_ffn_in_ln, lw.s_ffn_in_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+        wm, cm, sm_ = fold("decoder.mel_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
+        ws, cs, ss_ = fold("decoder.stop_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
         cout = torch.cat([cm, cs]).contiguous()
-        keep.append(cout)
-        dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr()
+        sout = torch.cat([sm_, ss_]).contiguous()
+        keep.extend([cout, sout])
+        dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln, dw.s_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr(), sout.data_ptr()
         self._dec_keep = keep  # owns the packed tensors for as long as the struct is cached
         self._dec_w, self._dec_key = dw, key
         return dw

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 4
+#define TTS_ABI_VERSION 5
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -140,6 +140,11 @@ typedef struct TtsDecLayerWeights {
   const float* c_cross_q_ln; /* [D] */
   const float* w_ffn_in_ln;  /* [4D][D] */
   const float* c_ffn_in_ln;  /* [4D] */
+  /* Row sums of the folded matrices, s_ln[n] = sum_k W_ln[n][k]: the pipelined kernel applies LayerNorm AFTER the
+   * product, LN(x) W^T = rstd * (x W_ln^T) - rstd * mean * s_ln + c_ln. */
+  const float* s_qkv_ln;     /* [3D] */
+  const float* s_cross_q_ln; /* [D] */
+  const float* s_ffn_in_ln;  /* [4D] */
 } TtsDecLayerWeights;
 
 typedef struct TtsDecoderWeights {
@@ -159,6 +164,7 @@ typedef struct TtsDecoderWeights {
   const float* w_mel_ln;    /* [M][D]  mel_net with the output LayerNorm folded in (see TtsDecLayerWeights) */
   const float* w_stop_ln;   /* [1][D] */
   const float* c_out_ln;    /* [M+1]   W_mel * beta_out, w_stop * beta_out */
+  const float* s_out_ln;    /* [M+1]   row sums of w_mel_ln | w_stop_ln */
   TtsDecLayerWeights layer[TTS_MAX_LAYERS];
 } TtsDecoderWeights;
 
@@ -197,7 +203,10 @@ int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void*
  *   prev_mel / prev_mel_stride: where step t reads frame t-1 from.  NULL = st->frames.
  *   update_state: 1 = also perform synthesize.py:42-45 on device (finished |= stop>0,
  *                 lengths += !finished); 0 = the caller does it (unchanged eval_batch).
- *   impl: 0 = default (fused persistent kernel when available), 1 = per-phase kernels. */
+ *   impl: 0 = default (pipelined persistent kernel when the shape is supported, else the fused one),
+ *         1 = per-phase kernels, 2 = per-phase kernels replayed from a CUDA graph,
+ *         3 = fused persistent kernel (FFMA2, one grid barrier per phase),
+ *         4 = pipelined persistent kernel (row-group pipelining, producer warp, 3xTF32 mma.sync). */
 int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32_t n_steps,
                      const float* prev_mel, int64_t prev_mel_stride, int32_t update_state,
                      int32_t impl, void* stream);

@@ -184,7 +184,7 @@ def test_tiny_encoder_and_teacher_forced_forward(tiny_engine, tiny_params, golde
             assert a.shape == b.shape and _err(a, b) < 1e-5
 
 
-@pytest.mark.parametrize("impl", [1, 2, 0])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_tiny_autoregressive_vs_golden(tiny_engine, tiny_params, golden_dir, impl):
     cfg, params = tiny_params
     z = np.load(os.path.join(golden_dir, "tiny_ar.npz"))
@@ -244,7 +244,7 @@ def test_full_ragged_forward_vs_reference_golden(full_engine, full_params, golde
         assert _err(got[k], torch.from_numpy(z[k])) < MEL_TOL, k
 
 
-@pytest.mark.parametrize("impl", [1, 2, 0])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4])
 def test_full_autoregressive_vs_reference_golden(full_params, golden_dir, ops, impl):
     """The reference's own eval_batch output (staggered stops) on the full-size model."""
     from tts_b200.engine import TtsEngine
@@ -266,7 +266,8 @@ def test_full_autoregressive_vs_reference_golden(full_params, golden_dir, ops, i
 
 @pytest.mark.parametrize("B,split_note", [(1, "split-KV over 18 CTAs per head"), (3, "split-KV"), (32, "one CTA per head"),
                                           (40, "two row blocks, second one partial"), (64, "two full row blocks")])
-def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_note):
+@pytest.mark.parametrize("impl", [3, 4])
+def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_note, impl):
     """Decode at several batch sizes (different split-KV factors), 24 steps, vs the cached oracle."""
     cfg, params = full_params
     p = dict(params)
@@ -275,7 +276,7 @@ def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_
     eng = TtsEngine.from_state_dict(p, cfg, DEV)
     batch = O.synth_batch(cfg, batch=B, text_len=37, n_frames=4, seed=11, ragged=B > 1)
     want = O.eval_batch_cached(p, cfg, batch, 24)
-    got = eng.generate(batch, max_frames=24, record_align="encdec", chunk=24)
+    got = eng.generate(batch, max_frames=24, record_align="encdec", chunk=24, impl=impl)
     assert got["generated_lengths"].cpu().tolist() == want["generated_lengths"].tolist() == [25] * B
     assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4
     assert _err(got["mel_aft"], want["mel_aft"]) < 2e-4
@@ -295,8 +296,9 @@ def test_decode_properties_at_baseline_shape(full_params, ops):
     a = eng.generate(batch, max_frames=T, record_align="none", memory=mem)
     b = eng.generate(batch, max_frames=T, record_align="none", memory=mem, session=a["session"])   # reuse buffers
     assert torch.equal(a["mel_pre"], b["mel_pre"]) and torch.equal(a["generated_lengths"], b["generated_lengths"])
-    c = eng.generate(batch, max_frames=T, record_align="none", memory=mem, impl=1)
-    assert _err(a["mel_pre"], c["mel_pre"]) < 1e-4 and torch.equal(a["generated_lengths"], c["generated_lengths"])
+    for other in (1, 3):   # per-phase kernels and the FFMA2 fused kernel agree with the default (pipelined) one
+        c = eng.generate(batch, max_frames=T, record_align="none", memory=mem, impl=other)
+        assert _err(a["mel_pre"], c["mel_pre"]) < 1e-4 and torch.equal(a["generated_lengths"], c["generated_lengths"])
     perm = torch.randperm(32, generator=torch.Generator().manual_seed(0))
     pb = {k: (v[perm] if torch.is_tensor(v) else v) for k, v in batch.items()}
     d = eng.generate(pb, max_frames=T, record_align="none", memory=mem[perm.to(DEV)].contiguous())
