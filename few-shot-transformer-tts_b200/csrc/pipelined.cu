@@ -33,7 +33,7 @@ namespace pipe {
 
 constexpr int kCWarps = 8;                 // consumer warps
 constexpr int kConsumers = kCWarps * 32;   // 256
-constexpr int kThreads = kConsumers + 32;  // + producer warp
+constexpr int kThreads = kConsumers + 64;  // + loader warp + signaler warp
 constexpr int kGroupRows = 16;             // batch rows per group (one m16 tile)
 constexpr int kKC = 768;                   // widest K slice of an activation tile / weight row in shared memory
 constexpr int kPad = 16;                   // floats of padding per shared-memory row (bank spread of LDS.128)
@@ -51,6 +51,7 @@ constexpr int kMaxSplit = 32;
 constexpr int kDescRing = 4;
 constexpr long long kSpinLimit = 1LL << 22;
 constexpr int kProfPhases = 160;
+constexpr int kProfStride = 16;
 
 enum Kind { kGemm = 0, kAttn = 1, kReduce = 2, kCombine = 3 };
 enum Mode { kPlain = 0, kQkv = 1, kPrenetOut = 2, kFinal = 3, kPartial = 4 };
@@ -81,6 +82,8 @@ struct Desc {
   int ring_floats;      // shared memory the rings + logits may use (the next phase's weights sit above it)
   // ---- reduce: Y[b][n] += sum_s part[s][b][n]
   const float* part; int n_parts;
+  // ---- this CTA's share of the phase (filled in by the loader warp: constant for the phase)
+  int s_n_lo, s_n_hi, s_k_lo, s_kc, s_ks;
 };
 
 struct Smem {
@@ -96,6 +99,7 @@ struct Smem {
   uint64_t* w_full;   // 2: weight slice landed (low / high placement)
   uint64_t* pdone;    // 1: consumers finished a phase
   uint64_t* rfull;    // [8][kSlots] ring slots
+  unsigned* sig;      // group-phases the consumers have finished (polled by the signaler warp)
   Desc* desc;         // [kDescRing]
 };
 
@@ -123,6 +127,7 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.w_full = sm.x_full + 2;
   sm.pdone = sm.x_full + 4;
   sm.rfull = sm.x_full + 5;
+  sm.sig = reinterpret_cast<unsigned*>(sm.rfull + kCWarps * kSlots);
   sm.desc = reinterpret_cast<Desc*>(sm.rfull + kCWarps * kSlots + 1);
   return sm;
 }
@@ -176,16 +181,18 @@ __device__ __forceinline__ f32x4 ld4cg(const float* p) {
   return r;
 }
 
-// TF32 split: x = hi + lo with hi, lo representable in TF32 (10-bit mantissa); hi*hi + hi*lo + lo*hi recovers
-// the fp32 product to ~2^-21 relative
+// TF32 split: the tensor core reads only the upper 19 bits of an fp32 operand (sign, 8-bit exponent, 10-bit
+// mantissa), so hi is x itself (truncated by the hardware) and lo = x - trunc(x) is exact in fp32;
+// lo*hi + hi*lo + hi*hi then recovers the fp32 product to ~2^-20 relative.  Two full-rate ALU ops per element
+// (the rounding conversion cvt.rna.tf32.f32 of the textbook split runs on a quarter-rate pipe and dominated the
+// product time).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -213,22 +220,28 @@ __device__ __forceinline__ void grid_wait(const Args& a, int g, unsigned target)
 struct Slice {
   int n_lo, n_hi, k_lo, kc, ks;
 };
-__device__ __forceinline__ Slice slice_of(const Desc& d, int c, int G) {
+__device__ __forceinline__ Slice compute_slice(const Desc& d, unsigned c, unsigned G) {   // N * G < 2^32
   Slice s;
   if (d.ksplit <= 1) {
     s.ks = 0;
-    s.n_lo = (int)(((long long)c * d.N) / G);
-    s.n_hi = (int)(((long long)(c + 1) * d.N) / G);
+    s.n_lo = (int)((c * (unsigned)d.N) / G);
+    s.n_hi = (int)(((c + 1u) * (unsigned)d.N) / G);
     s.k_lo = 0;
     s.kc = d.K;
   } else {  // CTA c works on K slice c % ksplit; the CTAs of one slice share the N rows
-    s.ks = c % d.ksplit;
-    const int i = c / d.ksplit, nc = (G - s.ks + d.ksplit - 1) / d.ksplit;
-    s.n_lo = (int)(((long long)i * d.N) / nc);
-    s.n_hi = (int)(((long long)(i + 1) * d.N) / nc);
+    const unsigned ksp = (unsigned)d.ksplit;
+    s.ks = (int)(c % ksp);
+    const unsigned i = c / ksp, nc = (G - (unsigned)s.ks + ksp - 1u) / ksp;
+    s.n_lo = (int)((i * (unsigned)d.N) / nc);
+    s.n_hi = (int)(((i + 1u) * (unsigned)d.N) / nc);
     s.kc = d.K / d.ksplit;
     s.k_lo = s.ks * s.kc;
   }
+  return s;
+}
+__device__ __forceinline__ Slice slice_of(const Desc& d, int, int) {
+  Slice s;
+  s.n_lo = d.s_n_lo; s.n_hi = d.s_n_hi; s.k_lo = d.s_k_lo; s.kc = d.s_kc; s.ks = d.s_ks;
   return s;
 }
 __device__ __forceinline__ float* weight_base(const Smem& sm, const Desc& d, const Slice& s) {
@@ -266,6 +279,40 @@ __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const 
     bulk_g2s(sm.xs + r * ld, d.X + (size_t)(b0 + r) * d.ldx + s.k_lo, row_bytes, sm.x_full);
 }
 
+// C[16 rows][8 NT cols] += A (activation fragments) x B (weight rows from shared memory), 3 x TF32.
+// FULL: every warp owns exactly kChunks chunks and NTMAX n-tiles -> no branches, the compiler interleaves freely.
+template <int NTMAX, bool FULL>
+__device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&xa)[kChunks][2], const float* wb, int ld,
+                                          int nch, int warp, int nt_run) {
+#pragma unroll
+  for (int j = 0; j < kChunks; ++j) {
+    const int c = warp + kCWarps * j;
+    if (FULL || c < nch) {
+      uint32_t ah[8], al[8];
+      // logical k = tq <-> float 4tq (+2 for the second MMA), k = tq+4 <-> float 4tq+1 (+2); A and B agree
+      split_tf32(xa[j][0].x, ah[0], al[0]); split_tf32(xa[j][1].x, ah[1], al[1]);
+      split_tf32(xa[j][0].y, ah[2], al[2]); split_tf32(xa[j][1].y, ah[3], al[3]);
+      split_tf32(xa[j][0].z, ah[4], al[4]); split_tf32(xa[j][1].z, ah[5], al[5]);
+      split_tf32(xa[j][0].w, ah[6], al[6]); split_tf32(xa[j][1].w, ah[7], al[7]);
+#pragma unroll
+      for (int nt = 0; nt < NTMAX; ++nt) {
+        if (FULL || nt < nt_run) {
+          const float4 wv = lds4(wb + nt * 8 * ld + c * 16);
+          uint32_t bh[4], bl[4];
+          split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
+          split_tf32(wv.z, bh[2], bl[2]); split_tf32(wv.w, bh[3], bl[3]);
+          mma_tf32(acc[nt][0], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], al[4], al[5], al[6], al[7], bh[2], bh[3]);
+          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
+          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
+        }
+      }
+    }
+  }
+}
+
 // ---- GEMM group-phase (consumers) --------------------------------------------------------------------------
 struct CState {
   unsigned gp;            // group-phases consumed so far (parity of x_full)
@@ -275,7 +322,7 @@ struct CState {
 
 template <int DH>
 __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const Smem& sm, CState& cs, int g, int t,
-                                           bool first_group) {
+                                           bool first_group, long long* prof) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int B = a.st.batch;
   const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
@@ -305,6 +352,7 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   __syncwarp();
   if (lane == 0) mbar_arrive(sm.x_empty);   // the tile lives in registers now: the producer may refill the slot
   if (!has_rows) return;
+  if (prof) prof[6] = clock64();
 
   // operands of the epilogue are requested now so that their latency hides behind the products
   float e_res[2], e_bias[2], e_lns[2];
@@ -312,11 +360,13 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   for (int k = 0; k < 2; ++k) {
     const int idx = tid + kConsumers * k, row = idx / kMaxRows, nl = idx - row * kMaxRows;
     const bool on = row < rows && nl < ncols;
-    e_res[k] = (on && d.R) ? __ldcg(d.R + (size_t)(b0 + row) * d.ldr + s.n_lo + nl) : 0.f;
-    e_bias[k] = (on && d.bias) ? __ldg(d.bias + s.n_lo + nl) : 0.f;
-    e_lns[k] = (on && d.ln) ? __ldg(d.lnsum + s.n_lo + nl) : 0.f;
+    e_res[k] = e_bias[k] = e_lns[k] = 0.f;   // asm volatile: issued here, ahead of the products
+    if (on && d.R) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(e_res[k]) : "l"(d.R + (size_t)(b0 + row) * d.ldr + s.n_lo + nl));
+    if (on && d.bias) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e_bias[k]) : "l"(d.bias + s.n_lo + nl));
+    if (on && d.ln) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e_lns[k]) : "l"(d.lnsum + s.n_lo + nl));
   }
 
+  if (prof) prof[11] = clock64();
   if (d.ln) {  // partial row statistics about the row's first element (plain sums merge exactly like the products)
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
@@ -347,10 +397,12 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
     }
   }
 
+  if (prof) prof[12] = clock64();
   if (first_group) {
     mbar_wait(&sm.w_full[d.hi], cs.wpar[d.hi], a.err);
     cs.wpar[d.hi] ^= 1u;
   }
+  if (prof) prof[7] = clock64();
 
   // ---- products: C[16 rows][8 NT cols] += A (activations) x B (weight rows), 3 x TF32
   float acc[3][2][4];
@@ -361,33 +413,14 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][h][i] = 0.f;
   const float* wb = weight_base(sm, d, s) + gq * ld + 4 * tq;
-#pragma unroll
-  for (int j = 0; j < kChunks; ++j) {
-    const int c = warp + kCWarps * j;
-    if (c < nch) {
-      uint32_t ah[8], al[8];
-      // logical k = tq <-> float 4tq (+2 for the second MMA), k = tq+4 <-> float 4tq+1 (+2); A and B agree
-      split_tf32(xa[j][0].x, ah[0], al[0]); split_tf32(xa[j][1].x, ah[1], al[1]);
-      split_tf32(xa[j][0].y, ah[2], al[2]); split_tf32(xa[j][1].y, ah[3], al[3]);
-      split_tf32(xa[j][0].z, ah[4], al[4]); split_tf32(xa[j][1].z, ah[5], al[5]);
-      split_tf32(xa[j][0].w, ah[6], al[6]); split_tf32(xa[j][1].w, ah[7], al[7]);
-#pragma unroll
-      for (int nt = 0; nt < 3; ++nt) {
-        if (nt < NT) {
-          const float4 wv = lds4(wb + nt * 8 * ld + c * 16);
-          uint32_t bh[4], bl[4];
-          split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
-          split_tf32(wv.z, bh[2], bl[2]); split_tf32(wv.w, bh[3], bl[3]);
-          mma_tf32(acc[nt][0], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-          mma_tf32(acc[nt][1], al[4], al[5], al[6], al[7], bh[2], bh[3]);
-          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
-          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
-        }
-      }
-    }
+  if (nch == kChunks * kCWarps) {   // K slice of 768: every warp owns exactly kChunks chunks -> straight-line code
+    if (NT == 1) mma_tiles<1, true>(acc, xa, wb, ld, nch, warp, NT);
+    else if (NT == 2) mma_tiles<2, true>(acc, xa, wb, ld, nch, warp, NT);
+    else mma_tiles<3, true>(acc, xa, wb, ld, nch, warp, NT);
+  } else {
+    mma_tiles<3, false>(acc, xa, wb, ld, nch, warp, NT);
   }
+  if (prof) prof[8] = clock64();
   {  // fragments -> cross-warp buffer [warp][row][24]
     float* rw = sm.red + warp * (kGroupRows * kMaxRows);
 #pragma unroll
@@ -401,6 +434,7 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
     }
   }
   consumer_bar();
+  if (prof) prof[9] = clock64();
 
   // ---- epilogue: one output per thread and round
 #pragma unroll
@@ -457,17 +491,25 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
       } break;
     }
   }
+  if (prof) prof[10] = clock64();
 }
 
 // ---- reduce group-phase: x[b][n] += sum_s part[s][b][n] (FFN-out partials + residual) ------------------------
 __device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g) {
   const int B = a.st.batch, G = gridDim.x, c = blockIdx.x;
   const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
-  const int n_lo = (int)(((long long)c * d.N) / G), n_hi = (int)(((long long)(c + 1) * d.N) / G), ncols = n_hi - n_lo;
+  const int n_lo = d.s_n_lo, n_hi = d.s_n_hi, ncols = n_hi - n_lo;
+  (void)G; (void)c;
   for (int idx = threadIdx.x; idx < rows * ncols; idx += kConsumers) {
     const int row = idx / ncols, n = n_lo + idx - row * ncols, b = b0 + row;
     float v = __ldcg(d.Y + (size_t)b * d.ldy + n);
-    for (int sidx = 0; sidx < d.n_parts; ++sidx) v += __ldcg(d.part + ((size_t)sidx * B + b) * d.N + n);
+    for (int s0 = 0; s0 < d.n_parts; s0 += 4) {   // four independent loads in flight
+      float pv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pv[i] = s0 + i < d.n_parts ? __ldcg(d.part + ((size_t)(s0 + i) * B + b) * d.N + n) : 0.f;
+      v += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+    }
     d.Y[(size_t)b * d.ldy + n] = v;
   }
 }
@@ -711,7 +753,20 @@ __device__ __forceinline__ int phases_per_layer(const Args& a) { return 8 + (a.n
 __device__ __forceinline__ int n_phases(const Args& a) { return 3 + phases_per_layer(a) * a.w.n_layers + 1; }
 
 template <int DH>
+__device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, float qscale, Desc& d);
+template <int DH>
 __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qscale, Desc& d) {
+  get_phase_body<DH>(a, ph, t, qscale, d);
+  if (d.kind == kGemm) {
+    const Slice s = compute_slice(d, blockIdx.x, gridDim.x);
+    d.s_n_lo = s.n_lo; d.s_n_hi = s.n_hi; d.s_k_lo = s.k_lo; d.s_kc = s.kc; d.s_ks = s.ks;
+  } else if (d.kind == kReduce) {
+    d.s_n_lo = (int)((blockIdx.x * (unsigned)d.N) / gridDim.x);
+    d.s_n_hi = (int)(((blockIdx.x + 1u) * (unsigned)d.N) / gridDim.x);
+  }
+}
+template <int DH>
+__device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, float qscale, Desc& d) {
   const int B = a.st.batch, D = a.w.d_model, H = a.w.n_heads, F = a.w.d_ffn, P = a.w.prenet_hidden;
   const int M = a.w.n_mels, S = a.st.mem_len, T = a.st.t_max, L = a.w.n_layers;
   const int ppl = phases_per_layer(a);
@@ -826,6 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
     mbar_init(&sm.w_full[1], 1);
     mbar_init(sm.pdone, 1);
     for (int i = 0; i < kCWarps * kSlots; ++i) mbar_init(&sm.rfull[i], 1);
+    *sm.sig = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int b = tid; b < B; b += kThreads) {
@@ -837,6 +893,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
 
   CState cs{0u, {0u, 0u}, 0u, 0u};
   unsigned p_gp = 0u, p_done = 0u;      // producer: group-phases staged, phase completions consumed
+  unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started
 
   for (int s = 0; s < a.n_steps; ++s) {
@@ -876,10 +933,32 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         }
       }
       __syncwarp();
+    } else if (warp == kCWarps + 1) {
+      // =========================== signaler warp (one elected lane) ===========================
+      // publishes the consumers' finished group-phases to the other CTAs: the gpu-scope release (a memory barrier
+      // that waits for the CTA's outstanding stores) runs here, off the consumers' critical path
+      if (lane == 0) {
+        for (int ph = 0; ph < n_ph; ++ph)
+          for (int g = 0; g < NG; ++g) {
+            ++s_gp;
+            long long spins = 0;
+            while (true) {
+              unsigned v;
+              asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sm.sig)) : "memory");
+              if (static_cast<int>(v - s_gp) >= 0) break;
+              if ((++spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+                atomicExch(a.err, 3);
+                break;
+              }
+            }
+            grid_arrive(a, g);
+          }
+      }
+      __syncwarp();
     } else {
       // =========================== consumer warps ===========================
       for (int ph = 0; ph < n_ph; ++ph) {
-        long long* prof = (blockIdx.x == 0 && tid == 0 && ph < kProfPhases) ? a.prof + 8 * ph : nullptr;
+        long long* prof = (blockIdx.x == 0 && tid == 0 && ph < kProfPhases) ? a.prof + kProfStride * ph : nullptr;
         for (int g = 0; g < NG; ++g) {
           if (prof && g < 2) prof[3 * g] = clock64();
           mbar_wait(sm.x_full, cs.gp & 1u, a.err);
@@ -887,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
           if (prof && g < 2) prof[3 * g + 1] = clock64();
           const Desc& d = sm.desc[ph % kDescRing];
           if (d.kind == kGemm) {
-            gemm_group<DH>(a, d, sm, cs, g, t, g == 0);
+            gemm_group<DH>(a, d, sm, cs, g, t, g == 0, g == 0 ? prof : nullptr);
           } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.x_empty);
@@ -895,10 +974,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             else if (d.kind == kReduce) reduce_group(a, d, g);
             else combine_group<DH>(a, d, sm, g, t);
           }
-          // writes of this group-phase that another CTA reads through the async proxy (TMA) need the cross-proxy fence
-          fence_proxy_async();
           consumer_bar();
-          if (tid == 0) grid_arrive(a, g);
+          if (tid == 0)   // every consumer's stores of this group-phase happen-before this (bar.sync): hand over
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sm.sig)), "r"(cs.gp) : "memory");
           if (prof && g < 2) prof[3 * g + 2] = clock64();
         }
         if (tid == 0) mbar_arrive(sm.pdone);
@@ -983,7 +1061,7 @@ static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
   };
   c.bar = reinterpret_cast<unsigned*>(take(32 * kMaxGroups));
   c.err = reinterpret_cast<int*>(take(32));
-  c.prof = reinterpret_cast<long long*>(take(2 * 8 * kProfPhases));
+  c.prof = reinterpret_cast<long long*>(take(2 * kProfStride * kProfPhases));
   c.x = take(B * D); c.q = take(B * D); c.ctx = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
   c.part = take((size_t)ksplit_for(w) * B * D);
   c.fpart = take((size_t)B * H * kMaxSplit * (dh + 4));
@@ -1015,7 +1093,7 @@ static int launch(const Args& a, cudaStream_t s) {
 int pipelined_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries) {
   using namespace pipe;
   const Carve c = carve(w, st->batch, st->scratch);
-  const int n = max_entries < 8 * kProfPhases ? max_entries : 8 * kProfPhases;
+  const int n = max_entries < kProfStride * kProfPhases ? max_entries : kProfStride * kProfPhases;
   TTS_CHECK_CUDA(cudaMemcpy(out_host, c.prof, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }

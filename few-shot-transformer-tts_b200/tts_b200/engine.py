@@ -88,15 +88,19 @@ class DecodeSession:
                 "decode_steps")
         self.t += n_steps
 
-    def phase_profile(self):
-        """[n_phases, 8] SM-clock stamps of CTA 0 for the last step: 0 start, 1 compute done, 2 barrier
-        passed; GEMM phases also 3 activations staged, 4 LayerNorm done, 5 weights landed, 6 FMA +
-        reduction done (last pass), 7 epilogue done (last pass)."""
-        n = 3 + 8 * self.engine.cfg.n_decoder_layer + 1
-        buf = (C.c_int64 * (8 * n))()
-        N.check(N.load().tts_decode_profile(C.byref(self.engine.decoder_weights()), C.byref(self._st), buf, 8 * n),
+    def phase_profile(self, n_phases=None):
+        """[n_phases, 8] SM-clock stamps of CTA 0 for the last step.  Fused kernel (impl 3): 0 start, 1 compute
+        done, 2 barrier passed; GEMM phases also 3 activations staged, 4 LayerNorm done, 5 weights landed, 6 FMA +
+        reduction done (last pass), 7 epilogue done (last pass).  Pipelined kernel (impl 4): for row group
+        g in {0, 1}: 3g wait for the group's inputs begins, 3g+1 inputs ready, 3g+2 group done and handed to the
+        signaler; GEMM phases, group 0: 6 fragments loaded, 7 weights landed, 8 products done, 9 cross-warp buffer
+        complete, 10 epilogue done (rows of 16 stamps)."""
+        n = n_phases if n_phases is not None else 3 + 8 * self.engine.cfg.n_decoder_layer + 1
+        stride = 8 if n_phases is None else 16
+        buf = (C.c_int64 * (stride * n))()
+        N.check(N.load().tts_decode_profile(C.byref(self.engine.decoder_weights()), C.byref(self._st), buf, stride * n),
                 "decode_profile")
-        return np.array(list(buf), dtype=np.int64).reshape(n, 8)
+        return np.array(list(buf), dtype=np.int64).reshape(n, stride)
 
     def alignments(self, t):
         """Views shaped like the reference's (attention.py:88): [B,H,T_kv,T_q] per layer."""
