@@ -71,8 +71,7 @@ struct Desc {
   int kind;
   // ---- GEMM: Y[b][n] = epilogue(sum_k X[b][k] W[n][k]) for the rows of one group
   const float* X; long long ldx; int K, N, ksplit;
-  const float* W; const float* W2; int n_w1; int ldw;   // W2: rows >= n_w1 come from a second matrix (mel | stop)
-  const float* bias; const float* lnsum;
+  const float* W;       // packed rows [ksplit][N][K/ksplit + 16]: weights | constant | LayerNorm row sum (tts_b200.h pk_*)
   int ln, relu, mode, hi, zero_x;
   float* Y; long long ldy; const float* R; long long ldr; float out_scale;
   float* kcache; float* vcache;
@@ -97,7 +96,8 @@ struct Smem {
   uint64_t* x_full;   // 1: producer -> consumers, tile landed / group may start
   uint64_t* x_empty;  // 1: consumers -> producer, slot free (8 arrivals)
   uint64_t* w_full;   // 2: weight slice landed (low / high placement)
-  uint64_t* pdone;    // 1: consumers finished a phase
+  uint64_t* pdone;    // phases the consumers have finished, as a plain counter (an mbarrier's parity would alias:
+                      // with a single row group the consumers can complete two phases before the loader looks)
   uint64_t* rfull;    // [8][kSlots] ring slots
   unsigned* sig;      // group-phases the consumers have finished (polled by the signaler warp)
   Desc* desc;         // [kDescRing]
@@ -216,6 +216,20 @@ __device__ __forceinline__ void grid_wait(const Args& a, int g, unsigned target)
   }
 }
 
+// spin until a shared-memory counter written with st.release.cta reaches `target`
+__device__ __forceinline__ void wait_count(const Args& a, const void* ctr, unsigned target) {
+  long long spins = 0;
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ctr)) : "memory");
+    if (static_cast<int>(v - target) >= 0) break;
+    if ((++spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
+      atomicExch(a.err, 3);
+      break;
+    }
+  }
+}
+
 // ---- work split of a GEMM phase over the CTAs -----------------------------------------------------------
 struct Slice {
   int n_lo, n_hi, k_lo, kc, ks;
@@ -251,18 +265,15 @@ __device__ __forceinline__ float* weight_base(const Smem& sm, const Desc& d, con
 }
 
 // ---- producer side ---------------------------------------------------------------------------------------
+// packed rows [n][kc + 16] (weights | constant | LayerNorm row sum | zeros): a CTA's slice is one contiguous run
 __device__ __forceinline__ void issue_weights(const Smem& sm, const Desc& d) {
   const Slice s = slice_of(d, blockIdx.x, gridDim.x);
   if (s.n_hi <= s.n_lo) return;
   const int ld = s.kc + kPad;
-  float* dst = weight_base(sm, d, s);
-  const unsigned row_bytes = (unsigned)s.kc * 4u;
+  const unsigned bytes = (unsigned)(s.n_hi - s.n_lo) * (unsigned)ld * 4u;
   uint64_t* bar = &sm.w_full[d.hi];
-  mbar_expect_tx(bar, (unsigned)(s.n_hi - s.n_lo) * row_bytes);
-  for (int n = s.n_lo; n < s.n_hi; ++n) {
-    const float* src = (n < d.n_w1 ? d.W + (size_t)n * d.ldw : d.W2 + (size_t)(n - d.n_w1) * d.ldw) + s.k_lo;
-    bulk_g2s(dst + (size_t)(n - s.n_lo) * ld, src, row_bytes, bar);
-  }
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(weight_base(sm, d, s), d.W + ((size_t)s.ks * d.N + s.n_lo) * ld, bytes, bar);
 }
 
 __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const Desc& d, int g) {
@@ -279,11 +290,15 @@ __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const 
     bulk_g2s(sm.xs + r * ld, d.X + (size_t)(b0 + r) * d.ldx + s.k_lo, row_bytes, sm.x_full);
 }
 
-// C[16 rows][8 NT cols] += A (activation fragments) x B (weight rows from shared memory), 3 x TF32.
+// C[16 rows][8 NT cols] += A (activation fragments) x B (weight rows from shared memory), 3 x TF32; the LayerNorm
+// partial sums (about the row's first element) ride along on the FMA pipe while the tensor pipe works.
 // FULL: every warp owns exactly kChunks chunks and NTMAX n-tiles -> no branches, the compiler interleaves freely.
+struct RowStats {
+  float s0[2], q0[2], s1[2], q1[2];   // rows gq / gq+8, two interleaved accumulators each
+};
 template <int NTMAX, bool FULL>
 __device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&xa)[kChunks][2], const float* wb, int ld,
-                                          int nch, int warp, int nt_run) {
+                                          int nch, int warp, int nt_run, float sh0, float sh1, RowStats& rs) {
 #pragma unroll
   for (int j = 0; j < kChunks; ++j) {
     const int c = warp + kCWarps * j;
@@ -309,6 +324,14 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&
           mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
         }
       }
+      {
+        const float d0 = xa[j][0].x - sh0, d1 = xa[j][0].y - sh0, d2 = xa[j][0].z - sh0, d3 = xa[j][0].w - sh0;
+        const float e0 = xa[j][1].x - sh1, e1 = xa[j][1].y - sh1, e2 = xa[j][1].z - sh1, e3 = xa[j][1].w - sh1;
+        rs.s0[0] += d0 + d2; rs.s0[1] += d1 + d3;
+        rs.q0[0] = fmaf(d0, d0, fmaf(d2, d2, rs.q0[0])); rs.q0[1] = fmaf(d1, d1, fmaf(d3, d3, rs.q0[1]));
+        rs.s1[0] += e0 + e2; rs.s1[1] += e1 + e3;
+        rs.q1[0] = fmaf(e0, e0, fmaf(e2, e2, rs.q1[0])); rs.q1[1] = fmaf(e1, e1, fmaf(e3, e3, rs.q1[1]));
+      }
     }
   }
 }
@@ -319,6 +342,39 @@ struct CState {
   unsigned wpar[2];       // parity of the two weight barriers
   unsigned issued, consumed;  // K/V ring tiles of this warp
 };
+
+template <int DH>
+__device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Smem& sm, const Slice& s, int b, int n, int t,
+                                          float v, float res) {
+  switch (d.mode) {
+    case kPlain:
+      d.Y[(size_t)b * d.ldy + n] = v * d.out_scale + res;
+      break;
+    case kPartial:
+      d.Y[((size_t)s.ks * a.st.batch + b) * d.ldy + n] = v;
+      break;
+    case kQkv: {
+      const int H = a.w.n_heads, D = H * DH;
+      const int which = n / D, cc = n - which * D;
+      if (which == 0) {
+        d.Y[(size_t)b * d.ldy + cc] = v * d.out_scale;
+      } else {
+        const int h = cc / DH, dd = cc - h * DH;
+        float* dst = which == 1 ? d.kcache : d.vcache;
+        dst[(((size_t)b * H + h) * a.st.t_max + t) * DH + dd] = v;
+      }
+    } break;
+    case kPrenetOut: {  // modules.py:114-118
+      const bool have = t > 0 && (t - 1) < sm.len[b];
+      d.Y[(size_t)b * d.ldy + n] = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * d.N + n) * __ldg(a.w.pe_scale);
+    } break;
+    case kFinal: {  // modules.py:144, tacotron.py:112-115
+      const bool on = t < sm.len[b];
+      if (n < a.w.n_mels) a.st.frames[((size_t)b * a.st.t_max + t) * a.w.n_mels + n] = on ? v : 0.f;
+      else a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
+    } break;
+  }
+}
 
 template <int DH>
 __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const Smem& sm, CState& cs, int g, int t,
@@ -354,34 +410,45 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   if (!has_rows) return;
   if (prof) prof[6] = clock64();
 
-  // operands of the epilogue are requested now so that their latency hides behind the products
-  float e_res[2], e_bias[2], e_lns[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int idx = tid + kConsumers * k, row = idx / kMaxRows, nl = idx - row * kMaxRows;
-    const bool on = row < rows && nl < ncols;
-    e_res[k] = e_bias[k] = e_lns[k] = 0.f;   // asm volatile: issued here, ahead of the products
-    if (on && d.R) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(e_res[k]) : "l"(d.R + (size_t)(b0 + row) * d.ldr + s.n_lo + nl));
-    if (on && d.bias) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e_bias[k]) : "l"(d.bias + s.n_lo + nl));
-    if (on && d.ln) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(e_lns[k]) : "l"(d.lnsum + s.n_lo + nl));
+  // epilogue mapping: thread (row = tid / 16, cg = tid % 16) finishes columns cg and cg + 16 of its row.
+  // The residual is requested now so that its latency hides behind the products.
+  const int erow = tid >> 4, ecg = tid & 15;
+  const bool on0 = erow < rows && ecg < ncols, on1 = erow < rows && ecg + 16 < ncols;
+  float res0 = 0.f, res1 = 0.f;
+  if (d.R != nullptr) {
+    const float* rp = d.R + (size_t)(b0 + erow) * d.ldr + s.n_lo + ecg;
+    if (on0) res0 = __ldcg(rp);
+    if (on1) res1 = __ldcg(rp + 16);
   }
 
-  if (prof) prof[11] = clock64();
-  if (d.ln) {  // partial row statistics about the row's first element (plain sums merge exactly like the products)
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  if (first_group) {
+    mbar_wait(&sm.w_full[d.hi], cs.wpar[d.hi], a.err);
+    cs.wpar[d.hi] ^= 1u;
+  }
+  if (prof) prof[7] = clock64();
+
+  // ---- products
+  float acc[3][2][4];
 #pragma unroll
-    for (int j = 0; j < kChunks; ++j) {
-      if (warp + kCWarps * j < nch) {
-        const float v0[4] = {xa[j][0].x, xa[j][0].y, xa[j][0].z, xa[j][0].w};
-        const float v1[4] = {xa[j][1].x, xa[j][1].y, xa[j][1].z, xa[j][1].w};
+  for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d0 = v0[e] - sh0, d1 = v1[e] - sh1;
-          s0 += d0; q0 = fmaf(d0, d0, q0);
-          s1 += d1; q1 = fmaf(d1, d1, q1);
-        }
-      }
-    }
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][h][i] = 0.f;
+  RowStats rs;
+  rs.s0[0] = rs.s0[1] = rs.q0[0] = rs.q0[1] = rs.s1[0] = rs.s1[1] = rs.q1[0] = rs.q1[1] = 0.f;
+  const float* wbase = weight_base(sm, d, s);
+  const float* wb = wbase + gq * ld + 4 * tq;
+  if (nch == kChunks * kCWarps) {   // K slice of 768: every warp owns exactly kChunks chunks -> straight-line code
+    if (NT == 1) mma_tiles<1, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    else if (NT == 2) mma_tiles<2, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    else mma_tiles<3, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+  } else {
+    mma_tiles<3, false>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+  }
+  if (prof) prof[8] = clock64();
+  if (d.ln) {  // row statistics: merge the 4 lanes that share a row, one record per warp and row
+    float s0 = rs.s0[0] + rs.s0[1], q0 = rs.q0[0] + rs.q0[1], s1 = rs.s1[0] + rs.s1[1], q1 = rs.q1[0] + rs.q1[1];
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
       s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
@@ -396,31 +463,6 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
       }
     }
   }
-
-  if (prof) prof[12] = clock64();
-  if (first_group) {
-    mbar_wait(&sm.w_full[d.hi], cs.wpar[d.hi], a.err);
-    cs.wpar[d.hi] ^= 1u;
-  }
-  if (prof) prof[7] = clock64();
-
-  // ---- products: C[16 rows][8 NT cols] += A (activations) x B (weight rows), 3 x TF32
-  float acc[3][2][4];
-#pragma unroll
-  for (int nt = 0; nt < 3; ++nt)
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[nt][h][i] = 0.f;
-  const float* wb = weight_base(sm, d, s) + gq * ld + 4 * tq;
-  if (nch == kChunks * kCWarps) {   // K slice of 768: every warp owns exactly kChunks chunks -> straight-line code
-    if (NT == 1) mma_tiles<1, true>(acc, xa, wb, ld, nch, warp, NT);
-    else if (NT == 2) mma_tiles<2, true>(acc, xa, wb, ld, nch, warp, NT);
-    else mma_tiles<3, true>(acc, xa, wb, ld, nch, warp, NT);
-  } else {
-    mma_tiles<3, false>(acc, xa, wb, ld, nch, warp, NT);
-  }
-  if (prof) prof[8] = clock64();
   {  // fragments -> cross-warp buffer [warp][row][24]
     float* rw = sm.red + warp * (kGroupRows * kMaxRows);
 #pragma unroll
@@ -436,60 +478,38 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   consumer_bar();
   if (prof) prof[9] = clock64();
 
-  // ---- epilogue: one output per thread and round
+  // ---- epilogue: every load first (branch-free), then the arithmetic of both outputs
+  {
+    const int nl0 = min(ecg, NT * 8 - 1), nl1 = min(ecg + 16, NT * 8 - 1);   // clamped: loads stay inside the slice's tiles
+    const float* rr = sm.red + erow * kMaxRows;
+    float v0 = 0.f, v1 = 0.f, S = 0.f, Q = 0.f;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int idx = tid + kConsumers * k, row = idx / kMaxRows, nl = idx - row * kMaxRows;
-    if (row >= rows || nl >= ncols || row >= kGroupRows) continue;
-    const int b = b0 + row, n = s.n_lo + nl;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < kCWarps; ++w) v += sm.red[w * (kGroupRows * kMaxRows) + row * kMaxRows + nl];
+    for (int w = 0; w < kCWarps; ++w) {
+      v0 += rr[w * (kGroupRows * kMaxRows) + nl0];
+      v1 += rr[w * (kGroupRows * kMaxRows) + nl1];
+      const float2 p = *reinterpret_cast<const float2*>(sm.spart + (w * kGroupRows + erow) * 2);
+      S += p.x;
+      Q += p.y;
+    }
+    const float2 c0 = *reinterpret_cast<const float2*>(wbase + nl0 * ld + s.kc);   // (constant, LayerNorm row sum)
+    const float2 c1 = *reinterpret_cast<const float2*>(wbase + nl1 * ld + s.kc);
     if (d.ln) {  // LayerNorm (eps 1e-6, modules.py:88) applied to the finished product
-      float S = 0.f, Q = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCWarps; ++w) {
-        const float2 p = *reinterpret_cast<const float2*>(sm.spart + (w * kGroupRows + row) * 2);
-        S += p.x;
-        Q += p.y;
-      }
       const float invK = 1.f / (float)d.K;
       const float ms = S * invK;
       const float var = fmaxf(Q * invK - ms * ms, 0.f);
       const float rstd = rsqrtf(var + 1e-6f);
-      const float mean = sm.sshift[row] + ms;
-      v = rstd * v - rstd * mean * e_lns[k];
+      const float nm = -rstd * (sm.sshift[erow] + ms);
+      v0 = fmaf(rstd, v0, nm * c0.y);
+      v1 = fmaf(rstd, v1, nm * c1.y);
     }
-    v += e_bias[k];
-    if (d.relu) v = fmaxf(v, 0.f);
-    switch (d.mode) {
-      case kPlain:
-        d.Y[(size_t)b * d.ldy + n] = v * d.out_scale + e_res[k];
-        break;
-      case kPartial:
-        d.Y[((size_t)s.ks * B + b) * d.ldy + n] = v;
-        break;
-      case kQkv: {
-        const int H = a.w.n_heads, D = H * DH;
-        const int which = n / D, cc = n - which * D;
-        if (which == 0) {
-          d.Y[(size_t)b * d.ldy + cc] = v * d.out_scale;
-        } else {
-          const int h = cc / DH, dd = cc - h * DH;
-          float* dst = which == 1 ? d.kcache : d.vcache;
-          dst[(((size_t)b * H + h) * a.st.t_max + t) * DH + dd] = v;
-        }
-      } break;
-      case kPrenetOut: {  // modules.py:114-118
-        const bool have = t > 0 && (t - 1) < sm.len[b];
-        d.Y[(size_t)b * d.ldy + n] = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * d.N + n) * __ldg(a.w.pe_scale);
-      } break;
-      case kFinal: {  // modules.py:144, tacotron.py:112-115
-        const bool on = t < sm.len[b];
-        if (n < a.w.n_mels) a.st.frames[((size_t)b * a.st.t_max + t) * a.w.n_mels + n] = on ? v : 0.f;
-        else a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
-      } break;
+    v0 += c0.x;
+    v1 += c1.x;
+    if (d.relu) {
+      v0 = fmaxf(v0, 0.f);
+      v1 = fmaxf(v1, 0.f);
     }
+    if (on0) store_out<DH>(a, d, sm, s, b0 + erow, s.n_lo + ecg, t, v0, res0);
+    if (on1) store_out<DH>(a, d, sm, s, b0 + erow, s.n_lo + ecg + 16, t, v1, res1);
   }
   if (prof) prof[10] = clock64();
 }
@@ -777,23 +797,23 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   d.ksplit = 1;
   if (ph == 0) {         // prenet (tacotron.py:55-65)
     d.X = a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * M; d.ldx = (long long)T * M; d.zero_x = t == 0;
-    d.K = M; d.N = P; d.W = a.w.prenet_w0; d.n_w1 = P; d.ldw = M; d.bias = a.w.prenet_b0; d.relu = 1;
+    d.K = M; d.N = P; d.W = a.w.pk_pre0; d.relu = 1;
     d.mode = kPlain; d.Y = a.p0; d.ldy = P; d.hi = 1;
     return;
   }
   if (ph == 1) {
-    d.X = a.p0; d.ldx = P; d.K = P; d.N = P; d.W = a.w.prenet_w1; d.n_w1 = P; d.ldw = P; d.bias = a.w.prenet_b1;
+    d.X = a.p0; d.ldx = P; d.K = P; d.N = P; d.W = a.w.pk_pre1;
     d.relu = 1; d.mode = kPlain; d.Y = a.p1; d.ldy = P; d.hi = 0;
     return;
   }
   if (ph == 2) {         // + shift / mask / PE (modules.py:114-118)
-    d.X = a.p1; d.ldx = P; d.K = P; d.N = D; d.W = a.w.prenet_w2; d.n_w1 = D; d.ldw = P; d.mode = kPrenetOut;
+    d.X = a.p1; d.ldx = P; d.K = P; d.N = D; d.W = a.w.pk_pre2; d.mode = kPrenetOut;
     d.Y = a.x; d.ldy = D; d.hi = 1;
     return;
   }
   if (ph == 3 + ppl * L) {  // final LN + mel / stop projections
-    d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = M + 1; d.W = a.w.w_mel_ln; d.W2 = a.w.w_stop_ln; d.n_w1 = M;
-    d.ldw = D; d.bias = a.w.c_out_ln; d.lnsum = a.w.s_out_ln; d.mode = kFinal; d.hi = 0;
+    d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = M + 1; d.W = a.w.pk_final;
+    d.mode = kFinal; d.hi = 0;
     return;
   }
   const int l = (ph - 3) / ppl;
@@ -811,8 +831,8 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   const int ring_floats = kWFloats - ((oproj_rows + 7) / 8) * 8 * (D + kPad);
   switch (id) {
     case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = 3 * D; d.W = lw.w_qkv_ln; d.n_w1 = 3 * D; d.ldw = D;
-      d.bias = lw.c_qkv_ln; d.lnsum = lw.s_qkv_ln; d.mode = kQkv; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = 3 * D; d.W = lw.pk_qkv;
+      d.mode = kQkv; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
       d.kcache = a.st.self_k + self_off; d.vcache = a.st.self_v + self_off; d.hi = 0;
       break;
     case 1:
@@ -825,12 +845,12 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kCombine; d.n_keys = t + 1; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
       break;
     case 3:  // output projection + residual (attention.py:118-119, modules.py:132)
-      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_self_out; d.n_w1 = D; d.ldw = D; d.mode = kPlain;
+      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_self_out; d.mode = kPlain;
       d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
       break;
     case 4:  // LN + cross query
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_cross_q_ln; d.n_w1 = D; d.ldw = D;
-      d.bias = lw.c_cross_q_ln; d.lnsum = lw.s_cross_q_ln; d.mode = kPlain; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_cross_q;
+      d.mode = kPlain; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
       d.hi = 0;
       break;
     case 5:
@@ -843,15 +863,15 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kCombine; d.n_keys = S; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
       break;
     case 7:
-      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.w_cross_out; d.n_w1 = D; d.ldw = D; d.mode = kPlain;
+      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_cross_out; d.mode = kPlain;
       d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
       break;
     case 8:  // LN + FFN-in + ReLU (modules.py:14-17)
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = F; d.W = lw.w_ffn_in_ln; d.n_w1 = F; d.ldw = D;
-      d.bias = lw.c_ffn_in_ln; d.lnsum = lw.s_ffn_in_ln; d.relu = 1; d.mode = kPlain; d.Y = a.hid; d.ldy = F; d.hi = 0;
+      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = F; d.W = lw.pk_ffn_in;
+      d.relu = 1; d.mode = kPlain; d.Y = a.hid; d.ldy = F; d.hi = 0;
       break;
     case 9:  // FFN-out: K-split partials, or + residual directly
-      d.X = a.hid; d.ldx = F; d.K = F; d.N = D; d.W = lw.w_ffn_out; d.n_w1 = D; d.ldw = F; d.hi = 1;
+      d.X = a.hid; d.ldx = F; d.K = F; d.N = D; d.W = lw.pk_ffn_out; d.hi = 1;
       if (red) {
         d.ksplit = a.ksplit; d.mode = kPartial; d.Y = a.part; d.ldy = D;
       } else {
@@ -879,7 +899,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
     mbar_init(sm.x_empty, kCWarps);
     mbar_init(&sm.w_full[0], 1);
     mbar_init(&sm.w_full[1], 1);
-    mbar_init(sm.pdone, 1);
+    *reinterpret_cast<volatile unsigned*>(sm.pdone) = 0u;
     for (int i = 0; i < kCWarps * kSlots; ++i) mbar_init(&sm.rfull[i], 1);
     *sm.sig = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -892,7 +912,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   const int t0 = *a.st.step_counter;
 
   CState cs{0u, {0u, 0u}, 0u, 0u};
-  unsigned p_gp = 0u, p_done = 0u;      // producer: group-phases staged, phase completions consumed
+  unsigned p_gp = 0u;                   // producer: group-phases staged
   unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started
 
@@ -917,19 +937,11 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             if (g == 0 && ph + 1 < n_ph) {
               Desc& dn = sm.desc[(ph + 1) % kDescRing];
               get_phase<DH>(a, ph + 1, t, qscale, dn);
-              if (ph >= 1) {                            // the consumers are done with phase ph-1: its weight half
-                mbar_wait(sm.pdone, p_done & 1u, a.err);  // (and the K/V rings) may be overwritten
-                ++p_done;
-              }
+              if (ph >= 1) wait_count(a, sm.pdone, epoch + ph);   // the consumers are done with phase ph-1: its weight
+                                                                  // half (and the K/V rings) may be overwritten
               if (dn.kind == kGemm) issue_weights(sm, dn);
             }
           }
-        }
-        // completions of the last two phases of this step (keeps the parity in lock-step)
-        const int left = n_ph >= 2 ? 2 : 1;
-        for (int i = 0; i < left; ++i) {
-          mbar_wait(sm.pdone, p_done & 1u, a.err);
-          ++p_done;
         }
       }
       __syncwarp();
@@ -941,16 +953,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         for (int ph = 0; ph < n_ph; ++ph)
           for (int g = 0; g < NG; ++g) {
             ++s_gp;
-            long long spins = 0;
-            while (true) {
-              unsigned v;
-              asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sm.sig)) : "memory");
-              if (static_cast<int>(v - s_gp) >= 0) break;
-              if ((++spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
-                atomicExch(a.err, 3);
-                break;
-              }
-            }
+            wait_count(a, sm.sig, s_gp);
             grid_arrive(a, g);
           }
       }
@@ -979,7 +982,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sm.sig)), "r"(cs.gp) : "memory");
           if (prof && g < 2) prof[3 * g + 2] = clock64();
         }
-        if (tid == 0) mbar_arrive(sm.pdone);
+        if (tid == 0)
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sm.pdone)), "r"(epoch + ph + 1u) : "memory");
       }
       if (tid == 0)
         for (int g = 0; g < NG; ++g) grid_wait(a, g, (epoch + n_ph) * G);   // the step is complete everywhere
@@ -1105,14 +1109,13 @@ bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   const int G = num_sms();
   const int D = w->d_model, F = w->d_ffn, P = w->prenet_hidden, M = w->n_mels;
   if (D > kKC || D % 16 != 0 || P > kKC || P % 16 != 0 || M > kKC || M % 16 != 0 || F % 16 != 0) return false;
-  if (!w->w_mel_ln || !w->w_stop_ln || !w->c_out_ln || !w->s_out_ln) return false;   // packed operands required
+  if (!w->pk_pre0 || !w->pk_pre1 || !w->pk_pre2 || !w->pk_final) return false;   // packed operands required
   for (int l = 0; l < w->n_layers; ++l) {
     const TtsDecLayerWeights& lw = w->layer[l];
-    if (!lw.w_qkv_ln || !lw.c_qkv_ln || !lw.s_qkv_ln || !lw.w_cross_q_ln || !lw.c_cross_q_ln || !lw.s_cross_q_ln ||
-        !lw.w_ffn_in_ln || !lw.c_ffn_in_ln || !lw.s_ffn_in_ln)
-      return false;
+    if (!lw.pk_qkv || !lw.pk_self_out || !lw.pk_cross_q || !lw.pk_cross_out || !lw.pk_ffn_in || !lw.pk_ffn_out) return false;
   }
   const int ks = ksplit_for(w);
+  if (w->pk_ksplit != ks) return false;
   if (F % ks != 0 || (F / ks) % 16 != 0 || F / ks > kKC || ks > G) return false;
   if (st->batch > kMaxBatch) return false;
   const int dh = D / w->n_heads;

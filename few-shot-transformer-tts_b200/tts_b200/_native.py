@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
 TTS_MAX_LAYERS = 16
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -31,14 +31,16 @@ class DecLayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln_self_g", "ln_self_b", "w_qkv", "w_self_out", "ln_cross_g", "ln_cross_b", "w_cross_q", "w_cross_kv",
         "w_cross_out", "ln_ffn_g", "ln_ffn_b", "w_ffn_in", "w_ffn_out", "w_qkv_ln", "c_qkv_ln", "w_cross_q_ln",
-        "c_cross_q_ln", "w_ffn_in_ln", "c_ffn_in_ln", "s_qkv_ln", "s_cross_q_ln", "s_ffn_in_ln")]
+        "c_cross_q_ln", "w_ffn_in_ln", "c_ffn_in_ln", "pk_qkv", "pk_self_out", "pk_cross_q", "pk_cross_out", "pk_ffn_in", "pk_ffn_out")]
 
 
 class DecoderWeights(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("n_layers", "d_model", "n_heads", "d_ffn", "n_mels", "prenet_hidden")] +
                 [(n, C.c_void_p) for n in ("prenet_w0", "prenet_b0", "prenet_w1", "prenet_b1", "prenet_w2", "pe_scale",
                                            "pe_table", "ln_out_g", "ln_out_b", "w_mel", "w_stop", "b_stop", "w_mel_ln",
-                                           "w_stop_ln", "c_out_ln", "s_out_ln")] +
+                                           "w_stop_ln", "c_out_ln", "pk_pre0", "pk_pre1", "pk_pre2",
+                                           "pk_final")] +
+                [("pk_ksplit", C.c_int32), ("pk_reserved", C.c_int32)] +
                 [("layer", DecLayerWeights * TTS_MAX_LAYERS)])
 
 

@@ -199,23 +199,48 @@ class TtsEngine:
             keep.extend([wf, cf, sf])
             return wf, cf, sf
 
+        def pack(wt, const=None, rowsum=None, ksplit=1):
+            """[ksplit][N][K/ksplit + 16] rows for the pipelined kernel (include/tts_b200.h, pk_*)."""
+            with torch.no_grad():
+                n, k = wt.shape
+                kc = k // ksplit
+                out = torch.zeros((ksplit, n, kc + 16), device=wt.device, dtype=torch.float32)
+                out[:, :, :kc] = wt.detach().view(n, ksplit, kc).permute(1, 0, 2)
+                if const is not None:
+                    out[0, :, kc] = const.detach().view(-1)
+                if rowsum is not None:
+                    out[0, :, kc + 1] = rowsum.view(-1)
+            keep.append(out)
+            return out.data_ptr()
+
+        ksplit = (dw.d_ffn + 767) // 768   # K split of FFN-out in the pipelined kernel (pipelined.cu: ksplit_for)
+        if dw.d_ffn % ksplit:
+            ksplit = 1
         for l in range(cfg.n_decoder_layer):
             lw = dw.layer[l]
             wf, cf, sf = fold(f"{p}self_attentions.{l}.qkv_transform.weight", f"{p}attn_layer_norms.{l}.weight",
                               f"{p}attn_layer_norms.{l}.bias")
-            lw.w_qkv_ln, lw.c_qkv_ln, lw.s_qkv_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+            lw.w_qkv_ln, lw.c_qkv_ln, lw.pk_qkv = wf.data_ptr(), cf.data_ptr(), pack(wf, cf, sf)
             wf, cf, sf = fold(f"{p}encdec_attentions.{l}.q_transform.weight", f"{p}encdec_layer_norms.{l}.weight",
                               f"{p}encdec_layer_norms.{l}.bias")
-            lw.w_cross_q_ln, lw.c_cross_q_ln, lw.s_cross_q_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+            lw.w_cross_q_ln, lw.c_cross_q_ln, lw.pk_cross_q = wf.data_ptr(), cf.data_ptr(), pack(wf, cf, sf)
             wf, cf, sf = fold(f"{p}ffn_layers.{l}.input_layer.weight", f"{p}ffn_layer_norms.{l}.weight",
                               f"{p}ffn_layer_norms.{l}.bias")
-            lw.w_ffn_in_ln, lw.c_ffn_in_ln, lw.s_ffn_in_ln = wf.data_ptr(), cf.data_ptr(), sf.data_ptr()
+            lw.w_ffn_in_ln, lw.c_ffn_in_ln, lw.pk_ffn_in = wf.data_ptr(), cf.data_ptr(), pack(wf, cf, sf)
+            lw.pk_self_out = pack(w[f"{p}self_attentions.{l}.output_transform.weight"])
+            lw.pk_cross_out = pack(w[f"{p}encdec_attentions.{l}.output_transform.weight"])
+            lw.pk_ffn_out = pack(w[f"{p}ffn_layers.{l}.output_layer.weight"], ksplit=ksplit)
         wm, cm, sm_ = fold("decoder.mel_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
         ws, cs, ss_ = fold("decoder.stop_net.weight", p + "output_layer_norm.weight", p + "output_layer_norm.bias")
         cout = torch.cat([cm, cs]).contiguous()
         sout = torch.cat([sm_, ss_]).contiguous()
         keep.extend([cout, sout])
-        dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln, dw.s_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr(), sout.data_ptr()
+        dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr()
+        dw.pk_final = pack(torch.cat([wm, ws], 0), cout, sout)
+        dw.pk_pre0 = pack(w["decoder.prenet.dense0.weight"], w["decoder.prenet.dense0.bias"])
+        dw.pk_pre1 = pack(w["decoder.prenet.dense1.weight"], w["decoder.prenet.dense1.bias"])
+        dw.pk_pre2 = pack(w["decoder.prenet.dense_final.weight"])
+        dw.pk_ksplit = ksplit
         self._dec_keep = keep  # owns the packed tensors for as long as the struct is cached
         self._dec_w, self._dec_key = dw, key
         return dw

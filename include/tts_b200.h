@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 5
+#define TTS_ABI_VERSION 6
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -140,11 +140,20 @@ typedef struct TtsDecLayerWeights {
   const float* c_cross_q_ln; /* [D] */
   const float* w_ffn_in_ln;  /* [4D][D] */
   const float* c_ffn_in_ln;  /* [4D] */
-  /* Row sums of the folded matrices, s_ln[n] = sum_k W_ln[n][k]: the pipelined kernel applies LayerNorm AFTER the
-   * product, LN(x) W^T = rstd * (x W_ln^T) - rstd * mean * s_ln + c_ln. */
-  const float* s_qkv_ln;     /* [3D] */
-  const float* s_cross_q_ln; /* [D] */
-  const float* s_ffn_in_ln;  /* [4D] */
+  /* Packed operands of the pipelined kernel: one row per output n, K + 16 floats:
+   *   [0, K)  the weight row (LayerNorm-folded where a LayerNorm precedes the projection),
+   *   [K]     the additive constant (bias, or c_ln[n]),
+   *   [K+1]   s_ln[n] = sum_k W_ln[n][k]: LayerNorm is applied AFTER the product,
+   *           LN(x) W^T = rstd * (x W_ln^T) - rstd * mean * s_ln + c_ln,
+   *   rest    zero.  A CTA's slice of rows is one contiguous run: one TMA bulk copy per phase brings weights
+   *           and epilogue constants, already laid out with the bank-spreading row padding the MMA loads want.
+   * pk_ffn_out is K-split: [pk_ksplit][D][4D / pk_ksplit + 16]. */
+  const float* pk_qkv;       /* [3D][D+16] */
+  const float* pk_self_out;  /* [D][D+16] */
+  const float* pk_cross_q;   /* [D][D+16] */
+  const float* pk_cross_out; /* [D][D+16] */
+  const float* pk_ffn_in;    /* [4D][D+16] */
+  const float* pk_ffn_out;   /* [pk_ksplit][D][4D/pk_ksplit+16] */
 } TtsDecLayerWeights;
 
 typedef struct TtsDecoderWeights {
@@ -164,7 +173,12 @@ typedef struct TtsDecoderWeights {
   const float* w_mel_ln;    /* [M][D]  mel_net with the output LayerNorm folded in (see TtsDecLayerWeights) */
   const float* w_stop_ln;   /* [1][D] */
   const float* c_out_ln;    /* [M+1]   W_mel * beta_out, w_stop * beta_out */
-  const float* s_out_ln;    /* [M+1]   row sums of w_mel_ln | w_stop_ln */
+  const float* pk_pre0;     /* [P][M+16]   packed like TtsDecLayerWeights.pk_* */
+  const float* pk_pre1;     /* [P][P+16] */
+  const float* pk_pre2;     /* [D][P+16] */
+  const float* pk_final;    /* [M+1][D+16]  w_mel_ln rows, then w_stop_ln; constant = c_out_ln */
+  int32_t pk_ksplit;        /* K split of pk_ffn_out: ceil(4D / 768) */
+  int32_t pk_reserved;
   TtsDecLayerWeights layer[TTS_MAX_LAYERS];
 } TtsDecoderWeights;
 
