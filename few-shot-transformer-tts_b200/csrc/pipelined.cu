@@ -163,7 +163,10 @@ __device__ __forceinline__ void bulk_g2s(float* dst, const float* src, unsigned 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy global writes (observed through an acquire) -> later async-proxy (TMA) reads of global memory.
+// The state-space-qualified form is a single FENCE.VIEW.ASYNC.G; the unqualified one adds a MEMBAR.ALL.GPU that
+// waits for every outstanding store of the warp (8 % of all stall samples in profiles/r2_pipe_a).
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ f32x4 ld4s(const float* p) {
@@ -339,7 +342,7 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&
 // ---- GEMM group-phase (consumers) --------------------------------------------------------------------------
 struct CState {
   unsigned gp;            // group-phases consumed so far (parity of x_full)
-  unsigned wpar[2];       // parity of the two weight barriers
+  unsigned wpar0, wpar1;  // parity of the two weight barriers (scalars: a dynamically indexed array would live in local memory)
   unsigned issued, consumed;  // K/V ring tiles of this warp
 };
 
@@ -421,9 +424,11 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
     if (on1) res1 = __ldcg(rp + 16);
   }
 
+  if (prof) prof[11] = clock64();
   if (first_group) {
-    mbar_wait(&sm.w_full[d.hi], cs.wpar[d.hi], a.err);
-    cs.wpar[d.hi] ^= 1u;
+    mbar_wait(&sm.w_full[d.hi], d.hi ? cs.wpar1 : cs.wpar0, a.err);
+    if (d.hi) cs.wpar1 ^= 1u;
+    else cs.wpar0 ^= 1u;
   }
   if (prof) prof[7] = clock64();
 
@@ -554,6 +559,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
   const int sc_cap = at.ring_floats - kCWarps * kSlots * kSlotF;
   const bool sc_ok = per <= sc_cap;                                   // else fall back to read-modify-write in HBM
 
+  unsigned issued = cs.issued, consumed = cs.consumed;   // registers (a by-reference capture would pin cs in local memory)
   // ---- producer cursor (next tile this warp will request) ----
   int pu = blockIdx.x, pi = warp;
   auto issue_next = [&]() {
@@ -568,7 +574,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     }
     if (pu >= n_units) return;
     const int key0 = j0 + pi * kTK, nk = min(kTK, j1 - key0);
-    const int slot = cs.issued % kSlots;
+    const int slot = issued % kSlots;
     if (lane == 0) {
       const unsigned bytes = (unsigned)nk * DH * 4u;
       mbar_expect_tx(&full[slot], 2u * bytes);
@@ -576,10 +582,10 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       bulk_g2s(ring + slot * kSlotF, at.kc + off, bytes, &full[slot]);
       bulk_g2s(ring + slot * kSlotF + kTile, at.vc + off, bytes, &full[slot]);
     }
-    cs.issued++;
+    issued++;
     pi += kCWarps;
   };
-  fence_proxy_async();  // the K/V row appended by other CTAs in the previous phase is read through the async proxy
+  if (lane == 0) fence_proxy_async();  // the K/V row appended by other CTAs in the previous phase is read by TMA
 #pragma unroll
   for (int sl = 0; sl < kSlots; ++sl) issue_next();
 
@@ -614,8 +620,8 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     const int n_tiles = (j1 - j0 + kTK - 1) / kTK;
     for (int ti = warp; ti < n_tiles; ti += kCWarps) {
       const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
-      const int slot = cs.consumed % kSlots;
-      mbar_wait(&full[slot], (cs.consumed / kSlots) & 1u, a.err);
+      const int slot = consumed % kSlots;
+      mbar_wait(&full[slot], (consumed / kSlots) & 1u, a.err);
       const float* kt = ring + slot * kSlotF;
       const float* vt = kt + kTile;
       float sv[kRounds];
@@ -668,7 +674,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
         }
       }
       m_run = m_new;
-      cs.consumed++;
+      consumed++;
       __syncwarp();   // every lane is done with this slot before it is refilled
       issue_next();
     }
@@ -724,6 +730,8 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     }
     consumer_bar();  // wrec / sc are reused by the next unit
   }
+  cs.issued = issued;
+  cs.consumed = consumed;
 }
 
 // ---- combine group-phase (only when the K/V streams were split, i.e. small batches): partials -> ctx, align rows
@@ -911,7 +919,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   __syncthreads();
   const int t0 = *a.st.step_counter;
 
-  CState cs{0u, {0u, 0u}, 0u, 0u};
+  CState cs{0u, 0u, 0u, 0u, 0u};
   unsigned p_gp = 0u;                   // producer: group-phases staged
   unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started

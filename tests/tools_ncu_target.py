@@ -20,9 +20,9 @@ batch = O.synth_batch(cfg, batch=B, text_len=258, n_frames=4, seed=1)
 mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
 sess = eng.new_session(B, 258, cfg.max_generation_frames, "encdec")
 sess.begin(mem, batch["input_lengths"].cuda())
-sess.step(T0)
+sess.step(T0, impl=int(os.environ.get("PIMPL", "0")))
 torch.cuda.synchronize()
 for _ in range(3):
-    sess.step(NS)
+    sess.step(NS, impl=int(os.environ.get("PIMPL", "0")))
     torch.cuda.synchronize()
 print("done", sess.t)

@@ -45,10 +45,11 @@ for target in steps:
             tot[i] += cols[i] * n
         print("   %-7s %3d %8.2f %8.2f %8.2f %8.2f %8.2f" % ((k, n) + tuple(cols)))
     print("   %-7s %3s %8.1f %8.1f %8.1f %8.1f %8.1f" % (("sum", "") + tuple(tot)))
-    print("   GEMM group 0 detail (us): frags | W wait | products | stats + C + barrier | epilogue | end barrier")
+    print("   GEMM group 0 detail (us): frags | res-loads | W wait | products | stats + C + barrier | epilogue | end barrier")
     for k, v in kinds.items():
         if k in ("self", "cross", "red", "final"):
             continue
         n = len(v)
         f = lambda i, j: sum(d[i] - d[j] for d in v) / n
-        print("   %-7s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f" % (k, f(6, 1), f(7, 6), f(8, 7), f(9, 8), f(10, 9), f(2, 10)))
+        print("   %-7s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f" % (k, f(6, 1), f(11, 6), f(7, 11), f(8, 7), f(9, 8), f(10, 9),
+                                                                   f(2, 10)))
