@@ -33,7 +33,7 @@ namespace pipe {
 
 constexpr int kCWarps = 8;                 // consumer warps
 constexpr int kConsumers = kCWarps * 32;   // 256
-constexpr int kThreads = kConsumers + 64;  // + loader warp + signaler warp
+constexpr int kThreads = kConsumers + 96;  // + loader warp + signaler warp + K/V feeder warp
 constexpr int kGroupRows = 16;             // batch rows per group (one m16 tile)
 constexpr int kKC = 768;                   // widest K slice of an activation tile / weight row in shared memory
 constexpr int kPad = 16;                   // floats of padding per shared-memory row (bank spread of LDS.128)
@@ -44,12 +44,12 @@ constexpr int kXsFloats = kGroupRows * kLdMax;          // activation slot
 constexpr int kWFloats = 2 * kMaxRows * kLdMax;         // weight region: two phases in flight
 constexpr int kRedFloats = kCWarps * kGroupRows * kMaxRows;
 constexpr int kTK = 8;                     // keys per K/V ring tile
-constexpr int kSlots = 2;                  // ring slots per warp
+constexpr int kSlots = 16;                 // slots of the CTA-wide K/V ring (K tile + V tile each)
 constexpr int kMaxBatch = 1024;
 constexpr int kMaxGroups = 64;
 constexpr int kMaxSplit = 32;
 constexpr int kDescRing = 4;
-constexpr long long kSpinLimit = 1LL << 22;
+constexpr long long kTimeoutCycles = 3LL << 30;   // ~1.6 s of SM clock: no wait may hang the GPU
 constexpr int kProfPhases = 160;
 constexpr int kProfStride = 16;
 
@@ -65,6 +65,9 @@ struct Args {
   long long* prof;
   int n_steps, update_state;
   int group_rows, n_groups, n_split, ksplit;
+  int prefetch;         // L2 prefetch of upcoming K/V streams (TTS_PREFETCH=1 enables it)
+  int ring_lo, n_slots; // K/V ring: first float of the weight region it may use (above the weight tiles of the GEMM
+                        // that precedes an attention phase) and its number of slots (below the next GEMM's tiles)
 };
 
 struct Desc {
@@ -78,7 +81,6 @@ struct Desc {
   // ---- attention over a K/V stream
   const float* kc; const float* vc; int rows_alloc, n_keys; const int32_t* key_len;
   float* align; long long align_bh_stride; int align_row_len;
-  int ring_floats;      // shared memory the rings + logits may use (the next phase's weights sit above it)
   // ---- reduce: Y[b][n] += sum_s part[s][b][n]
   const float* part; int n_parts;
   // ---- this CTA's share of the phase (filled in by the loader warp: constant for the phase)
@@ -98,7 +100,11 @@ struct Smem {
   uint64_t* w_full;   // 2: weight slice landed (low / high placement)
   uint64_t* pdone;    // phases the consumers have finished, as a plain counter (an mbarrier's parity would alias:
                       // with a single row group the consumers can complete two phases before the loader looks)
-  uint64_t* rfull;    // [8][kSlots] ring slots
+  uint64_t* rfull;    // [kSlots] ring slot filled (feeder warp -> consumers)
+  unsigned* drained;  // [kSlots] how many tiles have been consumed out of each slot.  A plain counter, not an mbarrier:
+                      // a consumer may reach the slot's use n+2 while use n is still being read, and a parity
+                      // wait cannot tell "two phases behind" from "done" (this aliasing was hit on hardware)
+  unsigned* kv_go;    // attention group-phases the loader has released to the feeder
   unsigned* sig;      // group-phases the consumers have finished (polled by the signaler warp)
   Desc* desc;         // [kDescRing]
 };
@@ -107,7 +113,7 @@ __host__ __device__ inline size_t smem_floats_fixed() {
   return (size_t)kXsFloats + kWFloats + kRedFloats + kCWarps * kGroupRows * 2 + kGroupRows;
 }
 static size_t smem_bytes(int B) {
-  return smem_floats_fixed() * sizeof(float) + (size_t)2 * B * sizeof(int) + (5 + kCWarps * kSlots) * sizeof(uint64_t) +
+  return smem_floats_fixed() * sizeof(float) + (size_t)2 * B * sizeof(int) + (8 + 2 * kSlots) * sizeof(uint64_t) +
          kDescRing * sizeof(Desc) + 64;
 }
 
@@ -127,8 +133,11 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.w_full = sm.x_full + 2;
   sm.pdone = sm.x_full + 4;
   sm.rfull = sm.x_full + 5;
-  sm.sig = reinterpret_cast<unsigned*>(sm.rfull + kCWarps * kSlots);
-  sm.desc = reinterpret_cast<Desc*>(sm.rfull + kCWarps * kSlots + 1);
+  sm.drained = reinterpret_cast<unsigned*>(sm.rfull + kSlots);
+  uint64_t* after = sm.rfull + 2 * kSlots;
+  sm.sig = reinterpret_cast<unsigned*>(after);
+  sm.kv_go = sm.sig + 1;
+  sm.desc = reinterpret_cast<Desc*>(after + 2);
   return sm;
 }
 
@@ -150,12 +159,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, int* err) {
-  long long spins = 0;
+  long long spins = 0, t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    ++spins;
-    if ((spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(err) != 0)) {
-      atomicExch(err, 2);  // never hang the GPU
-      break;
+    if ((++spins & 255) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeoutCycles || *reinterpret_cast<volatile int*>(err) != 0) {
+        atomicExch(err, 2);  // never hang the GPU
+        break;
+      }
     }
   }
 }
@@ -206,29 +217,34 @@ __device__ __forceinline__ void grid_arrive(const Args& a, int g) {
 }
 __device__ __forceinline__ void grid_wait(const Args& a, int g, unsigned target) {
   const unsigned* ctr = a.bar + 32 * g;
-  long long spins = 0;
+  long long spins = 0, t0 = 0;
   while (true) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     if (static_cast<int>(v - target) >= 0) break;
-    ++spins;
-    if ((spins & 1023) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
-      atomicExch(a.err, 1);
-      break;
+    if ((++spins & 255) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeoutCycles || *reinterpret_cast<volatile int*>(a.err) != 0) {
+        atomicExch(a.err, 1);
+        break;
+      }
     }
   }
 }
 
 // spin until a shared-memory counter written with st.release.cta reaches `target`
 __device__ __forceinline__ void wait_count(const Args& a, const void* ctr, unsigned target) {
-  long long spins = 0;
+  long long spins = 0, t0 = 0;
   while (true) {
     unsigned v;
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ctr)) : "memory");
     if (static_cast<int>(v - target) >= 0) break;
-    if ((++spins & 4095) == 0 && (spins > kSpinLimit || *reinterpret_cast<volatile int*>(a.err) != 0)) {
-      atomicExch(a.err, 3);
-      break;
+    if ((++spins & 4095) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeoutCycles || *reinterpret_cast<volatile int*>(a.err) != 0) {
+        atomicExch(a.err, 3);
+        break;
+      }
     }
   }
 }
@@ -343,7 +359,7 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&
 struct CState {
   unsigned gp;            // group-phases consumed so far (parity of x_full)
   unsigned wpar0, wpar1;  // parity of the two weight barriers (scalars: a dynamically indexed array would live in local memory)
-  unsigned issued, consumed;  // K/V ring tiles of this warp
+  unsigned ring_seq;      // K/V ring tiles of all attention units this CTA has finished (slot and parity of the next)
 };
 
 template <int DH>
@@ -540,144 +556,214 @@ __device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g
 }
 
 // ---- attention group-phase -----------------------------------------------------------------------------------
+// The K/V stream of a unit = (sample, head[, key split]) flows through ONE CTA-wide ring of kSlots tiles (8 K rows +
+// 8 V rows each) that the feeder warp keeps full with TMA bulk copies; a consumer warp takes the next tile nobody
+// has taken yet (shared counter), so fast and slow warps balance themselves and no consumer instruction is spent
+// on issuing copies.  Scores are kept in the log2 domain (q is pre-multiplied by log2 e): one EX2 per weight.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct UnitRange {
+  int item, split, j0, j1, n_tiles;
+};
+__device__ __forceinline__ UnitRange unit_range(int u, int ns, int n_keys, int item0) {
+  UnitRange r;
+  const int per = (n_keys + ns - 1) / ns;
+  const int litem = ns == 1 ? u : u / ns;
+  r.split = u - litem * ns;
+  r.item = item0 + litem;
+  r.j0 = min(n_keys, r.split * per);
+  r.j1 = min(n_keys, r.j0 + per);
+  r.n_tiles = (r.j1 - r.j0 + kTK - 1) / kTK;
+  return r;
+}
+
+// feeder warp: lane `sl` owns ring slot `sl`.  Every lane polls (non-blocking) whether its slot has been drained
+// and, if so, issues the next tile that maps to it; the lanes never block each other, so a freed slot is refilled
+// within one polling round (a single issuing thread was 2x too slow: ~700 cycles per tile, measured).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+template <int DH>
+__device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const float* kc, const float* vc, int rows_alloc,
+                                           int n_keys, int g, unsigned& f_seq) {
+  constexpr int kTile = kTK * DH, kSlotF = 2 * kTile;
+  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split, lane = threadIdx.x & 31;
+  const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
+  const int n_units = rows * H * ns, item0 = b0 * H;
+  const unsigned nsl = (unsigned)a.n_slots;
+  int total = 0;
+  for (int u = blockIdx.x; u < n_units; u += G) total += unit_range(u, ns, n_keys, item0).n_tiles;
+  // local index of the first tile of this group-phase that lands in my slot
+  int k = lane < (int)nsl ? (int)((lane + nsl - f_seq % nsl) % nsl) : total;
+  int u = blockIdx.x, base = 0;
+  UnitRange r = unit_range(u, ns, n_keys, item0);
+  const unsigned* my_drained = &sm.drained[lane < (int)nsl ? lane : 0];
+  uint64_t* my_full = &sm.rfull[lane < (int)nsl ? lane : 0];
+  float* dst = sm.wreg + a.ring_lo + (size_t)(lane < (int)nsl ? lane : 0) * kSlotF;
+  long long spins = 0, t0 = 0;
+  while (__any_sync(0xffffffffu, k < total)) {
+    if (k < total) {
+      const unsigned seq = f_seq + (unsigned)k;
+      unsigned dv;   // use number seq / nsl of my slot needs that many earlier tiles drained
+      asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(dv) : "r"(smem_u32(my_drained)) : "memory");
+      if (static_cast<int>(dv - seq / nsl) >= 0) {
+        while (k >= base + r.n_tiles) {   // unit that contains local tile k
+          base += r.n_tiles;
+          u += G;
+          r = unit_range(u, ns, n_keys, item0);
+        }
+        const int key0 = r.j0 + (k - base) * kTK, nk = min(kTK, r.j1 - key0);
+        const unsigned bytes = (unsigned)nk * DH * 4u;
+        const size_t off = ((size_t)r.item * rows_alloc + key0) * DH;
+        mbar_expect_tx(my_full, 2u * bytes);
+        bulk_g2s(dst, kc + off, bytes, my_full);
+        bulk_g2s(dst + kTile, vc + off, bytes, my_full);
+        k += (int)nsl;
+      }
+    }
+    if ((++spins & 1023) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeoutCycles || *reinterpret_cast<volatile int*>(a.err) != 0) {
+        atomicExch(a.err, 4);
+        break;
+      }
+    }
+  }
+  f_seq += (unsigned)total;
+}
+
+// one tile of 8 keys: scores, online softmax update, weighted V.  FULL: all 8 keys exist and none is masked.
+template <int DH, bool FULL>
+__device__ __forceinline__ void attn_tile(const float* kt, const float* vt, const f32x4 (&qv)[DH / 32], int nk, int key0,
+                                          int klen, float* logit_dst, float& m_run, float& l_run,
+                                          f32x2 (&o)[DH / 32][2], int kslot, int l8) {
+  constexpr int F4 = DH / 32, kRounds = kTK / 4;
+  float sv[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int kl = r * 4 + kslot;
+    f32x2 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < F4; ++i) {
+      const f32x4 kv = ld4s(kt + kl * DH + 4 * (l8 + 8 * i));
+      acc0 = fma2(qv[i].lo, kv.lo, acc0);
+      acc1 = fma2(qv[i].hi, kv.hi, acc1);
+    }
+    float x0, x1, y0, y1;
+    unpack2(acc0, x0, y0);
+    unpack2(acc1, x1, y1);
+    sv[r] = (x0 + y0) + (x1 + y1);
+  }
+#pragma unroll
+  for (int o8 = 1; o8 <= 4; o8 <<= 1)
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) sv[r] += __shfl_xor_sync(0xffffffffu, sv[r], o8);
+  float mt = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int kl = r * 4 + kslot;
+    if (!FULL) {
+      if (kl >= nk) sv[r] = -CUDART_INF_F;                  // stale shared memory beyond the tile's keys
+      else if (key0 + kl >= klen) sv[r] = kNegBias;         // logits + (-1e20), attention.py:84-85
+    }
+    if (logit_dst != nullptr && l8 == 0 && (FULL || kl < nk)) logit_dst[kl] = sv[r];
+    mt = fmaxf(mt, sv[r]);
+  }
+  mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+  mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+  if (mt > m_run) {   // warp-uniform; rare after the first tiles
+    const float corr = ex2(m_run - mt);
+    l_run *= corr;
+    const f32x2 c2 = pack2(corr, corr);
+#pragma unroll
+    for (int i = 0; i < F4; ++i) {
+      o[i][0] = fma2(o[i][0], c2, 0ull);
+      o[i][1] = fma2(o[i][1], c2, 0ull);
+    }
+    m_run = mt;
+  }
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int kl = r * 4 + kslot;
+    const float p = (FULL || kl < nk) ? ex2(sv[r] - m_run) : 0.f;
+    if (l8 == 0) l_run += p;
+    const f32x2 pp = pack2(p, p);
+#pragma unroll
+    for (int i = 0; i < F4; ++i) {
+      const f32x4 vv = ld4s(vt + kl * DH + 4 * (l8 + 8 * i));
+      if (FULL) {
+        o[i][0] = fma2(pp, vv.lo, o[i][0]);
+        o[i][1] = fma2(pp, vv.hi, o[i][1]);
+      } else {
+        o[i][0] = fma2(pp, kl < nk ? vv.lo : 0ull, o[i][0]);
+        o[i][1] = fma2(pp, kl < nk ? vv.hi : 0ull, o[i][1]);
+      }
+    }
+  }
+}
+
 template <int DH>
 __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const Smem& sm, CState& cs, int g, int t) {
   constexpr int F4 = DH / 32;            // float4 per lane per key row (8 lanes span a row)
   constexpr int kTile = kTK * DH;        // floats per K (or V) tile
   constexpr int kSlotF = 2 * kTile;      // K tile then V tile
-  constexpr int kRounds = kTK / 4;       // 4 key slots per warp pass
   constexpr int PS = DH + 4;
   const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split;
   const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
-  const int item0 = b0 * H, n_units = rows * H * ns, n_keys = at.n_keys;
-  const int per = (n_keys + ns - 1) / ns;
+  const int n_units = rows * H * ns, n_keys = at.n_keys;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kslot = lane >> 3, l8 = lane & 7;
-  float* ring = sm.wreg + (size_t)warp * kSlots * kSlotF;
-  uint64_t* full = sm.rfull + warp * kSlots;
   float* wrec = sm.red;  // [8][PS]
-  float* sc = sm.wreg + (size_t)kCWarps * kSlots * kSlotF;            // raw logits of the current unit
-  const int sc_cap = at.ring_floats - kCWarps * kSlots * kSlotF;
-  const bool sc_ok = per <= sc_cap;                                   // else fall back to read-modify-write in HBM
+  float* sc = sm.red + kCWarps * PS;                                  // scaled logits of the current unit
+  const int sc_cap = kRedFloats - kCWarps * PS;
+  unsigned seq_base = cs.ring_seq;
 
-  unsigned issued = cs.issued, consumed = cs.consumed;   // registers (a by-reference capture would pin cs in local memory)
-  // ---- producer cursor (next tile this warp will request) ----
-  int pu = blockIdx.x, pi = warp;
-  auto issue_next = [&]() {
-    int item = 0, j0 = 0, j1 = 0;
-    while (pu < n_units) {
-      item = ns == 1 ? pu : pu / ns;
-      j0 = min(n_keys, (pu - item * ns) * per);
-      j1 = min(n_keys, j0 + per);
-      if (pi * kTK < j1 - j0) break;
-      pu += G;
-      pi = warp;
-    }
-    if (pu >= n_units) return;
-    const int key0 = j0 + pi * kTK, nk = min(kTK, j1 - key0);
-    const int slot = issued % kSlots;
-    if (lane == 0) {
-      const unsigned bytes = (unsigned)nk * DH * 4u;
-      mbar_expect_tx(&full[slot], 2u * bytes);
-      const size_t off = ((size_t)(item0 + item) * at.rows_alloc + key0) * DH;
-      bulk_g2s(ring + slot * kSlotF, at.kc + off, bytes, &full[slot]);
-      bulk_g2s(ring + slot * kSlotF + kTile, at.vc + off, bytes, &full[slot]);
-    }
-    issued++;
-    pi += kCWarps;
-  };
-  if (lane == 0) fence_proxy_async();  // the K/V row appended by other CTAs in the previous phase is read by TMA
-#pragma unroll
-  for (int sl = 0; sl < kSlots; ++sl) issue_next();
-
-  f32x4 qnext[F4];
-#pragma unroll
-  for (int i = 0; i < F4; ++i) qnext[i].lo = qnext[i].hi = 0ull;
   for (int u = blockIdx.x; u < n_units; u += G) {
-    const int litem = ns == 1 ? u : u / ns, split = u - litem * ns, item = item0 + litem;
-    const int j0 = min(n_keys, split * per), j1 = min(n_keys, j0 + per);
+    const UnitRange ur = unit_range(u, ns, n_keys, b0 * H);
+    const int item = ur.item, j0 = ur.j0, j1 = ur.j1;
+    const bool sc_ok = j1 - j0 <= sc_cap;                             // else fall back to read-modify-write in HBM
     const int b = item / H;
     const int klen = at.key_len ? at.key_len[b] : n_keys;
     float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
 
     f32x4 qv[F4];
-    if (u == (int)blockIdx.x) {
+    {
+      const f32x2 sc2 = pack2(kLog2e, kLog2e);
 #pragma unroll
-      for (int i = 0; i < F4; ++i) qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
-    } else {
-#pragma unroll
-      for (int i = 0; i < F4; ++i) qv[i] = qnext[i];
-    }
-    if (u + G < n_units) {  // latency of the next unit's query hides behind this unit's stream
-      const int nitem = item0 + (ns == 1 ? u + G : (u + G) / ns);
-#pragma unroll
-      for (int i = 0; i < F4; ++i) qnext[i] = ld4cg(a.q + (size_t)nitem * DH + 4 * (l8 + 8 * i));
+      for (int i = 0; i < F4; ++i) {
+        qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+        qv[i].lo = fma2(qv[i].lo, sc2, 0ull);
+        qv[i].hi = fma2(qv[i].hi, sc2, 0ull);
+      }
     }
     float m_run = -CUDART_INF_F, l_run = 0.f;
     f32x2 o[F4][2];
 #pragma unroll
     for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
 
-    const int n_tiles = (j1 - j0 + kTK - 1) / kTK;
-    for (int ti = warp; ti < n_tiles; ti += kCWarps) {
+    for (int ti = warp; ti < ur.n_tiles; ti += kCWarps) {   // static assignment: bit-reproducible sums
       const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
-      const int slot = consumed % kSlots;
-      mbar_wait(&full[slot], (consumed / kSlots) & 1u, a.err);
-      const float* kt = ring + slot * kSlotF;
-      const float* vt = kt + kTile;
-      float sv[kRounds];
-      float mt = -CUDART_INF_F;
-#pragma unroll
-      for (int r = 0; r < kRounds; ++r) {
-        const int kl = r * 4 + kslot;
-        f32x2 accq = 0ull;
-#pragma unroll
-        for (int i = 0; i < F4; ++i) {
-          const f32x4 kv = ld4s(kt + kl * DH + 4 * (l8 + 8 * i));
-          accq = fma2(qv[i].lo, kv.lo, accq);
-          accq = fma2(qv[i].hi, kv.hi, accq);
-        }
-        float v = hsum2(accq);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (kl >= nk) v = -CUDART_INF_F;                 // stale smem beyond the tile's keys
-        else if (key0 + kl >= klen) v = kNegBias;        // logits + (-1e20), attention.py:84-85
-        if (kl < nk && l8 == 0 && arow != nullptr) {     // raw logit, normalised once the unit's (max, sum) is known
-          if (ns == 1 && sc_ok) sc[key0 + kl - j0] = v;
-          else arow[key0 + kl] = v;
-        }
-        sv[r] = v;
-        mt = fmaxf(mt, v);
-      }
-      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
-      mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
-      const float m_new = fmaxf(m_run, mt);
-      const float corr = expf(m_run - m_new);
-      l_run *= corr;
-      const f32x2 c2 = pack2(corr, corr);
-#pragma unroll
-      for (int i = 0; i < F4; ++i) {
-        o[i][0] = fma2(o[i][0], c2, 0ull);
-        o[i][1] = fma2(o[i][1], c2, 0ull);
-      }
-#pragma unroll
-      for (int r = 0; r < kRounds; ++r) {
-        const int kl = r * 4 + kslot;
-        const float p = kl < nk ? expf(sv[r] - m_new) : 0.f;
-        if (l8 == 0) l_run += p;
-        const f32x2 pp = pack2(p, p);
-#pragma unroll
-        for (int i = 0; i < F4; ++i) {
-          const f32x4 vv = ld4s(vt + kl * DH + 4 * (l8 + 8 * i));
-          o[i][0] = fma2(pp, kl < nk ? vv.lo : 0ull, o[i][0]);
-          o[i][1] = fma2(pp, kl < nk ? vv.hi : 0ull, o[i][1]);
-        }
-      }
-      m_run = m_new;
-      consumed++;
+      const unsigned seq = seq_base + (unsigned)ti, slot = seq % (unsigned)a.n_slots, use = seq / (unsigned)a.n_slots;
+      wait_count(a, &sm.drained[slot], use);      // the slot's previous tile has been consumed (no parity aliasing)
+      mbar_wait(&sm.rfull[slot], use & 1u, a.err);
+      const float* kt = sm.wreg + a.ring_lo + (size_t)slot * kSlotF;
+      float* ldst = arow == nullptr ? nullptr : ((ns == 1 && sc_ok) ? sc + (key0 - j0) : arow + key0);
+      if (nk == kTK && key0 + kTK <= klen)
+        attn_tile<DH, true>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8);
+      else
+        attn_tile<DH, false>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8);
       __syncwarp();   // every lane is done with this slot before it is refilled
-      issue_next();
+      if (lane == 0)
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&sm.drained[slot])), "r"(use + 1u) : "memory");
     }
+    seq_base += (unsigned)ur.n_tiles;
     // ---- warp record (max, sum, weighted V) -> shared ----
 #pragma unroll
     for (int i = 0; i < F4; ++i)
@@ -703,35 +789,33 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
 #pragma unroll
     for (int w = 0; w < kCWarps; ++w) m = fmaxf(m, wrec[w * PS + DH]);
     float l = 0.f;
+    float wgt[kCWarps];
 #pragma unroll
     for (int w = 0; w < kCWarps; ++w) {
       const float mw = wrec[w * PS + DH];
-      if (mw > -CUDART_INF_F) l += wrec[w * PS + DH + 1] * expf(mw - m);
+      wgt[w] = mw > -CUDART_INF_F ? ex2(mw - m) : 0.f;
+      l = fmaf(wrec[w * PS + DH + 1], wgt[w], l);
     }
     if (tid < DH) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kCWarps; ++w) {
-        const float mw = wrec[w * PS + DH];
-        if (mw > -CUDART_INF_F) v += wrec[w * PS + tid] * expf(mw - m);
-      }
+      for (int w = 0; w < kCWarps; ++w) v = fmaf(wrec[w * PS + tid], wgt[w], v);
       if (ns == 1) a.ctx[(size_t)item * DH + tid] = v / l;
-      else a.fpart[((size_t)item * ns + split) * PS + tid] = v;
+      else a.fpart[((size_t)item * ns + ur.split) * PS + tid] = v;
     }
     if (ns == 1) {
       if (arow != nullptr) {
         const float inv = 1.f / l;
-        if (sc_ok) for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = expf(sc[j - j0] - m) * inv;
-        else for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = expf(arow[j] - m) * inv;
+        if (sc_ok) for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = ex2(sc[j - j0] - m) * inv;
+        else for (int j = j0 + tid; j < j1; j += kConsumers) arow[j] = ex2(arow[j] - m) * inv;
       }
     } else if (tid == 0) {
-      a.fpart[((size_t)item * ns + split) * PS + DH] = m;       // -inf when the split is empty
-      a.fpart[((size_t)item * ns + split) * PS + DH + 1] = l;
+      a.fpart[((size_t)item * ns + ur.split) * PS + DH] = m;       // -inf when the split is empty
+      a.fpart[((size_t)item * ns + ur.split) * PS + DH + 1] = l;
     }
     consumer_bar();  // wrec / sc are reused by the next unit
   }
-  cs.issued = issued;
-  cs.consumed = consumed;
+  cs.ring_seq = seq_base;
 }
 
 // ---- combine group-phase (only when the K/V streams were split, i.e. small batches): partials -> ctx, align rows
@@ -751,7 +835,7 @@ __device__ __forceinline__ void combine_group(const Args& a, const Desc& d, cons
       float l = 0.f;
       for (int sidx = 0; sidx < ns; ++sidx) {
         const float pm = __ldcg(pr + sidx * PS + DH);
-        if (pm > -CUDART_INF_F) l += __ldcg(pr + sidx * PS + DH + 1) * expf(pm - m);
+        if (pm > -CUDART_INF_F) l += __ldcg(pr + sidx * PS + DH + 1) * ex2(pm - m);
       }
       ml[0] = m;
       ml[1] = 1.f / l;
@@ -762,13 +846,13 @@ __device__ __forceinline__ void combine_group(const Args& a, const Desc& d, cons
       float acc = 0.f;
       for (int sidx = 0; sidx < ns; ++sidx) {
         const float pm = __ldcg(pr + sidx * PS + DH);
-        if (pm > -CUDART_INF_F) acc = fmaf(__ldcg(pr + sidx * PS + tid), expf(pm - m), acc);
+        if (pm > -CUDART_INF_F) acc = fmaf(__ldcg(pr + sidx * PS + tid), ex2(pm - m), acc);
       }
       a.ctx[(size_t)item * DH + tid] = acc * inv;
     }
     if (d.align != nullptr) {  // raw logits of this step -> softmax weights
       float* row = d.align + (size_t)item * d.align_bh_stride + (size_t)t * d.align_row_len;
-      for (int j = tid; j < d.n_keys; j += kConsumers) row[j] = expf(__ldcg(row + j) - m) * inv;
+      for (int j = tid; j < d.n_keys; j += kConsumers) row[j] = ex2(__ldcg(row + j) - m) * inv;
     }
     consumer_bar();
   }
@@ -779,6 +863,39 @@ __device__ __forceinline__ void combine_group(const Args& a, const Desc& d, cons
 // final projection.  `comb` = attention streams are split (n_split > 1), `red` = FFN-out is K-split.
 __device__ __forceinline__ int phases_per_layer(const Args& a) { return 8 + (a.n_split > 1 ? 2 : 0) + (a.ksplit > 1 ? 1 : 0); }
 __device__ __forceinline__ int n_phases(const Args& a) { return 3 + phases_per_layer(a) * a.w.n_layers + 1; }
+
+// canonical id of phase `ph` (see get_phase_body): 0 qkv, 1 self, 2 comb, 3 oproj, 4 cq, 5 cross, 6 comb, 7 coproj,
+// 8 ffn1, 9 ffn2, 10 reduce; 100 + i for the prenet GEMMs, 200 for the final projection
+__device__ __forceinline__ int phase_id(const Args& a, int ph, int& layer) {
+  const int ppl = phases_per_layer(a);
+  layer = 0;
+  if (ph < 3) return 100 + ph;
+  if (ph == 3 + ppl * a.w.n_layers) return 200;
+  layer = (ph - 3) / ppl;
+  const int k = (ph - 3) % ppl;
+  if (a.n_split > 1) return k;
+  return k < 2 ? k : (k < 5 ? k + 1 : k + 2);
+}
+
+// Ask the memory system to pull the K/V rows this CTA will stream in an upcoming attention phase into L2 while the
+// GEMM phases leave HBM idle (the ring then refills at L2 latency instead of HBM latency).  Pure hint.
+template <int DH>
+__device__ __forceinline__ void prefetch_kv(const Args& a, const float* kc, const float* vc, int rows_alloc, int rows) {
+  if (a.n_split != 1 || rows <= 0) return;
+  const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x;
+  // keep the total under ~88 MB so that it survives in the 126 MB L2 until it is used
+  const long long cap = (88ll << 20) / ((long long)B * H * DH * 8);
+  const int r = (int)min((long long)rows, cap > 1 ? cap : 1);
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int b0 = g * a.group_rows, n_items = min(a.group_rows, B - b0) * H;
+    for (int u = blockIdx.x; u < n_items; u += G) {
+      const size_t off = (size_t)(b0 * H + u) * rows_alloc * DH;
+      const unsigned bytes = (unsigned)r * DH * 4u;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kc + off), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vc + off), "r"(bytes) : "memory");
+    }
+  }
+}
 
 template <int DH>
 __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, float qscale, Desc& d);
@@ -834,9 +951,6 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   const size_t self_off = (size_t)l * B * H * T * DH, cross_off = (size_t)l * B * H * S * DH;
   float* al_self = a.st.align_self ? a.st.align_self + (size_t)l * B * H * T * T : nullptr;
   float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
-  // attention phases: the next GEMM (an output projection, high placement) owns the top n-tiles of the weight region
-  const int oproj_rows = (D + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int ring_floats = kWFloats - ((oproj_rows + 7) / 8) * 8 * (D + kPad);
   switch (id) {
     case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
       d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = 3 * D; d.W = lw.pk_qkv;
@@ -847,7 +961,6 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kAttn;
       d.kc = a.st.self_k + self_off; d.vc = a.st.self_v + self_off; d.rows_alloc = T; d.n_keys = t + 1;
       d.key_len = nullptr; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
-      d.ring_floats = ring_floats;
       break;
     case 2:
       d.kind = kCombine; d.n_keys = t + 1; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
@@ -865,7 +978,6 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kAttn;
       d.kc = a.st.cross_k + cross_off; d.vc = a.st.cross_v + cross_off; d.rows_alloc = S; d.n_keys = S;
       d.key_len = a.st.input_lengths; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
-      d.ring_floats = ring_floats;
       break;
     case 6:
       d.kind = kCombine; d.n_keys = S; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
@@ -908,7 +1020,11 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
     mbar_init(&sm.w_full[0], 1);
     mbar_init(&sm.w_full[1], 1);
     *reinterpret_cast<volatile unsigned*>(sm.pdone) = 0u;
-    for (int i = 0; i < kCWarps * kSlots; ++i) mbar_init(&sm.rfull[i], 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&sm.rfull[i], 1);
+      sm.drained[i] = 0u;
+    }
+    *sm.kv_go = 0u;
     *sm.sig = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -919,8 +1035,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   __syncthreads();
   const int t0 = *a.st.step_counter;
 
-  CState cs{0u, 0u, 0u, 0u, 0u};
-  unsigned p_gp = 0u;                   // producer: group-phases staged
+  CState cs{0u, 0u, 0u, 0u};
+  unsigned p_gp = 0u, p_go = 0u;        // loader: group-phases staged, attention group-phases released to the feeder
+  unsigned f_go = 0u, f_seq = 0u;       // feeder: attention group-phases served, ring tiles issued
   unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started
 
@@ -939,6 +1056,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
               grid_wait(a, g, (epoch + ph) * G);      // (ph-1, g) is complete everywhere
               fence_proxy_async();
             }
+            if (d.kind == kAttn)   // q and the appended K/V row of this group are visible: the feeder may start
+              asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sm.kv_go)), "r"(++p_go) : "memory");
             mbar_wait(sm.x_empty, (p_gp & 1u) ^ 1u, a.err);
             stage_tile(a, sm, d, g);
             ++p_gp;
@@ -953,6 +1072,24 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         }
       }
       __syncwarp();
+    } else if (warp == kCWarps + 2) {
+      // =========================== K/V feeder warp (one lane per ring slot) ===========================
+      for (int ph = 0; ph < n_ph; ++ph) {
+        int l;
+        const int id = phase_id(a, ph, l);
+        if (id != 1 && id != 5) continue;
+        const size_t BH = (size_t)B * a.w.n_heads;
+        const size_t off = id == 1 ? (size_t)l * BH * T * DH : (size_t)l * BH * a.st.mem_len * DH;
+        const float* kc = (id == 1 ? a.st.self_k : a.st.cross_k) + off;
+        const float* vc = (id == 1 ? a.st.self_v : a.st.cross_v) + off;
+        const int rows_alloc = id == 1 ? T : a.st.mem_len, n_keys = id == 1 ? t + 1 : a.st.mem_len;
+        for (int g = 0; g < NG; ++g) {
+          wait_count(a, sm.kv_go, ++f_go);
+          fence_proxy_async();
+          feed_group<DH>(a, sm, kc, vc, rows_alloc, n_keys, g, f_seq);
+        }
+      }
+      __syncwarp();
     } else if (warp == kCWarps + 1) {
       // =========================== signaler warp (one elected lane) ===========================
       // publishes the consumers' finished group-phases to the other CTAs: the gpu-scope release (a memory barrier
@@ -963,6 +1100,20 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             ++s_gp;
             wait_count(a, sm.sig, s_gp);
             grid_arrive(a, g);
+            if (g == 0 && a.prefetch) {   // L2 prefetch of the K/V streams of the attention phase two GEMMs ahead
+              int l;
+              const int id = phase_id(a, ph, l);
+              const size_t BH = (size_t)B * a.w.n_heads;
+              if (id == 3) {
+                const size_t off = (size_t)l * BH * a.st.mem_len * DH;
+                prefetch_kv<DH>(a, a.st.cross_k + off, a.st.cross_v + off, a.st.mem_len, a.st.mem_len);
+              } else if (id == 7 && l + 1 < a.w.n_layers) {
+                const size_t off = (size_t)(l + 1) * BH * T * DH;
+                prefetch_kv<DH>(a, a.st.self_k + off, a.st.self_v + off, T, t);
+              } else if (id == 100) {
+                prefetch_kv<DH>(a, a.st.self_k, a.st.self_v, T, t);
+              }
+            }
           }
       }
       __syncwarp();
@@ -1046,6 +1197,18 @@ static int num_sms() {
 }
 
 static int ksplit_for(const TtsDecoderWeights* w) { return (w->d_ffn + kKC - 1) / kKC; }
+
+// The K/V ring lives in the weight region between the tiles of the GEMM before an attention phase (QKV or the
+// cross query: low placement) and the tiles of the GEMM after it (an output projection: high placement), so the
+// feeder may start while the consumers still read the former and the loader already streams the latter.
+static int ring_slots(const TtsDecoderWeights* w, int G, int* ring_lo) {
+  const int D = w->d_model, dh = D / w->n_heads;
+  auto tiles = [&](int N) { return ((N + G - 1) / G + 7) / 8; };
+  const int lo = tiles(3 * D) * 8 * (D + kPad), hi = kWFloats - tiles(D) * 8 * (D + kPad);
+  if (ring_lo) *ring_lo = lo;
+  const int n = (hi - lo) / (2 * kTK * dh);
+  return n > kSlots ? kSlots : n;
+}
 
 static int group_rows_for(int B) {
   const char* e = getenv("TTS_GROUP_ROWS");
@@ -1135,9 +1298,7 @@ bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   worst = worst > rows(P, G) ? worst : rows(P, G);
   worst = worst > rows(M + 1, G) ? worst : rows(M + 1, G);
   if (worst > kMaxRows) return false;
-  // K/V rings (+ at least a few logits) must fit below the output projection's weight tiles
-  const int oproj_tiles = (rows(D, G) + 7) / 8;
-  if (kCWarps * kSlots * 2 * kTK * dh + 64 > kWFloats - oproj_tiles * 8 * (D + kPad)) return false;
+  if (ring_slots(w, G, nullptr) < 2) return false;
   if (smem_bytes(st->batch) > 227 * 1024) return false;
   return true;
 }
@@ -1157,6 +1318,8 @@ int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st,
   a.n_groups = (st->batch + a.group_rows - 1) / a.group_rows;
   a.n_split = split_for(w, a.group_rows, num_sms());
   a.ksplit = ksplit_for(w);
+  a.prefetch = getenv("TTS_PREFETCH") != nullptr;   // off by default: it competes with the weight stream (measured -3 %)
+  a.n_slots = ring_slots(w, num_sms(), &a.ring_lo);
   TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, (32 * kMaxGroups + 32) * sizeof(unsigned), s));  // counters + error flag
   switch (w->d_model / w->n_heads) {
     case 32: return launch<32>(a, s);
