@@ -53,7 +53,11 @@ def decode_bytes(cfg, batch, mem_len, n_steps, elem=4):
     return total
 
 
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 55.06e9   # profiles/r1_fused_ncu_raw.csv (round 1)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (50 decode steps, t = 475..524, B=32, S=258) from the
+# committed `ncu --set full` captures (profiles/README.md), keyed by decode implementation
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {3: 55.06e9,    # fused_decode_kernel, profiles/r1_fused_ncu_raw.csv
+                                4: None}       # pipelined_decode_kernel: filled in from profiles/r1_pipe_ncu_raw.csv
+KERNEL_NAME = {3: "fused_decode_kernel", 4: "pipelined_decode_kernel"}
 
 
 def decode_bytes_range(cfg, batch, mem_len, t0, t1, elem=4):
@@ -298,13 +302,15 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     alg_bytes = decode_bytes(cfg, args.batch, args.text_len, args.frames)
     achieved = alg_bytes / dec_secs / 1e9
-    # one launch of the fused kernel = `chunk` decode steps; report the average launch
-    n_launch = max(1, -(-args.frames // args.chunk)) if args.decode_impl in (0, 3) else args.frames
-    roofline = {"bound": "hbm", "kernel": "fused_decode_kernel (one launch = %d decode steps; %d launches per job)"
-                % (args.chunk, n_launch) if args.decode_impl in (0, 3) else "decode step (per-phase kernels)",
+    # one launch of the persistent kernel = `chunk` decode steps; report the average launch
+    impl = args.decode_impl if args.decode_impl != 0 else 4      # the library's default is the pipelined kernel
+    persistent = impl in (3, 4)
+    n_launch = max(1, -(-args.frames // args.chunk)) if persistent else args.frames
+    std_shape = persistent and args.chunk == 50 and args.frames == 1000 and args.batch == 32 and args.text_len == 258
+    roofline = {"bound": "hbm", "kernel": "%s (one launch = %d decode steps; %d launches per job)"
+                % (KERNEL_NAME[impl], args.chunk, n_launch) if persistent else "decode step (per-phase kernels)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (args.decode_impl in (0, 3) and args.chunk == 50
-                                                            and args.frames == 1000 and args.batch == 32) else None,
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(impl) if std_shape else None,
                 "traffic_note": "dram__bytes_read+write of the launch covering t=475..524 (profiles/README.md); "
                                 "algorithmic bytes of that launch: %.3e" % decode_bytes_range(cfg, args.batch, args.text_len, 475, 525),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / n_launch,
@@ -344,7 +350,8 @@ def main():
     ap.add_argument("--text-len", type=int, default=258)
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--chunk", type=int, default=50, help="decode steps per launch / host poll")
-    ap.add_argument("--decode-impl", type=int, default=0, help="0 default, 1 per-phase kernels, 2 CUDA graph, 3 fused")
+    ap.add_argument("--decode-impl", type=int, default=0,
+                    help="0 default (= 4), 1 per-phase kernels, 2 CUDA graph, 3 fused FFMA2 kernel, 4 pipelined kernel")
     ap.add_argument("--ref-horizon", type=int, default=96, help="frames of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

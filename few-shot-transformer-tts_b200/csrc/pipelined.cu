@@ -748,9 +748,10 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
 #pragma unroll
     for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
 
+    // slot and use number of this warp's first tile; advanced incrementally (no division in the loop)
+    unsigned slot = (seq_base + (unsigned)warp) % (unsigned)a.n_slots, use = (seq_base + (unsigned)warp) / (unsigned)a.n_slots;
     for (int ti = warp; ti < ur.n_tiles; ti += kCWarps) {   // static assignment: bit-reproducible sums
       const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
-      const unsigned seq = seq_base + (unsigned)ti, slot = seq % (unsigned)a.n_slots, use = seq / (unsigned)a.n_slots;
       wait_count(a, &sm.drained[slot], use);      // the slot's previous tile has been consumed (no parity aliasing)
       mbar_wait(&sm.rfull[slot], use & 1u, a.err);
       const float* kt = sm.wreg + a.ring_lo + (size_t)slot * kSlotF;
@@ -762,6 +763,11 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       __syncwarp();   // every lane is done with this slot before it is refilled
       if (lane == 0)
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&sm.drained[slot])), "r"(use + 1u) : "memory");
+      slot += kCWarps;
+      while (slot >= (unsigned)a.n_slots) {
+        slot -= (unsigned)a.n_slots;
+        ++use;
+      }
     }
     seq_base += (unsigned)ur.n_tiles;
     // ---- warp record (max, sum, weighted V) -> shared ----
