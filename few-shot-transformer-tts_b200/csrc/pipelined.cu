@@ -44,7 +44,7 @@ constexpr int kXsFloats = kGroupRows * kLdMax;          // activation slot
 constexpr int kWFloats = 2 * kMaxRows * kLdMax;         // weight region: two phases in flight
 constexpr int kRedFloats = kCWarps * kGroupRows * kMaxRows;
 constexpr int kTK = 8;                     // keys per K/V ring tile
-constexpr int kSlots = 16;                 // slots of the CTA-wide K/V ring (K tile + V tile each)
+constexpr int kSlots = 24;                 // most slots of the CTA-wide K/V ring (K tile + V tile each; one feeder lane per slot)
 constexpr int kMaxBatch = 1024;
 constexpr int kMaxGroups = 64;
 constexpr int kMaxSplit = 32;
@@ -66,8 +66,10 @@ struct Args {
   int n_steps, update_state;
   int group_rows, n_groups, n_split, ksplit;
   int prefetch;         // L2 prefetch of upcoming K/V streams (TTS_PREFETCH=1 enables it)
-  int ring_lo, n_slots; // K/V ring: first float of the weight region it may use (above the weight tiles of the GEMM
-                        // that precedes an attention phase) and its number of slots (below the next GEMM's tiles)
+  int ring_lo, n_slots, n_hi;   // K/V ring.  Slots [0, n_hi) sit above the weight tiles of the GEMM that precedes an
+                                // attention phase (from float ring_lo on, below the next GEMM's tiles): they may be
+                                // filled while that GEMM still runs.  Slots [n_hi, n_slots) reuse the space of those
+                                // weight tiles and are filled once the consumers have finished the GEMM.
 };
 
 struct Desc {
@@ -95,6 +97,7 @@ struct Smem {
   float* sshift;   // [16]
   int* len;        // [B]
   int* fin;        // [B]
+  int* klen;       // [B] input_lengths (key mask of the cross attention), cached once per launch
   uint64_t* x_full;   // 1: producer -> consumers, tile landed / group may start
   uint64_t* x_empty;  // 1: consumers -> producer, slot free (8 arrivals)
   uint64_t* w_full;   // 2: weight slice landed (low / high placement)
@@ -113,7 +116,7 @@ __host__ __device__ inline size_t smem_floats_fixed() {
   return (size_t)kXsFloats + kWFloats + kRedFloats + kCWarps * kGroupRows * 2 + kGroupRows;
 }
 static size_t smem_bytes(int B) {
-  return smem_floats_fixed() * sizeof(float) + (size_t)2 * B * sizeof(int) + (8 + 2 * kSlots) * sizeof(uint64_t) +
+  return smem_floats_fixed() * sizeof(float) + (size_t)3 * B * sizeof(int) + (8 + 2 * kSlots) * sizeof(uint64_t) +
          kDescRing * sizeof(Desc) + 64;
 }
 
@@ -126,7 +129,8 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.sshift = sm.spart + kCWarps * kGroupRows * 2;
   sm.len = reinterpret_cast<int*>(sm.sshift + kGroupRows);
   sm.fin = sm.len + a.st.batch;
-  uintptr_t p = reinterpret_cast<uintptr_t>(sm.fin + a.st.batch);
+  sm.klen = sm.fin + a.st.batch;
+  uintptr_t p = reinterpret_cast<uintptr_t>(sm.klen + a.st.batch);
   p = (p + 15) & ~(uintptr_t)15;
   sm.x_full = reinterpret_cast<uint64_t*>(p);
   sm.x_empty = sm.x_full + 1;
@@ -582,6 +586,12 @@ __device__ __forceinline__ UnitRange unit_range(int u, int ns, int n_keys, int i
   return r;
 }
 
+template <int DH>
+__device__ __forceinline__ float* slot_ptr(const Args& a, const Smem& sm, unsigned slot) {
+  constexpr int kSlotF = 2 * kTK * DH;
+  return (int)slot < a.n_hi ? sm.wreg + a.ring_lo + (size_t)slot * kSlotF : sm.wreg + (size_t)((int)slot - a.n_hi) * kSlotF;
+}
+
 // feeder warp: lane `sl` owns ring slot `sl`.  Every lane polls (non-blocking) whether its slot has been drained
 // and, if so, issues the next tile that maps to it; the lanes never block each other, so a freed slot is refilled
 // within one polling round (a single issuing thread was 2x too slow: ~700 cycles per tile, measured).
@@ -593,7 +603,13 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
 }
 template <int DH>
 __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const float* kc, const float* vc, int rows_alloc,
-                                           int n_keys, int g, unsigned& f_seq) {
+                                           int n_keys, int g, unsigned& f_seq, unsigned go_target, bool gate_last,
+                                           unsigned low_target) {
+  // go_target: value of sm.kv_go once the loader has seen the previous phase of this group complete everywhere.
+  // Cross K/V never changes during decode and self K/V rows < t were written in earlier steps, so only the tile
+  // that holds the row appended in this step (gate_last: the last key of the stream) has to wait for it; all
+  // other tiles are requested as soon as their ring slot is free, i.e. while the consumers still run the GEMMs
+  // in front of the attention phase.
   constexpr int kTile = kTK * DH, kSlotF = 2 * kTile;
   const int B = a.st.batch, H = a.w.n_heads, G = gridDim.x, ns = a.n_split, lane = threadIdx.x & 31;
   const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
@@ -607,26 +623,41 @@ __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const 
   UnitRange r = unit_range(u, ns, n_keys, item0);
   const unsigned* my_drained = &sm.drained[lane < (int)nsl ? lane : 0];
   uint64_t* my_full = &sm.rfull[lane < (int)nsl ? lane : 0];
-  float* dst = sm.wreg + a.ring_lo + (size_t)(lane < (int)nsl ? lane : 0) * kSlotF;
+  float* dst = slot_ptr<DH>(a, sm, lane < (int)nsl ? lane : 0);
+  bool low_ok = lane < a.n_hi;   // low slots: only after the GEMM in front of the attention phase (pdone >= low_target)
   long long spins = 0, t0 = 0;
   while (__any_sync(0xffffffffu, k < total)) {
     if (k < total) {
+      bool continue_spin = false;
       const unsigned seq = f_seq + (unsigned)k;
       unsigned dv;   // use number seq / nsl of my slot needs that many earlier tiles drained
       asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(dv) : "r"(smem_u32(my_drained)) : "memory");
-      if (static_cast<int>(dv - seq / nsl) >= 0) {
+      if (!low_ok) {
+        unsigned pv;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(pv) : "r"(smem_u32(sm.pdone)) : "memory");
+        low_ok = static_cast<int>(pv - low_target) >= 0;
+      }
+      if (low_ok && static_cast<int>(dv - seq / nsl) >= 0) {
         while (k >= base + r.n_tiles) {   // unit that contains local tile k
           base += r.n_tiles;
           u += G;
           r = unit_range(u, ns, n_keys, item0);
         }
         const int key0 = r.j0 + (k - base) * kTK, nk = min(kTK, r.j1 - key0);
+        if (gate_last && key0 + nk == n_keys) {   // the freshly appended row: visible once kv_go says so
+          unsigned gv;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(gv) : "r"(smem_u32(sm.kv_go)) : "memory");
+          if (static_cast<int>(gv - go_target) < 0) continue_spin = true;
+          else fence_proxy_async();
+        }
+        if (!continue_spin) {
         const unsigned bytes = (unsigned)nk * DH * 4u;
         const size_t off = ((size_t)r.item * rows_alloc + key0) * DH;
         mbar_expect_tx(my_full, 2u * bytes);
         bulk_g2s(dst, kc + off, bytes, my_full);
         bulk_g2s(dst + kTile, vc + off, bytes, my_full);
         k += (int)nsl;
+        }
       }
     }
     if ((++spins & 1023) == 0) {
@@ -730,7 +761,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     const int item = ur.item, j0 = ur.j0, j1 = ur.j1;
     const bool sc_ok = j1 - j0 <= sc_cap;                             // else fall back to read-modify-write in HBM
     const int b = item / H;
-    const int klen = at.key_len ? at.key_len[b] : n_keys;
+    const int klen = at.key_len ? sm.klen[b] : n_keys;
     float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
 
     f32x4 qv[F4];
@@ -754,7 +785,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       const int key0 = j0 + ti * kTK, nk = min(kTK, j1 - key0);
       wait_count(a, &sm.drained[slot], use);      // the slot's previous tile has been consumed (no parity aliasing)
       mbar_wait(&sm.rfull[slot], use & 1u, a.err);
-      const float* kt = sm.wreg + a.ring_lo + (size_t)slot * kSlotF;
+      const float* kt = slot_ptr<DH>(a, sm, slot);
       float* ldst = arow == nullptr ? nullptr : ((ns == 1 && sc_ok) ? sc + (key0 - j0) : arow + key0);
       if (nk == kTK && key0 + kTK <= klen)
         attn_tile<DH, true>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8);
@@ -1037,6 +1068,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   for (int b = tid; b < B; b += kThreads) {
     sm.len[b] = a.st.lengths[b];
     sm.fin[b] = a.st.finished[b];
+    sm.klen[b] = a.st.input_lengths ? a.st.input_lengths[b] : a.st.mem_len;
   }
   __syncthreads();
   const int t0 = *a.st.step_counter;
@@ -1080,6 +1112,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
       __syncwarp();
     } else if (warp == kCWarps + 2) {
       // =========================== K/V feeder warp (one lane per ring slot) ===========================
+      fence_proxy_async();   // K/V rows appended in earlier steps (observed through the step-end barrier) are read by TMA
       for (int ph = 0; ph < n_ph; ++ph) {
         int l;
         const int id = phase_id(a, ph, l);
@@ -1089,10 +1122,12 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         const float* kc = (id == 1 ? a.st.self_k : a.st.cross_k) + off;
         const float* vc = (id == 1 ? a.st.self_v : a.st.cross_v) + off;
         const int rows_alloc = id == 1 ? T : a.st.mem_len, n_keys = id == 1 ? t + 1 : a.st.mem_len;
+        // the ring sits above the weight tiles of the GEMM in front of an attention phase; FFN weights are larger
+        // and reach into it, so self-attention of layer l > 0 may be pre-filled once FFN-out of layer l-1 is done
+        if (id == 1 && l > 0) wait_count(a, sm.pdone, epoch + (unsigned)ph - 1u - (a.ksplit > 1 ? 1u : 0u));
         for (int g = 0; g < NG; ++g) {
-          wait_count(a, sm.kv_go, ++f_go);
-          fence_proxy_async();
-          feed_group<DH>(a, sm, kc, vc, rows_alloc, n_keys, g, f_seq);
+          ++f_go;
+          feed_group<DH>(a, sm, kc, vc, rows_alloc, n_keys, g, f_seq, f_go, id == 1, epoch + (unsigned)ph);
         }
       }
       __syncwarp();
@@ -1207,13 +1242,17 @@ static int ksplit_for(const TtsDecoderWeights* w) { return (w->d_ffn + kKC - 1) 
 // The K/V ring lives in the weight region between the tiles of the GEMM before an attention phase (QKV or the
 // cross query: low placement) and the tiles of the GEMM after it (an output projection: high placement), so the
 // feeder may start while the consumers still read the former and the loader already streams the latter.
-static int ring_slots(const TtsDecoderWeights* w, int G, int* ring_lo) {
+static int ring_slots(const TtsDecoderWeights* w, int G, int* ring_lo, int* n_hi) {
   const int D = w->d_model, dh = D / w->n_heads;
   auto tiles = [&](int N) { return ((N + G - 1) / G + 7) / 8; };
   const int lo = tiles(3 * D) * 8 * (D + kPad), hi = kWFloats - tiles(D) * 8 * (D + kPad);
+  const int slot_f = 2 * kTK * dh;
+  int nh = (hi - lo) / slot_f, nl = lo / slot_f;
+  if (nh > kSlots) nh = kSlots;
+  if (nh + nl > kSlots) nl = kSlots - nh;
   if (ring_lo) *ring_lo = lo;
-  const int n = (hi - lo) / (2 * kTK * dh);
-  return n > kSlots ? kSlots : n;
+  if (n_hi) *n_hi = nh;
+  return nh + nl;
 }
 
 static int group_rows_for(int B) {
@@ -1304,7 +1343,7 @@ bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   worst = worst > rows(P, G) ? worst : rows(P, G);
   worst = worst > rows(M + 1, G) ? worst : rows(M + 1, G);
   if (worst > kMaxRows) return false;
-  if (ring_slots(w, G, nullptr) < 2) return false;
+  if (ring_slots(w, G, nullptr, nullptr) < 2) return false;
   if (smem_bytes(st->batch) > 227 * 1024) return false;
   return true;
 }
@@ -1325,7 +1364,7 @@ int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st,
   a.n_split = split_for(w, a.group_rows, num_sms());
   a.ksplit = ksplit_for(w);
   a.prefetch = getenv("TTS_PREFETCH") != nullptr;   // off by default: it competes with the weight stream (measured -3 %)
-  a.n_slots = ring_slots(w, num_sms(), &a.ring_lo);
+  a.n_slots = ring_slots(w, num_sms(), &a.ring_lo, &a.n_hi);
   TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, (32 * kMaxGroups + 32) * sizeof(unsigned), s));  // counters + error flag
   switch (w->d_model / w->n_heads) {
     case 32: return launch<32>(a, s);
