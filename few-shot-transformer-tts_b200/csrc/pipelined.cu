@@ -36,7 +36,8 @@ constexpr int kConsumers = kCWarps * 32;   // 256
 constexpr int kThreads = kConsumers + 96;  // + loader warp + signaler warp + K/V feeder warp
 constexpr int kGroupRows = 16;             // batch rows per group (one m16 tile)
 constexpr int kKC = 768;                   // widest K slice of an activation tile / weight row in shared memory
-constexpr int kPad = 16;                   // floats of padding per shared-memory row (bank spread of LDS.128)
+constexpr int kPad = 16;                   // floats of padding per weight row in shared memory (bank spread of LDS.128)
+constexpr int kXPad = 4;                   // floats of padding per activation row: rows 4 banks apart -> ldmatrix conflict-free
 constexpr int kLdMax = kKC + kPad;
 constexpr int kMaxRows = 24;               // weight rows per CTA and phase (3 n-tiles of 8)
 constexpr int kChunks = kKC / 16 / kCWarps;             // 16-float K chunks per warp (6)
@@ -306,7 +307,7 @@ __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const 
     mbar_arrive(sm.x_full);
     return;
   }
-  const int ld = s.kc + kPad;
+  const int ld = s.kc + kXPad;
   const unsigned row_bytes = (unsigned)s.kc * 4u;
   mbar_expect_tx(sm.x_full, (unsigned)rows * row_bytes);
   for (int r = 0; r < rows; ++r)
@@ -315,23 +316,26 @@ __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const 
 
 // C[16 rows][8 NT cols] += A (activation fragments) x B (weight rows from shared memory), 3 x TF32; the LayerNorm
 // partial sums (about the row's first element) ride along on the FMA pipe while the tensor pipe works.
+// A fragments come from ldmatrix (one instruction = the four registers of an m16n8k8 TF32 A operand, already in
+// consecutive registers: assembling them from 128-bit loads cost ~4 MOVs per MMA).  xq[j][s] covers k8-step s of
+// chunk j: {(row gq, k tq), (row gq+8, k tq), (row gq, k tq+4), (row gq+8, k tq+4)}.  The packed weight rows are
+// permuted within every 16-float chunk so that floats 4tq..4tq+3 of a row are k = tq, tq+4, tq+8, tq+12.
 // FULL: every warp owns exactly kChunks chunks and NTMAX n-tiles -> no branches, the compiler interleaves freely.
 struct RowStats {
   float s0[2], q0[2], s1[2], q1[2];   // rows gq / gq+8, two interleaved accumulators each
 };
 template <int NTMAX, bool FULL>
-__device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&xa)[kChunks][2], const float* wb, int ld,
+__device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float (&xq)[kChunks][2][4], const float* wb, int ld,
                                           int nch, int warp, int nt_run, float sh0, float sh1, RowStats& rs) {
 #pragma unroll
   for (int j = 0; j < kChunks; ++j) {
     const int c = warp + kCWarps * j;
     if (FULL || c < nch) {
-      uint32_t ah[8], al[8];
-      // logical k = tq <-> float 4tq (+2 for the second MMA), k = tq+4 <-> float 4tq+1 (+2); A and B agree
-      split_tf32(xa[j][0].x, ah[0], al[0]); split_tf32(xa[j][1].x, ah[1], al[1]);
-      split_tf32(xa[j][0].y, ah[2], al[2]); split_tf32(xa[j][1].y, ah[3], al[3]);
-      split_tf32(xa[j][0].z, ah[4], al[4]); split_tf32(xa[j][1].z, ah[5], al[5]);
-      split_tf32(xa[j][0].w, ah[6], al[6]); split_tf32(xa[j][1].w, ah[7], al[7]);
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int st = 0; st < 2; ++st)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(xq[j][st][i], ah[st][i], al[st][i]);
 #pragma unroll
       for (int nt = 0; nt < NTMAX; ++nt) {
         if (FULL || nt < nt_run) {
@@ -339,17 +343,17 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[3][2][4], const float4 (&
           uint32_t bh[4], bl[4];
           split_tf32(wv.x, bh[0], bl[0]); split_tf32(wv.y, bh[1], bl[1]);
           split_tf32(wv.z, bh[2], bl[2]); split_tf32(wv.w, bh[3], bl[3]);
-          mma_tf32(acc[nt][0], al[0], al[1], al[2], al[3], bh[0], bh[1]);
-          mma_tf32(acc[nt][1], al[4], al[5], al[6], al[7], bh[2], bh[3]);
-          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bl[2], bl[3]);
-          mma_tf32(acc[nt][0], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
-          mma_tf32(acc[nt][1], ah[4], ah[5], ah[6], ah[7], bh[2], bh[3]);
+          mma_tf32(acc[nt][0], al[0][0], al[0][1], al[0][2], al[0][3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], al[1][0], al[1][1], al[1][2], al[1][3], bh[2], bh[3]);
+          mma_tf32(acc[nt][0], ah[0][0], ah[0][1], ah[0][2], ah[0][3], bl[0], bl[1]);
+          mma_tf32(acc[nt][1], ah[1][0], ah[1][1], ah[1][2], ah[1][3], bl[2], bl[3]);
+          mma_tf32(acc[nt][0], ah[0][0], ah[0][1], ah[0][2], ah[0][3], bh[0], bh[1]);
+          mma_tf32(acc[nt][1], ah[1][0], ah[1][1], ah[1][2], ah[1][3], bh[2], bh[3]);
         }
       }
       {
-        const float d0 = xa[j][0].x - sh0, d1 = xa[j][0].y - sh0, d2 = xa[j][0].z - sh0, d3 = xa[j][0].w - sh0;
-        const float e0 = xa[j][1].x - sh1, e1 = xa[j][1].y - sh1, e2 = xa[j][1].z - sh1, e3 = xa[j][1].w - sh1;
+        const float d0 = xq[j][0][0] - sh0, d1 = xq[j][0][2] - sh0, d2 = xq[j][1][0] - sh0, d3 = xq[j][1][2] - sh0;
+        const float e0 = xq[j][0][1] - sh1, e1 = xq[j][0][3] - sh1, e2 = xq[j][1][1] - sh1, e3 = xq[j][1][3] - sh1;
         rs.s0[0] += d0 + d2; rs.s0[1] += d1 + d3;
         rs.q0[0] = fmaf(d0, d0, fmaf(d2, d2, rs.q0[0])); rs.q0[1] = fmaf(d1, d1, fmaf(d3, d3, rs.q0[1]));
         rs.s1[0] += e0 + e2; rs.s1[1] += e1 + e3;
@@ -410,23 +414,35 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   const int ld = s.kc + kPad, nch = s.kc >> 4;
   const int ncols = s.n_hi - s.n_lo, NT = (ncols + 7) >> 3;
 
-  // ---- activation fragments: rows gq and gq+8, floats 4tq..4tq+3 of the 16-float chunks {warp, warp+8, ...}
-  float4 xa[kChunks][2];
+  // ---- activation fragments (ldmatrix.x4: lanes 8i..8i+7 give the row addresses of 8x4-float matrix i =
+  //      {rows 0-7 | 8-15} x {k 0-3 | 4-7} of the k8-step), chunks {warp, warp+8, ...} of 16 floats
+  float xq[kChunks][2][4];
   float sh0 = 0.f, sh1 = 0.f;
   const bool live = has_rows && !d.zero_x;
+  const int ldx = s.kc + kXPad;
+  {
+    const int mid = lane >> 3, rin = lane & 7;
+    const uint32_t lane_addr = smem_u32(sm.xs + (rin + (mid & 1) * 8) * ldx + (mid >> 1) * 4);
 #pragma unroll
-  for (int j = 0; j < kChunks; ++j) {
-    const int c = warp + kCWarps * j;
-    if (live && c < nch) {
-      xa[j][0] = lds4(sm.xs + gq * ld + c * 16 + 4 * tq);
-      xa[j][1] = lds4(sm.xs + (gq + 8) * ld + c * 16 + 4 * tq);
-    } else {
-      xa[j][0] = xa[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kChunks; ++j) {
+      const int c = warp + kCWarps * j;
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        if (live && c < nch) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(lane_addr + (uint32_t)(c * 16 + st * 8) * 4u));
+          xq[j][st][0] = __uint_as_float(r0); xq[j][st][1] = __uint_as_float(r1);
+          xq[j][st][2] = __uint_as_float(r2); xq[j][st][3] = __uint_as_float(r3);
+        } else {
+          xq[j][st][0] = xq[j][st][1] = xq[j][st][2] = xq[j][st][3] = 0.f;
+        }
+      }
     }
   }
   if (live && d.ln) {
-    sh0 = sm.xs[gq * ld];
-    sh1 = sm.xs[(gq + 8) * ld];
+    sh0 = sm.xs[gq * ldx];
+    sh1 = sm.xs[(gq + 8) * ldx];
   }
   __syncwarp();
   if (lane == 0) mbar_arrive(sm.x_empty);   // the tile lives in registers now: the producer may refill the slot
@@ -465,11 +481,11 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
   const float* wbase = weight_base(sm, d, s);
   const float* wb = wbase + gq * ld + 4 * tq;
   if (nch == kChunks * kCWarps) {   // K slice of 768: every warp owns exactly kChunks chunks -> straight-line code
-    if (NT == 1) mma_tiles<1, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
-    else if (NT == 2) mma_tiles<2, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
-    else mma_tiles<3, true>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    if (NT == 1) mma_tiles<1, true>(acc, xq, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    else if (NT == 2) mma_tiles<2, true>(acc, xq, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    else mma_tiles<3, true>(acc, xq, wb, ld, nch, warp, NT, sh0, sh1, rs);
   } else {
-    mma_tiles<3, false>(acc, xa, wb, ld, nch, warp, NT, sh0, sh1, rs);
+    mma_tiles<3, false>(acc, xq, wb, ld, nch, warp, NT, sh0, sh1, rs);
   }
   if (prof) prof[8] = clock64();
   if (d.ln) {  // row statistics: merge the 4 lanes that share a row, one record per warp and row

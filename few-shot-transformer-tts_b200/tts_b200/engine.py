@@ -205,7 +205,10 @@ class TtsEngine:
                 n, k = wt.shape
                 kc = k // ksplit
                 out = torch.zeros((ksplit, n, kc + 16), device=wt.device, dtype=torch.float32)
-                out[:, :, :kc] = wt.detach().view(n, ksplit, kc).permute(1, 0, 2)
+                rows = wt.detach().view(n, ksplit, kc).permute(1, 0, 2)
+                # within every 16-float chunk, float 4t+i holds k = t + 4i: lane t of an MMA quad reads its four
+                # B-operand values (two k8-steps) with one 128-bit load (pipelined.cu: mma_tiles)
+                out[:, :, :kc] = rows.reshape(ksplit, n, kc // 16, 4, 4).transpose(3, 4).reshape(ksplit, n, kc)
                 if const is not None:
                     out[0, :, kc] = const.detach().view(-1)
                 if rowsum is not None:
