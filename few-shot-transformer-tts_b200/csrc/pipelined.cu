@@ -55,7 +55,7 @@ constexpr int kProfPhases = 160;
 constexpr int kProfStride = 16;
 
 enum Kind { kGemm = 0, kAttn = 1, kReduce = 2, kCombine = 3 };
-enum Mode { kPlain = 0, kQkv = 1, kPrenetOut = 2, kFinal = 3, kPartial = 4 };
+enum Mode { kPlain = 0, kQkv = 1, kPrenetOut = 2, kFinal = 3, kPartial = 4, kHid = 5 };
 
 struct Args {
   TtsDecoderWeights w;
@@ -308,6 +308,12 @@ __device__ __forceinline__ void stage_tile(const Args& a, const Smem& sm, const 
     return;
   }
   const int ld = s.kc + kXPad;
+  if (d.ldx == ld) {   // stored at the shared-memory stride (K-split-major if split): the group's rows are one run
+    const unsigned bytes = (unsigned)rows * (unsigned)ld * 4u;
+    mbar_expect_tx(sm.x_full, bytes);
+    bulk_g2s(sm.xs, d.X + ((size_t)s.ks * a.st.batch + b0) * d.ldx, bytes, sm.x_full);
+    return;
+  }
   const unsigned row_bytes = (unsigned)s.kc * 4u;
   mbar_expect_tx(sm.x_full, (unsigned)rows * row_bytes);
   for (int r = 0; r < rows; ++r)
@@ -380,6 +386,10 @@ __device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Sm
     case kPartial:
       d.Y[((size_t)s.ks * a.st.batch + b) * d.ldy + n] = v;
       break;
+    case kHid: {   // FFN hidden, K-split-major for the FFN-out phase: [n / kc][b][n % kc], row stride ldy = kc + kXPad
+      const int kc = (int)d.ldy - kXPad, sl = n / kc;
+      d.Y[((size_t)sl * a.st.batch + b) * d.ldy + (n - sl * kc)] = v;
+    } break;
     case kQkv: {
       const int H = a.w.n_heads, D = H * DH;
       const int which = n / D, cc = n - which * D;
@@ -853,7 +863,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       float v = 0.f;
 #pragma unroll
       for (int w = 0; w < kCWarps; ++w) v = fmaf(wrec[w * PS + tid], wgt[w], v);
-      if (ns == 1) a.ctx[(size_t)item * DH + tid] = v / l;
+      if (ns == 1) a.ctx[(size_t)b * (H * DH + kXPad) + (item - b * H) * DH + tid] = v / l;
       else a.fpart[((size_t)item * ns + ur.split) * PS + tid] = v;
     }
     if (ns == 1) {
@@ -901,7 +911,7 @@ __device__ __forceinline__ void combine_group(const Args& a, const Desc& d, cons
         const float pm = __ldcg(pr + sidx * PS + DH);
         if (pm > -CUDART_INF_F) acc = fmaf(__ldcg(pr + sidx * PS + tid), ex2(pm - m), acc);
       }
-      a.ctx[(size_t)item * DH + tid] = acc * inv;
+      a.ctx[(size_t)(item / H) * (H * DH + kXPad) + (item % H) * DH + tid] = acc * inv;
     }
     if (d.align != nullptr) {  // raw logits of this step -> softmax weights
       float* row = d.align + (size_t)item * d.align_bh_stride + (size_t)t * d.align_row_len;
@@ -976,21 +986,21 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   if (ph == 0) {         // prenet (tacotron.py:55-65)
     d.X = a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * M; d.ldx = (long long)T * M; d.zero_x = t == 0;
     d.K = M; d.N = P; d.W = a.w.pk_pre0; d.relu = 1;
-    d.mode = kPlain; d.Y = a.p0; d.ldy = P; d.hi = 1;
+    d.mode = kPlain; d.Y = a.p0; d.ldy = P + kXPad; d.hi = 1;
     return;
   }
   if (ph == 1) {
-    d.X = a.p0; d.ldx = P; d.K = P; d.N = P; d.W = a.w.pk_pre1;
-    d.relu = 1; d.mode = kPlain; d.Y = a.p1; d.ldy = P; d.hi = 0;
+    d.X = a.p0; d.ldx = P + kXPad; d.K = P; d.N = P; d.W = a.w.pk_pre1;
+    d.relu = 1; d.mode = kPlain; d.Y = a.p1; d.ldy = P + kXPad; d.hi = 0;
     return;
   }
   if (ph == 2) {         // + shift / mask / PE (modules.py:114-118)
-    d.X = a.p1; d.ldx = P; d.K = P; d.N = D; d.W = a.w.pk_pre2; d.mode = kPrenetOut;
-    d.Y = a.x; d.ldy = D; d.hi = 1;
+    d.X = a.p1; d.ldx = P + kXPad; d.K = P; d.N = D; d.W = a.w.pk_pre2; d.mode = kPrenetOut;
+    d.Y = a.x; d.ldy = D + kXPad; d.hi = 1;
     return;
   }
   if (ph == 3 + ppl * L) {  // final LN + mel / stop projections
-    d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = M + 1; d.W = a.w.pk_final;
+    d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = M + 1; d.W = a.w.pk_final;
     d.mode = kFinal; d.hi = 0;
     return;
   }
@@ -1006,7 +1016,7 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
   switch (id) {
     case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = 3 * D; d.W = lw.pk_qkv;
+      d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = 3 * D; d.W = lw.pk_qkv;
       d.mode = kQkv; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
       d.kcache = a.st.self_k + self_off; d.vcache = a.st.self_v + self_off; d.hi = 0;
       break;
@@ -1019,11 +1029,11 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kCombine; d.n_keys = t + 1; d.align = al_self; d.align_bh_stride = (long long)T * T; d.align_row_len = T;
       break;
     case 3:  // output projection + residual (attention.py:118-119, modules.py:132)
-      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_self_out; d.mode = kPlain;
-      d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
+      d.X = a.ctx; d.ldx = D + kXPad; d.K = D; d.N = D; d.W = lw.pk_self_out; d.mode = kPlain;
+      d.Y = a.x; d.ldy = D + kXPad; d.R = a.x; d.ldr = D + kXPad; d.hi = 1;
       break;
     case 4:  // LN + cross query
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_cross_q;
+      d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = D; d.W = lw.pk_cross_q;
       d.mode = kPlain; d.Y = a.q; d.ldy = D; d.out_scale = qscale;
       d.hi = 0;
       break;
@@ -1036,23 +1046,23 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
       d.kind = kCombine; d.n_keys = S; d.align = al_cross; d.align_bh_stride = (long long)T * S; d.align_row_len = S;
       break;
     case 7:
-      d.X = a.ctx; d.ldx = D; d.K = D; d.N = D; d.W = lw.pk_cross_out; d.mode = kPlain;
-      d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D; d.hi = 1;
+      d.X = a.ctx; d.ldx = D + kXPad; d.K = D; d.N = D; d.W = lw.pk_cross_out; d.mode = kPlain;
+      d.Y = a.x; d.ldy = D + kXPad; d.R = a.x; d.ldr = D + kXPad; d.hi = 1;
       break;
     case 8:  // LN + FFN-in + ReLU (modules.py:14-17)
-      d.ln = 1; d.X = a.x; d.ldx = D; d.K = D; d.N = F; d.W = lw.pk_ffn_in;
-      d.relu = 1; d.mode = kPlain; d.Y = a.hid; d.ldy = F; d.hi = 0;
+      d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = F; d.W = lw.pk_ffn_in;
+      d.relu = 1; d.mode = kHid; d.Y = a.hid; d.ldy = F / a.ksplit + kXPad; d.hi = 0;
       break;
     case 9:  // FFN-out: K-split partials, or + residual directly
-      d.X = a.hid; d.ldx = F; d.K = F; d.N = D; d.W = lw.pk_ffn_out; d.hi = 1;
+      d.X = a.hid; d.ldx = F / a.ksplit + kXPad; d.K = F; d.N = D; d.W = lw.pk_ffn_out; d.hi = 1;
       if (red) {
         d.ksplit = a.ksplit; d.mode = kPartial; d.Y = a.part; d.ldy = D;
       } else {
-        d.mode = kPlain; d.Y = a.x; d.ldy = D; d.R = a.x; d.ldr = D;
+        d.mode = kPlain; d.Y = a.x; d.ldy = D + kXPad; d.R = a.x; d.ldr = D + kXPad;
       }
       break;
     default:
-      d.kind = kReduce; d.Y = a.x; d.ldy = D; d.N = D; d.part = a.part; d.n_parts = a.ksplit;
+      d.kind = kReduce; d.Y = a.x; d.ldy = D + kXPad; d.N = D; d.part = a.part; d.n_parts = a.ksplit;
       break;
   }
 }
@@ -1298,7 +1308,11 @@ static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
   c.bar = reinterpret_cast<unsigned*>(take(32 * kMaxGroups));
   c.err = reinterpret_cast<int*>(take(32));
   c.prof = reinterpret_cast<long long*>(take(2 * kProfStride * kProfPhases));
-  c.x = take(B * D); c.q = take(B * D); c.ctx = take(B * D); c.hid = take(B * F); c.p0 = take(B * P); c.p1 = take(B * P);
+  // activations that are staged by TMA are stored with the shared-memory row stride (K + kXPad): a row group is one
+  // contiguous run = one bulk copy.  hid is K-split-major: [ksplit][B][F / ksplit + kXPad].
+  const size_t ks = ksplit_for(w);
+  c.x = take(B * (D + kXPad)); c.q = take(B * D); c.ctx = take(B * (D + kXPad)); c.hid = take(ks * B * (F / ks + kXPad));
+  c.p0 = take(B * (P + kXPad)); c.p1 = take(B * (P + kXPad));
   c.part = take((size_t)ksplit_for(w) * B * D);
   c.fpart = take((size_t)B * H * kMaxSplit * (dh + 4));
   c.floats = off;
