@@ -96,6 +96,7 @@ struct Smem {
   float* red;      // [8][16][24] cross-warp reduction / attention warp records
   float* spart;    // [8][16][2] LayerNorm partial (sum, sum of squares) about the row's first element
   float* sshift;   // [16]
+  float* qbuf;     // [2][96] query of the CTA's first attention unit of a group-phase, prefetched by the feeder warp
   int* len;        // [B]
   int* fin;        // [B]
   int* klen;       // [B] input_lengths (key mask of the cross attention), cached once per launch
@@ -104,6 +105,7 @@ struct Smem {
   uint64_t* w_full;   // 2: weight slice landed (low / high placement)
   uint64_t* pdone;    // phases the consumers have finished, as a plain counter (an mbarrier's parity would alias:
                       // with a single row group the consumers can complete two phases before the loader looks)
+  uint64_t* qfull;    // 2: prefetched query landed
   uint64_t* rfull;    // [kSlots] ring slot filled (feeder warp -> consumers)
   unsigned* drained;  // [kSlots] how many tiles have been consumed out of each slot.  A plain counter, not an mbarrier:
                       // a consumer may reach the slot's use n+2 while use n is still being read, and a parity
@@ -114,10 +116,10 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t smem_floats_fixed() {
-  return (size_t)kXsFloats + kWFloats + kRedFloats + kCWarps * kGroupRows * 2 + kGroupRows;
+  return (size_t)kXsFloats + kWFloats + kRedFloats + kCWarps * kGroupRows * 2 + kGroupRows + 2 * 96;
 }
 static size_t smem_bytes(int B) {
-  return smem_floats_fixed() * sizeof(float) + (size_t)3 * B * sizeof(int) + (8 + 2 * kSlots) * sizeof(uint64_t) +
+  return smem_floats_fixed() * sizeof(float) + (size_t)3 * B * sizeof(int) + (10 + 2 * kSlots) * sizeof(uint64_t) +
          kDescRing * sizeof(Desc) + 64;
 }
 
@@ -128,7 +130,8 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.red = sm.wreg + kWFloats;
   sm.spart = sm.red + kRedFloats;
   sm.sshift = sm.spart + kCWarps * kGroupRows * 2;
-  sm.len = reinterpret_cast<int*>(sm.sshift + kGroupRows);
+  sm.qbuf = sm.sshift + kGroupRows;
+  sm.len = reinterpret_cast<int*>(sm.qbuf + 2 * 96);
   sm.fin = sm.len + a.st.batch;
   sm.klen = sm.fin + a.st.batch;
   uintptr_t p = reinterpret_cast<uintptr_t>(sm.klen + a.st.batch);
@@ -137,7 +140,8 @@ __device__ __forceinline__ Smem make_smem(const Args& a, float* base) {
   sm.x_empty = sm.x_full + 1;
   sm.w_full = sm.x_full + 2;
   sm.pdone = sm.x_full + 4;
-  sm.rfull = sm.x_full + 5;
+  sm.qfull = sm.x_full + 5;
+  sm.rfull = sm.x_full + 7;
   sm.drained = reinterpret_cast<unsigned*>(sm.rfull + kSlots);
   uint64_t* after = sm.rfull + 2 * kSlots;
   sm.sig = reinterpret_cast<unsigned*>(after);
@@ -374,6 +378,7 @@ struct CState {
   unsigned gp;            // group-phases consumed so far (parity of x_full)
   unsigned wpar0, wpar1;  // parity of the two weight barriers (scalars: a dynamically indexed array would live in local memory)
   unsigned ring_seq;      // K/V ring tiles of all attention units this CTA has finished (slot and parity of the next)
+  unsigned q_uses;        // prefetched queries consumed (slot = uses & 1, parity = (uses >> 1) & 1)
 };
 
 template <int DH>
@@ -602,6 +607,10 @@ struct UnitRange {
 };
 __device__ __forceinline__ UnitRange unit_range(int u, int ns, int n_keys, int item0) {
   UnitRange r;
+  if (ns == 1) {   // one stream per (sample, head): no divisions on the consumers' critical path
+    r.split = 0; r.item = item0 + u; r.j0 = 0; r.j1 = n_keys; r.n_tiles = (n_keys + kTK - 1) / kTK;
+    return r;
+  }
   const int per = (n_keys + ns - 1) / ns;
   const int litem = ns == 1 ? u : u / ns;
   r.split = u - litem * ns;
@@ -630,7 +639,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, unsigned parity) {
 template <int DH>
 __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const float* kc, const float* vc, int rows_alloc,
                                            int n_keys, int g, unsigned& f_seq, unsigned go_target, bool gate_last,
-                                           unsigned low_target) {
+                                           unsigned low_target, unsigned& f_q) {
   // go_target: value of sm.kv_go once the loader has seen the previous phase of this group complete everywhere.
   // Cross K/V never changes during decode and self K/V rows < t were written in earlier steps, so only the tile
   // that holds the row appended in this step (gate_last: the last key of the stream) has to wait for it; all
@@ -651,8 +660,22 @@ __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const 
   uint64_t* my_full = &sm.rfull[lane < (int)nsl ? lane : 0];
   float* dst = slot_ptr<DH>(a, sm, lane < (int)nsl ? lane : 0);
   bool low_ok = lane < a.n_hi;   // low slots: only after the GEMM in front of the attention phase (pdone >= low_target)
+  // lane 31: the query of the first unit (written in the phase before this one) -> shared memory, as soon as the
+  // loader has seen that phase complete; the consumers then find it without an L2 round trip
+  bool q_todo = lane == 31 && (int)blockIdx.x < n_units;
   long long spins = 0, t0 = 0;
-  while (__any_sync(0xffffffffu, k < total)) {
+  while (__any_sync(0xffffffffu, k < total || q_todo)) {
+    if (q_todo) {
+      unsigned gv;
+      asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(gv) : "r"(smem_u32(sm.kv_go)) : "memory");
+      if (static_cast<int>(gv - go_target) >= 0) {
+        fence_proxy_async();
+        uint64_t* qb = &sm.qfull[f_q & 1u];
+        mbar_expect_tx(qb, (unsigned)DH * 4u);
+        bulk_g2s(sm.qbuf + (f_q & 1u) * 96, a.q + (size_t)unit_range(blockIdx.x, ns, n_keys, item0).item * DH, (unsigned)DH * 4u, qb);
+        q_todo = false;
+      }
+    }
     if (k < total) {
       bool continue_spin = false;
       const unsigned seq = f_seq + (unsigned)k;
@@ -695,6 +718,7 @@ __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const 
     }
   }
   f_seq += (unsigned)total;
+  if ((int)blockIdx.x < n_units) ++f_q;
 }
 
 // one tile of 8 keys: scores, online softmax update, weighted V.  FULL: all 8 keys exist and none is masked.
@@ -768,7 +792,8 @@ __device__ __forceinline__ void attn_tile(const float* kt, const float* vt, cons
 }
 
 template <int DH>
-__device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const Smem& sm, CState& cs, int g, int t) {
+__device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const Smem& sm, CState& cs, int g, int t,
+                                           long long* prof) {
   constexpr int F4 = DH / 32;            // float4 per lane per key row (8 lanes span a row)
   constexpr int kTile = kTK * DH;        // floats per K (or V) tile
   constexpr int kSlotF = 2 * kTile;      // K tile then V tile
@@ -793,9 +818,16 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     f32x4 qv[F4];
     {
       const f32x2 sc2 = pack2(kLog2e, kLog2e);
+      const bool pre = u == (int)blockIdx.x;   // the first unit's query was prefetched into shared memory by the feeder
+      const float* qsrc = a.q + (size_t)item * DH;
+      if (pre) {
+        mbar_wait(&sm.qfull[cs.q_uses & 1u], (cs.q_uses >> 1) & 1u, a.err);
+        qsrc = sm.qbuf + (cs.q_uses & 1u) * 96;
+        ++cs.q_uses;
+      }
 #pragma unroll
       for (int i = 0; i < F4; ++i) {
-        qv[i] = ld4cg(a.q + (size_t)item * DH + 4 * (l8 + 8 * i));
+        qv[i] = pre ? ld4s(qsrc + 4 * (l8 + 8 * i)) : ld4cg(qsrc + 4 * (l8 + 8 * i));
         qv[i].lo = fma2(qv[i].lo, sc2, 0ull);
         qv[i].hi = fma2(qv[i].hi, sc2, 0ull);
       }
@@ -804,6 +836,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     f32x2 o[F4][2];
 #pragma unroll
     for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
+    if (prof) prof[6] = clock64();
 
     // slot and use number of this warp's first tile; advanced incrementally (no division in the loop)
     unsigned slot = (seq_base + (unsigned)warp) % (unsigned)a.n_slots, use = (seq_base + (unsigned)warp) / (unsigned)a.n_slots;
@@ -827,6 +860,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       }
     }
     seq_base += (unsigned)ur.n_tiles;
+    if (prof) prof[7] = clock64();
     // ---- warp record (max, sum, weighted V) -> shared ----
 #pragma unroll
     for (int i = 0; i < F4; ++i)
@@ -848,6 +882,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       wrec[warp * PS + DH + 1] = lw;
     }
     consumer_bar();
+    if (prof) prof[8] = clock64();
     float m = -CUDART_INF_F;
 #pragma unroll
     for (int w = 0; w < kCWarps; ++w) m = fmaxf(m, wrec[w * PS + DH]);
@@ -876,7 +911,9 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       a.fpart[((size_t)item * ns + ur.split) * PS + DH] = m;       // -inf when the split is empty
       a.fpart[((size_t)item * ns + ur.split) * PS + DH + 1] = l;
     }
+    if (prof) prof[9] = clock64();
     consumer_bar();  // wrec / sc are reused by the next unit
+    if (prof) prof[10] = clock64();
   }
   cs.ring_seq = seq_base;
 }
@@ -1083,6 +1120,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
     mbar_init(&sm.w_full[0], 1);
     mbar_init(&sm.w_full[1], 1);
     *reinterpret_cast<volatile unsigned*>(sm.pdone) = 0u;
+    mbar_init(&sm.qfull[0], 1);
+    mbar_init(&sm.qfull[1], 1);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&sm.rfull[i], 1);
       sm.drained[i] = 0u;
@@ -1099,9 +1138,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   __syncthreads();
   const int t0 = *a.st.step_counter;
 
-  CState cs{0u, 0u, 0u, 0u};
+  CState cs{0u, 0u, 0u, 0u, 0u};
   unsigned p_gp = 0u, p_go = 0u;        // loader: group-phases staged, attention group-phases released to the feeder
-  unsigned f_go = 0u, f_seq = 0u;       // feeder: attention group-phases served, ring tiles issued
+  unsigned f_go = 0u, f_seq = 0u, f_q = 0u;   // feeder: attention group-phases served, ring tiles issued, queries prefetched
   unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started
 
@@ -1153,7 +1192,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         if (id == 1 && l > 0) wait_count(a, sm.pdone, epoch + (unsigned)ph - 1u - (a.ksplit > 1 ? 1u : 0u));
         for (int g = 0; g < NG; ++g) {
           ++f_go;
-          feed_group<DH>(a, sm, kc, vc, rows_alloc, n_keys, g, f_seq, f_go, id == 1, epoch + (unsigned)ph);
+          feed_group<DH>(a, sm, kc, vc, rows_alloc, n_keys, g, f_seq, f_go, id == 1, epoch + (unsigned)ph, f_q);
         }
       }
       __syncwarp();
@@ -1199,7 +1238,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
           } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.x_empty);
-            if (d.kind == kAttn) attn_group<DH>(a, d, sm, cs, g, t);
+            if (d.kind == kAttn) attn_group<DH>(a, d, sm, cs, g, t, g == 0 ? prof : nullptr);
             else if (d.kind == kReduce) reduce_group(a, d, g);
             else combine_group<DH>(a, d, sm, g, t);
           }

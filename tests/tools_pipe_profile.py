@@ -53,3 +53,9 @@ for target in steps:
         f = lambda i, j: sum(d[i] - d[j] for d in v) / n
         print("   %-7s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f" % (k, f(6, 1), f(11, 6), f(7, 11), f(8, 7), f(9, 8), f(10, 9),
                                                                    f(2, 10)))
+    print("   attention group 0 detail (us): setup+q | tile loop (warp 0) | wait other warps | merge+ctx+align | unit-end barrier | group-end")
+    for k in ("self", "cross"):
+        v = kinds[k]
+        n = len(v)
+        f = lambda i, j: sum(d[i] - d[j] for d in v) / n
+        print("   %-7s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f" % (k, f(6, 1), f(7, 6), f(8, 7), f(9, 8), f(10, 9), f(2, 10)))
