@@ -44,7 +44,7 @@ constexpr int kChunks = kKC / 16 / kCWarps;             // 16-float K chunks per
 constexpr int kXsFloats = kGroupRows * kLdMax;          // activation slot
 constexpr int kWFloats = 2 * kMaxRows * kLdMax;         // weight region: two phases in flight
 constexpr int kRedFloats = kCWarps * kGroupRows * kMaxRows;
-constexpr int kTK = 8;                     // keys per K/V ring tile
+constexpr int kTK = 8;                     // keys per K/V ring tile (16-key tiles: register spills, no gain; 4-key tiles: slower)
 constexpr int kSlots = 24;                 // most slots of the CTA-wide K/V ring (K tile + V tile each; one feeder lane per slot)
 constexpr int kMaxBatch = 1024;
 constexpr int kMaxGroups = 64;
