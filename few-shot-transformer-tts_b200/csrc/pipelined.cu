@@ -79,6 +79,7 @@ struct Desc {
   const float* X; long long ldx; int K, N, ksplit;
   const float* W;       // packed rows [ksplit][N][K/ksplit + 16]: weights | constant | LayerNorm row sum (tts_b200.h pk_*)
   int ln, relu, mode, hi, zero_x;
+  float inv_k;          // 1 / K
   float* Y; long long ldy; const float* R; long long ldr; float out_scale;
   float* kcache; float* vcache;
   // ---- attention over a K/V stream
@@ -392,12 +393,14 @@ __device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Sm
       d.Y[((size_t)s.ks * a.st.batch + b) * d.ldy + n] = v;
       break;
     case kHid: {   // FFN hidden, K-split-major for the FFN-out phase: [n / kc][b][n % kc], row stride ldy = kc + kXPad
-      const int kc = (int)d.ldy - kXPad, sl = n / kc;
+      const int kc = (int)d.ldy - kXPad;
+      int sl = 0;
+      for (int e = kc; e <= n; e += kc) ++sl;   // n / kc for a handful of slices, without a runtime division
       d.Y[((size_t)sl * a.st.batch + b) * d.ldy + (n - sl * kc)] = v;
     } break;
     case kQkv: {
       const int H = a.w.n_heads, D = H * DH;
-      const int which = n / D, cc = n - which * D;
+      const int which = (n >= D) + (n >= 2 * D), cc = n - which * D;   // q | k | v without a runtime division
       if (which == 0) {
         d.Y[(size_t)b * d.ldy + cc] = v * d.out_scale;
       } else {
@@ -550,7 +553,7 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
     const float2 c0 = *reinterpret_cast<const float2*>(wbase + nl0 * ld + s.kc);   // (constant, LayerNorm row sum)
     const float2 c1 = *reinterpret_cast<const float2*>(wbase + nl1 * ld + s.kc);
     if (d.ln) {  // LayerNorm (eps 1e-6, modules.py:88) applied to the finished product
-      const float invK = 1.f / (float)d.K;
+      const float invK = d.inv_k;
       const float ms = S * invK;
       const float var = fmaxf(Q * invK - ms * ms, 0.f);
       const float rstd = rsqrtf(var + 1e-6f);
@@ -1003,6 +1006,7 @@ template <int DH>
 __device__ __forceinline__ void get_phase(const Args& a, int ph, int t, float qscale, Desc& d) {
   get_phase_body<DH>(a, ph, t, qscale, d);
   if (d.kind == kGemm) {
+    d.inv_k = 1.f / (float)d.K;
     const Slice s = compute_slice(d, blockIdx.x, gridDim.x);
     d.s_n_lo = s.n_lo; d.s_n_hi = s.n_hi; d.s_k_lo = s.k_lo; d.s_kc = s.kc; d.s_ks = s.ks;
   } else if (d.kind == kReduce) {
