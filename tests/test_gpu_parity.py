@@ -313,6 +313,28 @@ def test_decode_properties_at_baseline_shape(full_params, ops):
     assert _err(a["mel_pre"][:, :6], want["mel_pre"][:, :6]) < 2e-4
 
 
+def test_long_decode_and_wide_batch_impl_agreement(full_params, ops):
+    """Long streams (640 frames: every K/V ring slot is reused dozens of times, 80-tile streams) and a wide batch
+    (B=128: eight row groups in flight) on the pipelined kernel vs the independent fused FFMA2 kernel."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=32, text_len=258, n_frames=4, seed=5)
+    mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
+    a = eng.generate(batch, max_frames=640, record_align="none", memory=mem, chunk=50, impl=4)
+    b = eng.generate(batch, max_frames=640, record_align="none", memory=mem, chunk=50, impl=3)
+    assert a["generated_lengths"].cpu().tolist() == b["generated_lengths"].cpu().tolist() == [641] * 32
+    assert _err(a["mel_pre"], b["mel_pre"]) < 2e-4 and _err(a["mel_aft"], b["mel_aft"]) < 2e-4
+    assert float(a["mel_pre"][:, -1].abs().max()) > 0.0
+    wide = O.synth_batch(cfg, batch=128, text_len=61, n_frames=4, seed=6, ragged=True)
+    c = eng.generate(wide, max_frames=20, record_align="encdec", chunk=20, impl=4)
+    d = eng.generate(wide, max_frames=20, record_align="encdec", chunk=20, impl=3)
+    assert _err(c["mel_pre"], d["mel_pre"]) < 2e-4
+    assert _err(c["alignments"]["encdec"][3], d["alignments"]["encdec"][3]) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # the drop-in nn.Module API, driven the way the reference's synthesize.py / train.py drive it
 # ---------------------------------------------------------------------------------------------
