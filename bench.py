@@ -65,19 +65,52 @@ def decode_bytes_range(cfg, batch, mem_len, t0, t1, elem=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML is read in-process
+    from a thread (nvidia_ml_py); the `nvidia-smi -lms` subprocess of the recipe is the fallback - it costs ~4 % of
+    this job's wall clock (20 cooperative launches per synthesis stall behind its queries), NVML reads do not."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, period=0.05):
+        self.rows, self.proc, self.index, self.period = [], None, index, period
+        self.stop, self.thread, self.source = threading.Event(), None, None
+
+    def _nvml_loop(self, nv, h):
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                self.rows.append([str(sm), str(mx), "%.1f" % pw] + ["Active" if bits & b else "Not Active" for _, b in names])
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __enter__(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.source = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -89,13 +122,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self.thread is not None:
             self.thread.join(timeout=2)
+        return False
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -110,8 +146,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0, "source": self.source}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def measured_peaks():
