@@ -30,6 +30,25 @@ def sinusoid_table(length: int, channels: int) -> torch.Tensor:
     return torch.from_numpy(tab.astype(np.float32))
 
 
+def pack_rows(wt, const=None, rowsum=None, ksplit=1):
+    """Packed operand of the pipelined decode kernel (include/tts_b200.h, pk_*): [ksplit][N][K/ksplit + 16] with
+    row = weights | additive constant | LayerNorm row sum | zeros.  Within every 16-float chunk of the weights,
+    float 4t+i holds k = t + 4i, so that lane t of an MMA quad reads its four B-operand values (two k8-steps)
+    with one 128-bit load (pipelined.cu: mma_tiles)."""
+    with torch.no_grad():
+        n, k = wt.shape
+        kc = k // ksplit
+        assert kc * ksplit == k and kc % 16 == 0, (k, ksplit)
+        out = torch.zeros((ksplit, n, kc + 16), device=wt.device, dtype=torch.float32)
+        rows = wt.detach().view(n, ksplit, kc).permute(1, 0, 2)
+        out[:, :, :kc] = rows.reshape(ksplit, n, kc // 16, 4, 4).transpose(3, 4).reshape(ksplit, n, kc)
+        if const is not None:
+            out[0, :, kc] = const.detach().view(-1)
+        if rowsum is not None:
+            out[0, :, kc + 1] = rowsum.view(-1)
+    return out
+
+
 class DecodeSession:
     """Device state of one autoregressive batch: self/cross K/V caches, frames, lengths.
     Layout and meaning of every buffer: include/tts_b200.h (TtsDecodeState)."""
@@ -200,19 +219,7 @@ class TtsEngine:
             return wf, cf, sf
 
         def pack(wt, const=None, rowsum=None, ksplit=1):
-            """[ksplit][N][K/ksplit + 16] rows for the pipelined kernel (include/tts_b200.h, pk_*)."""
-            with torch.no_grad():
-                n, k = wt.shape
-                kc = k // ksplit
-                out = torch.zeros((ksplit, n, kc + 16), device=wt.device, dtype=torch.float32)
-                rows = wt.detach().view(n, ksplit, kc).permute(1, 0, 2)
-                # within every 16-float chunk, float 4t+i holds k = t + 4i: lane t of an MMA quad reads its four
-                # B-operand values (two k8-steps) with one 128-bit load (pipelined.cu: mma_tiles)
-                out[:, :, :kc] = rows.reshape(ksplit, n, kc // 16, 4, 4).transpose(3, 4).reshape(ksplit, n, kc)
-                if const is not None:
-                    out[0, :, kc] = const.detach().view(-1)
-                if rowsum is not None:
-                    out[0, :, kc + 1] = rowsum.view(-1)
+            out = pack_rows(wt, const, rowsum, ksplit)
             keep.append(out)
             return out.data_ptr()
 

@@ -114,3 +114,25 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(base, f)
+
+
+def test_packed_rows_layout():
+    """Host packing of the pipelined kernel's weight operand (tts_b200.h pk_*): k-permutation per 16-float chunk,
+    K-split-major slices, constants in the row tail."""
+    import torch
+    from tts_b200.engine import pack_rows
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(10, 64, generator=g)
+    c, s = torch.randn(10, generator=g), torch.randn(10, generator=g)
+    p = pack_rows(w, c, s)
+    assert p.shape == (1, 10, 80)
+    for n in (0, 7):
+        for chunk in range(4):
+            for t in range(4):
+                for i in range(4):
+                    assert p[0, n, chunk * 16 + 4 * t + i] == w[n, chunk * 16 + t + 4 * i]
+    assert torch.equal(p[0, :, 64], c) and torch.equal(p[0, :, 65], s) and float(p[0, :, 66:].abs().max()) == 0.0
+    q = pack_rows(w, ksplit=2)
+    assert q.shape == (2, 10, 48)
+    assert q[1, 3, 4 * 2 + 1] == w[3, 32 + 2 + 4 * 1] and q[0, 3, 16 + 4 * 3 + 0] == w[3, 16 + 3]
+    assert float(q[:, :, 32:].abs().max()) == 0.0
