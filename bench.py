@@ -56,7 +56,7 @@ def decode_bytes(cfg, batch, mem_len, n_steps, elem=4):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (50 decode steps, t = 475..524, B=32, S=258) from the
 # committed `ncu --set full` captures (profiles/README.md), keyed by decode implementation
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {3: 55.06e9,    # fused_decode_kernel, profiles/r1_fused_ncu_raw.csv
-                                4: 55.366e9}   # pipelined_decode_kernel, profiles/r1_pipe_ncu_raw.csv (54.90 GB read + 0.46 GB written)
+                                4: 55.371e9}   # pipelined_decode_kernel, profiles/r1_pipe_ncu_raw.csv (54.90 GB read + 0.47 GB written)
 KERNEL_NAME = {3: "fused_decode_kernel", 4: "pipelined_decode_kernel"}
 
 
