@@ -255,7 +255,7 @@ def run_ours(args):
     import __graft_entry__ as G
     if not os.path.exists(G.LIB):
         G.build()
-    from oracle import tts_oracle as O      # weights/inputs generator + cpu_baseline only
+    from tts_b200 import synthetic as O     # workload definition: config, seeded weights and inputs (no oracle here)
     from tts_b200 import _native
     from tts_b200.engine import TtsEngine
 
