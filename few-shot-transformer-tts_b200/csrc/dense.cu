@@ -5,6 +5,10 @@
 // Reference call sites replaced: every nn.Linear / nn.Conv1d / nn.LayerNorm / nn.Embedding on
 // the path — transformer/attention.py:43-47, modules.py:11-19,36-47,49-56,88-106,114-118,
 // tacotron.py:21-44,50-64,78-90,112-115.
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "common.cuh"
 
 namespace tts {
@@ -248,6 +252,20 @@ __global__ void cond_embed_kernel(const float* __restrict__ vec, int vec_dim, co
 
 using namespace tts;
 
+namespace tts {
+// 1 = dense GEMMs with K % 32 == 0 run on the tcgen05 kernel; initial value from TTS_GEMM_TC (default: see below)
+static std::atomic<int> g_gemm_tc{[]() { const char* e = getenv("TTS_GEMM_TC"); return e != nullptr ? (e[0] == '1' ? 1 : 0) : 0; }()};
+bool gemm_tc_supported(int M, int N, int K, int lda, int ldw);
+int launch_gemm_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                   const TtsGemmEpilogue& epi, cudaStream_t s);
+}  // namespace tts
+
+extern "C" int tts_gemm_use_tensor_cores(int on) {
+  const int prev = g_gemm_tc.load();
+  if (on >= 0) g_gemm_tc.store(on ? 1 : 0);
+  return prev;
+}
+
 extern "C" int tts_gemm_nt(const float* A, int32_t lda, const float* W, int32_t ldw, float* C, int32_t ldc,
                            int32_t M, int32_t N, int32_t K, const TtsGemmEpilogue* epi_in, void* stream) {
   TTS_REQUIRE(M > 0 && N > 0 && K > 0, "tts_gemm_nt: empty problem M=%d N=%d K=%d", M, N, K);
@@ -263,6 +281,9 @@ extern "C" int tts_gemm_nt(const float* A, int32_t lda, const float* W, int32_t 
   TTS_REQUIRE(epi.scale == nullptr || epi.shift != nullptr, "tts_gemm_nt: scale without shift");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long big_ctas = (long)ceil_div(M, 128) * ceil_div(N, 128);
+  // large, K % 32 == 0 problems run on the tcgen05 3xTF32 kernel (gemm_tc.cu); TTS_GEMM_TC=0 keeps the FFMA2 kernels
+  if (g_gemm_tc.load(std::memory_order_relaxed) != 0 && M >= 256 && big_ctas >= 32 && gemm_tc_supported(M, N, K, lda, ldw) && (reinterpret_cast<uintptr_t>(C) & 3) == 0)
+    return launch_gemm_tc(A, lda, W, ldw, C, ldc, M, N, K, epi, s);
   if (big_ctas >= 148) {
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128));
     gemm_nt_kernel<128, 128, 8, 8><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, epi);

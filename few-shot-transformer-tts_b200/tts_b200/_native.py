@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
 TTS_MAX_LAYERS = 16
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -58,6 +58,7 @@ _EXPORTS = {
     "tts_launch_count_reset": (None, []),
     "tts_gemm_nt": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                               C.c_int32, C.c_int32, C.POINTER(GemmEpilogue), C.c_void_p]),
+    "tts_gemm_use_tensor_cores": (C.c_int, [C.c_int]),
     "tts_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_embed_pe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 6
+#define TTS_ABI_VERSION 7
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -71,6 +71,10 @@ typedef struct TtsGemmEpilogue {
  * tacotron.py:50-52,56-64,78,85,112,114.  K % 4 == 0, lda % 4 == 0, ldw % 4 == 0. */
 int tts_gemm_nt(const float* A, int32_t lda, const float* W, int32_t ldw, float* C, int32_t ldc,
                 int32_t M, int32_t N, int32_t K, const TtsGemmEpilogue* epi, void* stream);
+
+/* Route large tts_gemm_nt problems with K % 32 == 0 through the tcgen05 (TMEM-accumulating) 3xTF32 kernel (1) or keep
+ * the packed-FFMA2 kernels (0); on < 0 only queries.  Returns the previous setting.  Initial value: TTS_GEMM_TC. */
+int tts_gemm_use_tensor_cores(int on);
 
 /* y[r,:] = LayerNorm(x[r,:]) * gamma + beta, eps = 1e-6 (modules.py:36,43,47,88,95,102,106).
  * row_len/rows_per_batch (optional) zero rows at or beyond the length (common.py:51 impute). */

@@ -313,6 +313,30 @@ def test_decode_properties_at_baseline_shape(full_params, ops):
     assert _err(a["mel_pre"][:, :6], want["mel_pre"][:, :6]) < 2e-4
 
 
+def test_tcgen05_gemm_vs_float64(ops):
+    """csrc/gemm_tc.cu (tcgen05.mma kind::tf32, 3-term split, TMEM accumulator) against a float64 product, with every
+    epilogue feature the dense path uses and ragged M / N tails; the FFMA2 kernel on the same inputs as a second check."""
+    from tts_b200 import _native
+    lib = _native.load()
+    prev = lib.tts_gemm_use_tensor_cores(1)
+    try:
+        g = torch.Generator().manual_seed(4)
+        for (M, N, K) in ((256, 128, 64), (1000, 200, 96), (4128, 512, 512), (2000, 1536, 768)):
+            x = torch.randn(M, K, generator=g).to(DEV)
+            w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+            b = torch.randn(N, generator=g).to(DEV)
+            res = torch.randn(M, N, generator=g).to(DEV)
+            lib.tts_gemm_use_tensor_cores(1)
+            y = ops.linear(x, w, bias=b, act=ops.ACT_RELU, residual=res, alpha=0.5)
+            lib.tts_gemm_use_tensor_cores(0)
+            y0 = ops.linear(x, w, bias=b, act=ops.ACT_RELU, residual=res, alpha=0.5)
+            want = torch.relu(0.5 * (x.double() @ w.double().t()) + b.double()) + res.double()
+            assert _err(y.double(), want) < 2e-5, (M, N, K)
+            assert _err(y, y0) < 2e-5, (M, N, K)
+    finally:
+        lib.tts_gemm_use_tensor_cores(prev)
+
+
 def test_long_decode_and_wide_batch_impl_agreement(full_params, ops):
     """Long streams (640 frames: every K/V ring slot is reused dozens of times, 80-tile streams) and a wide batch
     (B=128: eight row groups in flight) on the pipelined kernel vs the independent fused FFMA2 kernel."""
