@@ -253,8 +253,8 @@ __global__ void cond_embed_kernel(const float* __restrict__ vec, int vec_dim, co
 using namespace tts;
 
 namespace tts {
-// 1 = dense GEMMs with K % 32 == 0 run on the tcgen05 kernel; initial value from TTS_GEMM_TC (default: see below)
-static std::atomic<int> g_gemm_tc{[]() { const char* e = getenv("TTS_GEMM_TC"); return e != nullptr ? (e[0] == '1' ? 1 : 0) : 0; }()};
+// 1 = large dense GEMMs with K % 32 == 0 run on the tcgen05 kernel (default); TTS_GEMM_TC=0 keeps the FFMA2 kernels
+static std::atomic<int> g_gemm_tc{[]() { const char* e = getenv("TTS_GEMM_TC"); return e != nullptr ? (e[0] == '1' ? 1 : 0) : 1; }()};
 bool gemm_tc_supported(int M, int N, int K, int lda, int ldw);
 int launch_gemm_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    const TtsGemmEpilogue& epi, cudaStream_t s);

@@ -2,10 +2,11 @@
 // C[M,N] = epi(A[M,K] * W[N,K]^T) with fp32-class accuracy through the 3-term TF32 split
 //     A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T,   hi = the upper 19 bits the tensor core reads, lo = x - hi.
 // One CTA computes a 128 x 128 tile:
-//   warps 0-3  loaders + epilogue: cp.async 16-byte chunks of A and W into the canonical K-major, no-swizzle
-//              core-matrix layout (8 rows x 16 bytes = 128 contiguous bytes per core matrix), compute the `lo`
-//              copy of the chunks they loaded, cross-proxy fence, arrive on the stage's `full` mbarrier;
-//   warp 4     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8): 4 k-steps x 3 terms per stage,
+//   warps 0-7  loaders + epilogue: 16-byte chunks of A and W travel global -> registers (requested one stage ahead)
+//              -> shared memory in the canonical K-major, no-swizzle core-matrix layout (8 rows x 16 bytes = 128
+//              contiguous bytes per core matrix), once as `hi` (rounded to TF32) and once as `lo` = x - hi;
+//              cross-proxy fence, arrive on the stage's `full` mbarrier;
+//   warp 8     one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8): 4 k-steps x 3 terms per stage,
 //              accumulating in tensor memory (128 lanes x 128 fp32 columns); tcgen05.commit frees the stage;
 //   epilogue   tcgen05.ld 32x32b.x8 (thread = one output row, 8 columns at a time), the TtsGemmEpilogue of
 //              tts_b200.h applied in registers, row-wise stores.
@@ -19,12 +20,16 @@ namespace tts {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32, kStages = 3;
-constexpr int kLoaders = 128;                  // warps 0-3
+constexpr int kLoaders = 256;                  // warps 0-7
 constexpr int kThreads = kLoaders + 32;        // + MMA warp
 constexpr int kTileBytes = BM * BK * 4;        // 16 KB: one operand tile (hi or lo) of one stage
 constexpr int kStageBytes = 4 * kTileBytes;    // A_hi, A_lo, W_hi, W_lo
 constexpr int kKBlockBytes = BM * 16;          // 2048: all rows of one 16-byte k-block (LBO)
-constexpr int kTmemCols = 128;
+constexpr int kAcc = 4;                        // accumulators in tensor memory, k-blocks dealt round-robin: the tensor
+                                               // core adds into fp32 with truncation, so the error grows linearly with
+                                               // the number of accumulations (measured 1.1e-4 at K = 2560 with one
+                                               // accumulator); four partial sums added in registers (RN) cut it 4x
+constexpr int kTmemCols = kAcc * BN;           // 512 = all of tensor memory (one CTA per SM)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
     sh->err = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {   // the MMA warp owns the tensor-memory allocation
+  if (warp == kLoaders / 32) {   // the MMA warp owns the tensor-memory allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -105,67 +110,62 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = sh->tmem_base;
 
-  if (warp < 4) {
-    // ================= loaders: 8 chunks of A and 8 of W per thread and stage =================
-    // chunk id = i * 128 + tid -> row = id / 8, k-block = id % 8 (8 threads read 128 contiguous bytes of a row)
-    auto issue = [&](int kb) {
-      const int s = kb % kStages;
-      uint8_t* st = smem + s * kStageBytes;
+  if (warp < kLoaders / 32) {
+    // ================= loaders: 4 chunks of A and 4 of W per thread and stage =================
+    // chunk c = i * 256 + tid -> k-block = 2 * (c >> 8) + (c & 1), row = (c >> 1) & 127: two neighbouring threads
+    // read one 32-byte sector of a row, and their shared-memory stores conflict at most 2-way
+    float4 ra[4], rw[4];
+    auto load = [&](int kb) {
       const int k0 = kb * BK;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = i * kLoaders + tid, row = id >> 3, kq = id & 7;
-        const uint32_t off = (uint32_t)kq * kKBlockBytes + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * kLoaders + tid, kq = 2 * (c >> 8) + (c & 1), row = (c >> 1) & 127;
         const int gm = m0 + row, gn = n0 + row;
-        const float* pa = A + (size_t)(gm < M ? gm : 0) * lda + k0 + kq * 4;
-        const float* pw = W + (size_t)(gn < N ? gn : 0) * ldw + k0 + kq * 4;
-        const unsigned sa = gm < M ? 16u : 0u, sw = gn < N ? 16u : 0u;   // src-size 0 = zero fill
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(st + off)), "l"(pa), "r"(sa) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(st + 2 * kTileBytes + off)), "l"(pw), "r"(sw) : "memory");
+        ra[i] = gm < M ? __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + kq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rw[i] = gn < N ? __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + kq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto convert = [&](int kb) {   // lo = x - trunc_tf32(x) for the chunks this thread loaded
-      const int s = kb % kStages;
+    auto split = [](float x, float& hi, float& lo) {   // hi: round to nearest TF32 (low 13 bits zero), lo exact
+      hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+      lo = x - hi;
+    };
+    auto store = [&](int s, const float4 (&va)[4], const float4 (&vw)[4]) {
       uint8_t* st = smem + s * kStageBytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = i * kLoaders + tid, row = id >> 3, kq = id & 7;
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * kLoaders + tid, kq = 2 * (c >> 8) + (c & 1), row = (c >> 1) & 127;
         const uint32_t off = (uint32_t)kq * kKBlockBytes + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-#pragma unroll
-        for (int op = 0; op < 2; ++op) {
-          const float4 v = *reinterpret_cast<const float4*>(st + op * 2 * kTileBytes + off);
-          float4 l;
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          *reinterpret_cast<float4*>(st + op * 2 * kTileBytes + kTileBytes + off) = l;
-        }
+        float4 h, l;
+        split(va[i].x, h.x, l.x); split(va[i].y, h.y, l.y); split(va[i].z, h.z, l.z); split(va[i].w, h.w, l.w);
+        *reinterpret_cast<float4*>(st + off) = h;
+        *reinterpret_cast<float4*>(st + kTileBytes + off) = l;
+        split(vw[i].x, h.x, l.x); split(vw[i].y, h.y, l.y); split(vw[i].z, h.z, l.z); split(vw[i].w, h.w, l.w);
+        *reinterpret_cast<float4*>(st + 2 * kTileBytes + off) = h;
+        *reinterpret_cast<float4*>(st + 3 * kTileBytes + off) = l;
       }
     };
     bool ok = true;
-    const int pre = n_kb < kStages - 1 ? n_kb : kStages - 1;
-    for (int kb = 0; kb < pre; ++kb) issue(kb);
+    load(0);
     for (int kb = 0; kb < n_kb && ok; ++kb) {
-      const int nx = kb + kStages - 1;
-      if (nx < n_kb) {
-        if (nx >= kStages) ok = mbar_wait(&sh->empty[nx % kStages], ((nx / kStages) - 1) & 1u);
-        issue(nx);
-      } else {
-        asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
+      float4 ca[4], cw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ca[i] = ra[i];
+        cw[i] = rw[i];
       }
-      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
-      convert(kb);
+      if (kb + 1 < n_kb) load(kb + 1);   // in flight while this stage is converted and stored
+      const int s = kb % kStages;
+      if (kb >= kStages) ok = mbar_wait(&sh->empty[s], ((kb / kStages) - 1) & 1u);
+      store(s, ca, cw);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor-core reads
-      mbar_arrive(&sh->full[kb % kStages]);
+      mbar_arrive(&sh->full[s]);
     }
     if (!ok) atomicExch(&sh->err, 1);
 
     // ================= epilogue: thread = output row, 8 columns per tensor-memory load =================
     ok = mbar_wait(&sh->accum, 0u) && ok;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = warp * 32 + lane, m = m0 + row;
+    const int row = (warp & 3) * 32 + lane, m = m0 + row;   // a warp reads the TMEM lanes 32 * (warp % 4) ...
     const int rpb = epi.rows_per_batch > 0 ? epi.rows_per_batch : M;
     const int valid = epi.valid_rows > 0 ? epi.valid_rows : rpb;
     const int orpb = epi.out_rows_per_batch > 0 ? epi.out_rows_per_batch : rpb;
@@ -173,19 +173,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
     const bool store_row = ok && m < M && r < valid;
     const bool dead = store_row && epi.row_len != nullptr && r >= epi.row_len[b];
     const size_t orow = (size_t)b * orpb + r + epi.out_row_offset;
-    for (int c0 = 0; c0 < BN; c0 += 8) {
-      uint32_t v[8];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                   : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 8) {   // ... and half of the columns
+      float v[8];
+      const int n_acc = n_kb < kAcc ? n_kb : kAcc;   // accumulators that were written
+#pragma unroll
+      for (int a = 0; a < kAcc; ++a) {
+        if (a < n_acc) {   // uniform
+          uint32_t u[8];
+          const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * BN + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                       : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = a == 0 ? __uint_as_float(u[j]) : v[j] + __uint_as_float(u[j]);
+        }
+      }
       if (!store_row) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int n = n0 + c0 + j;
         if (n >= N) continue;
-        float x = __uint_as_float(v[j]) * epi.alpha;
+        float x = v[j] * epi.alpha;
         if (epi.scale) x = x * epi.scale[n] + epi.shift[n];
         if (epi.bias) x += epi.bias[n];
         if (epi.act == 1) x = fmaxf(x, 0.f);
@@ -216,9 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint32_t ko = (uint32_t)ks * 2u * kKBlockBytes;   // two 16-byte k-blocks per K=8 instruction
-          umma_tf32(tmem_d, make_desc(a_lo + ko), make_desc(w_hi + ko), (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_d, make_desc(a_hi + ko), make_desc(w_lo + ko), 1u);
-          umma_tf32(tmem_d, make_desc(a_hi + ko), make_desc(w_hi + ko), 1u);
+          const uint32_t acc = tmem_d + (uint32_t)((kb % kAcc) * BN);
+          umma_tf32(acc, make_desc(a_lo + ko), make_desc(w_hi + ko), (kb >= kAcc || ks > 0) ? 1u : 0u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(w_lo + ko), 1u);
+          umma_tf32(acc, make_desc(a_hi + ko), make_desc(w_hi + ko), 1u);
         }
         umma_commit(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it
       }
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4)
+  if (warp == kLoaders / 32)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)kTmemCols) : "memory");
 }
 
