@@ -377,6 +377,47 @@ def run_ours(args):
     return 0
 
 
+def run_forward(args):
+    """Secondary workload (not the headline): the teacher-forced FORWARD pass of BASELINE.json configs[2]
+    (batch 64 x 1000 mel frames, 256-byte text) through TtsEngine.forward.  The backward pass and the NCCL gradient
+    all-reduce of the training step are not built, so this is NOT the train-step metric."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    from tts_b200 import synthetic as O
+    from tts_b200 import _native
+    from tts_b200.engine import TtsEngine
+    cfg = O.ModelConfig()
+    eng = TtsEngine.from_state_dict(O.synth_params(cfg, seed=0), cfg, dev)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v)
+             for k, v in O.synth_batch(cfg, batch=args.tf_batch, text_len=args.text_len, n_frames=args.frames, seed=1).items()}
+    lib = _native.load()
+    for _ in range(max(args.warmup, 3)):
+        eng.forward(batch, want_align=False)
+    torch.cuda.synchronize(dev)
+    lib.tts_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = eng.forward(batch, want_align=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / args.steps
+    # forward FLOPs per SURVEY.md §8d (dense contractions + attention + postnet), 2 flops per MAC
+    S, T, B = args.text_len, args.frames, args.tf_batch
+    flops = B * (S * (37.75e6 + 4 * S * 512 * 6 + 14.16e6) + T * (99.09e6 + 4 * T * 768 * 6 * 0.5 + 4 * S * 768 * 6 + 0.565e6
+                                                                 + 0.124e6 + 8.68e6))
+    print(json.dumps({"metric": "teacher-forced FORWARD ms (forward only: backward / all-reduce not built)", "value": ms,
+                      "unit": "ms", "n_gpus": 1, "steps": args.steps, "higher_is_better": False, "dtype": "f32 (3xTF32 tcgen05 GEMMs)",
+                      "data": "synthetic", "config": {"workload": "teacher-forced forward, batch=%d x %d mel frames, %d text tokens"
+                                                       % (B, T, S)},
+                      "gpu_launches": int(lib.tts_launch_count()) // args.steps,
+                      "achieved_tflops_fp32_equivalent": flops / ms / 1e9,
+                      "mel_bef_abs_mean": float(out["mel_bef"].abs().mean())}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,7 +432,12 @@ def main():
                     help="0 default (= 4), 1 per-phase kernels, 2 CUDA graph, 3 fused FFMA2 kernel, 4 pipelined kernel")
     ap.add_argument("--ref-horizon", type=int, default=96, help="frames of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="decode", choices=["decode", "forward"],
+                    help="decode = the headline (default); forward = teacher-forced forward pass only (secondary)")
+    ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")
     args = ap.parse_args()
+    if args.workload == "forward":
+        return run_forward(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
