@@ -313,6 +313,31 @@ def test_decode_properties_at_baseline_shape(full_params, ops):
     assert _err(a["mel_pre"][:, :6], want["mel_pre"][:, :6]) < 2e-4
 
 
+@pytest.mark.parametrize("rows", [8, 11])
+def test_pipelined_group_size_override(full_params, ops, rows):
+    """TTS_GROUP_ROWS splits the batch differently (4 groups of 8 with split K/V streams and combine phases; 3 ragged
+    groups of 11/11/10): same frames as the fused kernel."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=32, text_len=70, n_frames=4, seed=8, ragged=True)
+    mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
+    ref = eng.generate(batch, max_frames=20, record_align="encdec", memory=mem, chunk=20, impl=3)
+    old = os.environ.get("TTS_GROUP_ROWS")
+    os.environ["TTS_GROUP_ROWS"] = str(rows)
+    try:
+        got = eng.generate(batch, max_frames=20, record_align="encdec", memory=mem, chunk=20, impl=4)
+    finally:
+        if old is None:
+            del os.environ["TTS_GROUP_ROWS"]
+        else:
+            os.environ["TTS_GROUP_ROWS"] = old
+    assert _err(got["mel_pre"], ref["mel_pre"]) < 2e-4
+    assert _err(got["alignments"]["encdec"][5], ref["alignments"]["encdec"][5]) < 1e-5
+
+
 def test_tcgen05_gemm_vs_float64(ops):
     """csrc/gemm_tc.cu (tcgen05.mma kind::tf32, 3-term split, TMEM accumulator) against a float64 product, with every
     epilogue feature the dense path uses and ragged M / N tails; the FFMA2 kernel on the same inputs as a second check."""
