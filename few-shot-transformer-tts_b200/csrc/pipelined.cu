@@ -817,6 +817,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
     const int b = item / H;
     const int klen = at.key_len ? sm.klen[b] : n_keys;
     float* arow = at.align ? at.align + (size_t)item * at.align_bh_stride + (size_t)t * at.align_row_len : nullptr;
+    if (prof) prof[12] = clock64();
 
     f32x4 qv[F4];
     {
@@ -828,6 +829,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
         qsrc = sm.qbuf + (cs.q_uses & 1u) * 96;
         ++cs.q_uses;
       }
+      if (prof) prof[13] = clock64();
 #pragma unroll
       for (int i = 0; i < F4; ++i) {
         qv[i] = pre ? ld4s(qsrc + 4 * (l8 + 8 * i)) : ld4cg(qsrc + 4 * (l8 + 8 * i));
@@ -1242,6 +1244,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
           } else {
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.x_empty);
+            if (prof && g == 0) prof[11] = clock64();
             if (d.kind == kAttn) attn_group<DH>(a, d, sm, cs, g, t, g == 0 ? prof : nullptr);
             else if (d.kind == kReduce) reduce_group(a, d, g);
             else combine_group<DH>(a, d, sm, g, t);

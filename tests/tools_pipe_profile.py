@@ -59,3 +59,5 @@ for target in steps:
         n = len(v)
         f = lambda i, j: sum(d[i] - d[j] for d in v) / n
         print("   %-7s %6.2f %6.2f %6.2f %6.2f %6.2f %6.2f" % (k, f(6, 1), f(7, 6), f(8, 7), f(9, 8), f(10, 9), f(2, 10)))
+        print("   %-7s setup detail: x_empty arrive %5.2f | unit setup %5.2f | q wait %5.2f | q load+scale %5.2f" % (
+            k, f(11, 1), f(12, 11), f(13, 12), f(6, 13)))
