@@ -1,15 +1,17 @@
 // Pipelined persistent decode kernel (impl 4, the default): ONE cooperative launch runs `n_steps` whole decode
 // steps with one CTA per SM, like megakernel.cu, but the step is software-pipelined over ROW GROUPS of the batch
 // so that the latency of the grid-wide dependency between phases (barrier + activation broadcast, ~2 us measured,
-// profiles/r2_microbench.txt) hides behind the work of the other group(s):
+// profiles/r1_microbench.txt) hides behind the work of the other group(s):
 //
 //   * the batch is cut into groups of <= 16 rows (one m16 MMA tile).  Every (phase, group) pair has its own
 //     grid-barrier counter: group g of phase p only waits for group g of phase p-1, so while the last CTAs
 //     finish (p, g) everybody else already works on (p, g+1) or (p+1, g-1).
-//   * warp specialisation: 8 consumer warps compute; a 9th producer warp polls the barrier counters, stages the
-//     next activation tile with 1-D TMA bulk copies (one mbarrier, one slot: the consumers pull the tile into
-//     registers and release the slot at once) and streams the NEXT phase's weight slice into the half of the
-//     weight region the current phase does not use.
+//   * warp specialisation (11 warps): 8 consumer warps compute; a LOADER warp polls the barrier counters, stages the
+//     next activation tile with a 1-D TMA bulk copy (one mbarrier, one slot: the consumers pull the tile into
+//     registers with ldmatrix and release the slot at once) and streams the NEXT phase's packed weight slice into the
+//     half of the weight region the current phase does not use; a SIGNALER warp publishes finished group-phases
+//     with the gpu-scope release (a memory barrier) off the consumers' path; a FEEDER warp (one lane per ring slot)
+//     keeps the K/V ring of the attention phases full.
 //   * products run on the legacy tensor-core path: mma.sync m16n8k8 TF32 with the 3-term split
 //     (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate) which keeps fp32-class accuracy (parity 1e-3 on mel
 //     frames needs it; a single TF32 pass does not).  tcgen05 needs M >= 64 per CTA; a CTA owns 5-21 weight
@@ -18,7 +20,11 @@
 //     statistics are computed by the consumers from the fragments they already hold (no pass over the tile).
 //   * FFN-out (K = 3072) is split 4-way along K across CTAs (each CTA then stages the same 16 x 768 tile shape as
 //     every other phase instead of 16 x 3072) and a short reduce phase adds the four partials to the residual.
-//   * attention phases are megakernel.cu's per-warp TMA rings over the K/V streams (online softmax), per group.
+//   * attention phases: one (sample, head) stream per CTA and group through a CTA-wide ring of 20 x 6 KB tiles
+//     (120 KB in flight per SM, partly filled while the preceding GEMM still runs), online softmax in the log2
+//     domain, static tile-to-warp assignment (bit-reproducible).
+// Measured (profiles/r1_*): 419 us per decode step at B=32, S=258 averaged over 1000 frames = 0.40 of the HBM
+// roofline; DESIGN.md section 4.1 has the breakdown and what was tried.
 //
 // Reference semantics: transformer/tacotron.py:107-116, transformer/modules.py:108-145,
 // transformer/attention.py:53-122, synthesize.py:35-45.
