@@ -422,7 +422,8 @@ __device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Sm
     case kFinal: {  // modules.py:144, tacotron.py:112-115
       const bool on = t < sm.len[b];
       if (n < a.w.n_mels) a.st.frames[((size_t)b * a.st.t_max + t) * a.w.n_mels + n] = on ? v : 0.f;
-      else a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
+      else if (n == a.w.n_mels) a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
+      else a.p0[(size_t)b * (a.w.prenet_hidden + kXPad) + (n - a.w.n_mels - 1)] = fmaxf(v, 0.f);
     } break;
   }
 }
@@ -1049,7 +1050,11 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
     return;
   }
   if (ph == 3 + ppl * L) {  // final LN + mel / stop projections
-    d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = M + 1; d.W = a.w.pk_final;
+    // ... and, fused into the same rows, the first prenet layer of the NEXT step: relu(W0 mel + b0) with
+    // mel = W_mel LN(x) is relu((W0 W_mel_ln) xhat + W0 c_mel + b0), so rows M+1.. of pk_final give p0 directly and
+    // steps t > 0 skip the prenet's first phase (a dead row's p0 differs from the reference's relu(b0), but its
+    // prenet output is masked in the third prenet phase either way: modules.py:114-116)
+    d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = M + 1 + P; d.W = a.w.pk_final;
     d.mode = kFinal; d.hi = 0;
     return;
   }
@@ -1158,13 +1163,15 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
 
   for (int s = 0; s < a.n_steps; ++s) {
     const int t = t0 + s;
+    const int off = t > 0 ? 1 : 0;          // steps t > 0 skip table phase 0 (fused into the previous final phase)
+    const int n_ph_s = n_ph - off;          // phases of this step; `ph` below counts them, table index = ph + off
     if (warp == kCWarps) {
       // =========================== producer warp (one elected lane) ===========================
       if (lane == 0) {
         fence_proxy_async();  // frames / activations written by other CTAs in the previous step are read by TMA
-        get_phase<DH>(a, 0, t, qscale, sm.desc[0]);
+        get_phase<DH>(a, off, t, qscale, sm.desc[0]);
         if (sm.desc[0].kind == kGemm) issue_weights(sm, sm.desc[0]);
-        for (int ph = 0; ph < n_ph; ++ph) {
+        for (int ph = 0; ph < n_ph_s; ++ph) {
           const Desc& d = sm.desc[ph % kDescRing];
           for (int g = 0; g < NG; ++g) {
             if (ph > 0) {
@@ -1176,9 +1183,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             mbar_wait(sm.x_empty, (p_gp & 1u) ^ 1u, a.err);
             stage_tile(a, sm, d, g);
             ++p_gp;
-            if (g == 0 && ph + 1 < n_ph) {
+            if (g == 0 && ph + 1 < n_ph_s) {
               Desc& dn = sm.desc[(ph + 1) % kDescRing];
-              get_phase<DH>(a, ph + 1, t, qscale, dn);
+              get_phase<DH>(a, ph + 1 + off, t, qscale, dn);
               if (ph >= 1) wait_count(a, sm.pdone, epoch + ph);   // the consumers are done with phase ph-1: its weight
                                                                   // half (and the K/V rings) may be overwritten
               if (dn.kind == kGemm) issue_weights(sm, dn);
@@ -1190,9 +1197,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
     } else if (warp == kCWarps + 2) {
       // =========================== K/V feeder warp (one lane per ring slot) ===========================
       fence_proxy_async();   // K/V rows appended in earlier steps (observed through the step-end barrier) are read by TMA
-      for (int ph = 0; ph < n_ph; ++ph) {
+      for (int ph = 0; ph < n_ph_s; ++ph) {
         int l;
-        const int id = phase_id(a, ph, l);
+        const int id = phase_id(a, ph + off, l);
         if (id != 1 && id != 5) continue;
         const size_t BH = (size_t)B * a.w.n_heads;
         const size_t off = id == 1 ? (size_t)l * BH * T * DH : (size_t)l * BH * a.st.mem_len * DH;
@@ -1213,14 +1220,14 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
       // publishes the consumers' finished group-phases to the other CTAs: the gpu-scope release (a memory barrier
       // that waits for the CTA's outstanding stores) runs here, off the consumers' critical path
       if (lane == 0) {
-        for (int ph = 0; ph < n_ph; ++ph)
+        for (int ph = 0; ph < n_ph_s; ++ph)
           for (int g = 0; g < NG; ++g) {
             ++s_gp;
             wait_count(a, sm.sig, s_gp);
             grid_arrive(a, g);
             if (g == 0 && a.prefetch) {   // L2 prefetch of the K/V streams of the attention phase two GEMMs ahead
               int l;
-              const int id = phase_id(a, ph, l);
+              const int id = phase_id(a, ph + off, l);
               const size_t BH = (size_t)B * a.w.n_heads;
               if (id == 3) {
                 const size_t off = (size_t)l * BH * a.st.mem_len * DH;
@@ -1237,8 +1244,8 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
       __syncwarp();
     } else {
       // =========================== consumer warps ===========================
-      for (int ph = 0; ph < n_ph; ++ph) {
-        long long* prof = (blockIdx.x == 0 && tid == 0 && ph < kProfPhases) ? a.prof + kProfStride * ph : nullptr;
+      for (int ph = 0; ph < n_ph_s; ++ph) {
+        long long* prof = (blockIdx.x == 0 && tid == 0 && ph + off < kProfPhases) ? a.prof + kProfStride * (ph + off) : nullptr;
         for (int g = 0; g < NG; ++g) {
           if (prof && g < 2) prof[3 * g] = clock64();
           mbar_wait(sm.x_full, cs.gp & 1u, a.err);
@@ -1264,9 +1271,9 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(sm.pdone)), "r"(epoch + ph + 1u) : "memory");
       }
       if (tid == 0)
-        for (int g = 0; g < NG; ++g) grid_wait(a, g, (epoch + n_ph) * G);   // the step is complete everywhere
+        for (int g = 0; g < NG; ++g) grid_wait(a, g, (epoch + n_ph_s) * G);   // the step is complete everywhere
     }
-    epoch += n_ph;
+    epoch += n_ph_s;
     __syncthreads();
     // synthesize.py:42-45, replicated identically in every CTA
     if (a.update_state) {
@@ -1425,7 +1432,7 @@ bool pipelined_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) {
   worst = worst > rows(F, G) ? worst : rows(F, G);
   worst = worst > rows(D, G / ks) ? worst : rows(D, G / ks);
   worst = worst > rows(P, G) ? worst : rows(P, G);
-  worst = worst > rows(M + 1, G) ? worst : rows(M + 1, G);
+  worst = worst > rows(M + 1 + P, G) ? worst : rows(M + 1 + P, G);
   if (worst > kMaxRows) return false;
   if (ring_slots(w, G, nullptr, nullptr) < 2) return false;
   if (smem_bytes(st->batch) > 227 * 1024) return false;

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
 TTS_MAX_LAYERS = 16
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)

@@ -246,7 +246,15 @@ class TtsEngine:
         sout = torch.cat([sm_, ss_]).contiguous()
         keep.extend([cout, sout])
         dw.w_mel_ln, dw.w_stop_ln, dw.c_out_ln = wm.data_ptr(), ws.data_ptr(), cout.data_ptr()
-        dw.pk_final = pack(torch.cat([wm, ws], 0), cout, sout)
+        # rows M+1.. of pk_final: the first prenet layer applied to the frame being emitted, folded through mel_net
+        # (pipelined.cu: the final phase then produces p0 of the NEXT step and steps t > 0 skip that prenet phase)
+        with torch.no_grad():
+            w0, b0 = w["decoder.prenet.dense0.weight"].detach(), w["decoder.prenet.dense0.bias"].detach()
+            wf = ops.linear(w0.contiguous(), wm.t().contiguous())                   # [P, D] = W0 @ W_mel_ln
+            cf = ops.linear(cm[None, :].contiguous(), w0.contiguous()).view(-1) + b0  # W0 c_mel + b0
+            sf = wf.double().sum(dim=1).float()
+        keep.extend([wf, cf, sf])
+        dw.pk_final = pack(torch.cat([wm, ws, wf], 0), torch.cat([cout, cf]), torch.cat([sout, sf]))
         dw.pk_pre0 = pack(w["decoder.prenet.dense0.weight"], w["decoder.prenet.dense0.bias"])
         dw.pk_pre1 = pack(w["decoder.prenet.dense1.weight"], w["decoder.prenet.dense1.bias"])
         dw.pk_pre2 = pack(w["decoder.prenet.dense_final.weight"])

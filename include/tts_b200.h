@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 7
+#define TTS_ABI_VERSION 8
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -180,7 +180,8 @@ typedef struct TtsDecoderWeights {
   const float* pk_pre0;     /* [P][M+16]   packed like TtsDecLayerWeights.pk_* */
   const float* pk_pre1;     /* [P][P+16] */
   const float* pk_pre2;     /* [D][P+16] */
-  const float* pk_final;    /* [M+1][D+16]  w_mel_ln rows, then w_stop_ln; constant = c_out_ln */
+  const float* pk_final;    /* [M+1+P][D+16]  w_mel_ln rows, w_stop_ln (constant = c_out_ln), then prenet_w0 * w_mel_ln
+                             * (constant = prenet_w0 * c_mel + prenet_b0): the next step's first prenet layer */
   int32_t pk_ksplit;        /* K split of pk_ffn_out: ceil(4D / 768) */
   int32_t pk_reserved;
   TtsDecLayerWeights layer[TTS_MAX_LAYERS];
