@@ -23,7 +23,7 @@
 //   * attention phases: one (sample, head) stream per CTA and group through a CTA-wide ring of 20 x 6 KB tiles
 //     (120 KB in flight per SM, partly filled while the preceding GEMM still runs), online softmax in the log2
 //     domain, static tile-to-warp assignment (bit-reproducible).
-// Measured (profiles/r1_*): 419 us per decode step at B=32, S=258 averaged over 1000 frames = 0.40 of the HBM
+// Measured (profiles/r1_*): 414 us per decode step at B=32, S=258 averaged over 1000 frames = 0.40 of the HBM
 // roofline; DESIGN.md section 4.1 has the breakdown and what was tried.
 //
 // Reference semantics: transformer/tacotron.py:107-116, transformer/modules.py:108-145,
