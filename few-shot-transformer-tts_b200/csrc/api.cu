@@ -27,12 +27,6 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int enqueue_step_phases(const TtsDecoderWeights* w, const TtsDecodeState* st, int update_state, cudaStream_t s);
 int decode_reset(const TtsDecodeState* st, cudaStream_t s);
 size_t decode_scratch_floats(const TtsDecoderWeights* w, int B);
-// megakernel.cu
-int launch_fused_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
-                       cudaStream_t s);
-size_t fused_scratch_floats(const TtsDecoderWeights* w, int B);
-bool fused_supported(const TtsDecoderWeights* w, const TtsDecodeState* st);
-int fused_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries);
 // pipelined.cu
 int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
                            cudaStream_t s);
@@ -134,10 +128,8 @@ extern "C" size_t tts_decode_scratch_bytes(const TtsDecoderWeights* w, int32_t b
   (void)mem_len;
   (void)t_max;
   if (!w || batch <= 0) return 0;
-  const size_t a = decode_scratch_floats(w, batch), b = fused_scratch_floats(w, batch),
-               c = pipelined_scratch_floats(w, batch);
-  const size_t m = a > b ? (a > c ? a : c) : (b > c ? b : c);
-  return m * sizeof(float) + 256;
+  const size_t a = decode_scratch_floats(w, batch), c = pipelined_scratch_floats(w, batch);
+  return (a > c ? a : c) * sizeof(float) + 256;
 }
 
 extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void* stream) {
@@ -165,8 +157,8 @@ extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState
 extern "C" int tts_decode_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, int64_t* out_host,
                                   int32_t max_entries) {
   TTS_REQUIRE(w && st && out_host && max_entries > 0, "decode_profile: bad arguments");
-  if (g_last_impl == 4) return pipelined_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
-  return fused_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
+  TTS_REQUIRE(g_last_impl == 4, "decode_profile: only the pipelined kernel (impl 4) records phase stamps");
+  return pipelined_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
 }
 
 extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32_t n_steps,
@@ -175,13 +167,19 @@ extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState
   int rc = check_decode_args(w, st);
   if (rc) return rc;
   TTS_REQUIRE(n_steps >= 0, "decode_steps: n_steps=%d", n_steps);
-  TTS_REQUIRE(prev_mel == nullptr, "decode_steps: external prev_mel is not supported; copy the frame into st->frames");
-  (void)prev_mel_stride;
+  if (prev_mel != nullptr) {   // frame t-1 supplied by the caller: place it where every implementation reads it from
+    int t_host = 0;
+    TTS_CHECK_CUDA(cudaMemcpyAsync(&t_host, st->step_counter, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    TTS_CHECK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (t_host > 0 && t_host <= st->t_max)
+      TTS_CHECK_CUDA(cudaMemcpy2DAsync(st->frames + (size_t)(t_host - 1) * w->n_mels, (size_t)st->t_max * w->n_mels * sizeof(float),
+                                       prev_mel, (size_t)prev_mel_stride * sizeof(float), (size_t)w->n_mels * sizeof(float),
+                                       (size_t)st->batch, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 0) impl = pipelined_supported(w, st) ? 4 : (fused_supported(w, st) ? 3 : 2);
+  if (impl == 0) impl = pipelined_supported(w, st) ? 4 : 2;
   g_last_impl = impl;
   if (impl == 4) return launch_pipelined_steps(w, st, n_steps, update_state, s);
-  if (impl == 3) return launch_fused_steps(w, st, n_steps, update_state, s);
   if (impl == 1) {
     for (int i = 0; i < n_steps; ++i)
       if ((rc = enqueue_step_phases(w, st, update_state, s))) return rc;

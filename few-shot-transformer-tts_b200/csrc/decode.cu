@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(SkinnyArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, s4 = (lane & 3) * 4;       // rows 4g..4g+3, floats s4..s4+3 of a 16-chunk
   const int t = *a.step;
+  if (t >= a.t_max) return;   // past the session's capacity: advance_kernel reports it, nothing is written
   const int b0 = blockIdx.y * kRowsPerBlock;
   const int n0 = blockIdx.x * a.w_rows;
   const int nrows = min(a.w_rows, a.N - n0);
@@ -193,6 +194,7 @@ struct DecAttnArgs {
   float* part_o; float* part_m; float* part_l;           // [B][H][n_split][dh|1|1]
   float* align; long long align_bh_stride; int align_row_len;  // row for this step: align + bh*stride + t*row_len
   const int32_t* step;
+  int t_max;
 };
 
 template <int DH>
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(DecAttnArgs a) {
   const int split = blockIdx.x % a.n_split, bh = blockIdx.x / a.n_split;
   const int b = bh / a.H;
   const int t = *a.step;
+  if (t >= a.t_max) return;
   const int n_keys = a.n_keys_fixed > 0 ? a.n_keys_fixed : t + 1;
   const int klen = a.key_len ? a.key_len[b] : n_keys;
   const int per = ceil_div(n_keys, a.n_split);
@@ -342,6 +345,7 @@ template <int DH>
 __global__ void __launch_bounds__(128) decode_attn_combine_kernel(DecAttnArgs a) {
   const int bh = blockIdx.x, tid = threadIdx.x;
   const int t = *a.step;
+  if (t >= a.t_max) return;
   const int n_keys = a.n_keys_fixed > 0 ? a.n_keys_fixed : t + 1;
   float m = -CUDART_INF_F;
   for (int s = 0; s < a.n_split; ++s) m = fmaxf(m, a.part_m[(size_t)bh * a.n_split + s]);
@@ -372,6 +376,10 @@ __global__ void advance_kernel(const float* __restrict__ stop_logits, int32_t* l
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   const int t = *step;
+  if (t >= t_max) {   // a caller stepped past t_max: no buffer was touched; report instead of corrupting memory
+    if (threadIdx.x == 0) *n_unfinished = -2;
+    return;
+  }
   int mine = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     bool fin = finished[b] != 0;
@@ -515,7 +523,7 @@ int enqueue_step_phases(const TtsDecoderWeights* w, const TtsDecodeState* st, in
     memset(&at, 0, sizeof(at));
     at.q = sc.q; at.B = B; at.H = H; at.n_split = ns; at.kc = st->self_k + self_off; at.vc = st->self_v + self_off;
     at.rows_alloc = T; at.n_keys_fixed = 0; at.key_len = nullptr; at.out = sc.ctx;
-    at.part_o = sc.part_o; at.part_m = sc.part_m; at.part_l = sc.part_l; at.step = st->step_counter;
+    at.part_o = sc.part_o; at.part_m = sc.part_m; at.part_l = sc.part_l; at.step = st->step_counter; at.t_max = T;
     if (st->align_self) {
       at.align = st->align_self + (size_t)l * B * H * T * T; at.align_bh_stride = (long long)T * T; at.align_row_len = T;
     }
@@ -534,7 +542,7 @@ int enqueue_step_phases(const TtsDecoderWeights* w, const TtsDecodeState* st, in
     memset(&at, 0, sizeof(at));
     at.q = sc.q; at.B = B; at.H = H; at.n_split = ns; at.kc = st->cross_k + cross_off; at.vc = st->cross_v + cross_off;
     at.rows_alloc = S; at.n_keys_fixed = S; at.key_len = st->input_lengths; at.out = sc.ctx;
-    at.part_o = sc.part_o; at.part_m = sc.part_m; at.part_l = sc.part_l; at.step = st->step_counter;
+    at.part_o = sc.part_o; at.part_m = sc.part_m; at.part_l = sc.part_l; at.step = st->step_counter; at.t_max = T;
     if (st->align_cross) {
       at.align = st->align_cross + (size_t)l * B * H * T * S; at.align_bh_stride = (long long)T * S; at.align_row_len = S;
     }

@@ -14,6 +14,8 @@
 // K % 32 == 0 (every Linear / Conv-as-GEMM of the encoder, the cross-K/V precompute and the Postnet except the
 // 80-channel input layers).  Reference call sites: transformer/attention.py:43-47,63-68,119; modules.py:11-19;
 // tacotron.py:78,85.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace tts {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
     const int valid = epi.valid_rows > 0 ? epi.valid_rows : rpb;
     const int orpb = epi.out_rows_per_batch > 0 ? epi.out_rows_per_batch : rpb;
     const int b = m / rpb, r = m - b * rpb;
-    const bool store_row = ok && m < M && r < valid;
+    const bool store_row = m < M && r < valid;   // on a barrier timeout (!ok) the tile is stored as NaN: loud, never stale
     const bool dead = store_row && epi.row_len != nullptr && r >= epi.row_len[b];
     const size_t orow = (size_t)b * orpb + r + epi.out_row_offset;
     for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 8) {   // ... and half of the columns
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const float* __res
         else if (epi.act == 2) x = tanhf(x);
         if (epi.residual) x += epi.residual[orow * epi.ldr + n];
         if (dead) x = 0.f;
+        if (!ok) x = __int_as_float(0x7fc00000);
         if (epi.head_dim > 0) {
           const int dm = epi.n_heads * epi.head_dim;
           const int w = n / dm, hn = n - w * dm, h = hn / epi.head_dim, d = hn - h * epi.head_dim;
@@ -251,10 +254,13 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldw) {
 
 int launch_gemm_tc(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                    const TtsGemmEpilogue& epi, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0ull};   // bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::smem_bytes()));
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   dim3 grid(ceil_div(N, tc::BN), ceil_div(M, tc::BM));
   tc::gemm_tc_kernel<<<grid, tc::kThreads, tc::smem_bytes(), s>>>(A, lda, W, ldw, C, ldc, M, N, K, epi);

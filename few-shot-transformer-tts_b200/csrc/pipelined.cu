@@ -32,6 +32,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace tts {
@@ -1154,6 +1156,13 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   }
   __syncthreads();
   const int t0 = *a.st.step_counter;
+  // never step past the session's capacity (K/V rows, frames and the PE table end at t_max): run what fits and
+  // report -2 through n_unfinished instead of writing out of bounds
+  const int n_run = min(a.n_steps, T - t0);
+  if (n_run <= 0) {
+    if (blockIdx.x == 0 && tid == 0) *a.st.n_unfinished = -2;
+    return;
+  }
 
   CState cs{0u, 0u, 0u, 0u, 0u};
   unsigned p_gp = 0u, p_go = 0u;        // loader: group-phases staged, attention group-phases released to the feeder
@@ -1161,9 +1170,13 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
   unsigned s_gp = 0u;                   // signaler: group-phases published
   unsigned epoch = 0u;                  // phases completed per group since the kernel started
 
-  for (int s = 0; s < a.n_steps; ++s) {
+  for (int s = 0; s < n_run; ++s) {
     const int t = t0 + s;
-    const int off = t > 0 ? 1 : 0;          // steps t > 0 skip table phase 0 (fused into the previous final phase)
+    // Steps after the first of a launch skip table phase 0 (the previous step's final phase already produced p0 from
+    // the frame it emitted).  The FIRST step of every launch runs it from st->frames[:, t-1]: that is the ABI
+    // contract (a caller may have written, primed or clamped that frame between launches) and it makes the scratch
+    // content irrelevant across launches and implementations.
+    const int off = s > 0 ? 1 : 0;
     const int n_ph_s = n_ph - off;          // phases of this step; `ph` below counts them, table index = ph + off
     if (warp == kCWarps) {
       // =========================== producer warp (one elected lane) ===========================
@@ -1294,10 +1307,11 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
         }
       if (tid == 0) {
         *a.st.step_counter = t + 1;
-        *a.st.n_unfinished = (*reinterpret_cast<volatile int*>(a.err) != 0) ? -1 : unfinished;
+        *a.st.n_unfinished = (*reinterpret_cast<volatile int*>(a.err) != 0) ? -1
+                             : ((s + 1 == n_run && n_run < a.n_steps) ? -2 : unfinished);
       }
     }
-    if ((a.update_state && unfinished == 0) || s + 1 == a.n_steps) break;  // uniform across CTAs
+    if ((a.update_state && unfinished == 0) || s + 1 == n_run) break;  // uniform across CTAs
     if (*reinterpret_cast<volatile int*>(a.err) != 0) break;
   }
 }
@@ -1311,15 +1325,17 @@ struct Carve {
   size_t floats;
 };
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+static int num_sms() {   // per device: a process may drive several GPUs
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 static int ksplit_for(const TtsDecoderWeights* w) { return (w->d_ffn + kKC - 1) / kKC; }
@@ -1382,14 +1398,17 @@ static Carve carve(const TtsDecoderWeights* w, int B, float* base) {
 
 template <int DH>
 static int launch(const Args& a, cudaStream_t s) {
-  static bool configured = false;
+  static std::atomic<unsigned long long> configured{0ull};   // bit per device
   const size_t smem = smem_bytes(a.st.batch);
-  if (!configured) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(pipelined_decode_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int per_sm = 0;
     TTS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipelined_decode_kernel<DH>, kThreads, smem));
     TTS_REQUIRE(per_sm >= 1, "pipelined decode kernel does not fit on an SM");
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   Args args = a;
   void* params[] = {&args};

@@ -100,9 +100,12 @@ class Postnet(nn.Module):
 
 
 class Decoder(nn.Module):
-    #: "all" | "encdec" | "none": which attention maps the cached decode records (the reference
-    #: always returns both; the self maps cost L*B*H*T^2 floats of HBM)
-    record_alignments = "all"
+    #: "all" | "encdec" | "none": which attention maps the cached decode records.  The reference returns both
+    #: lists, but its callers only consume 'encdec' (synthesize.py:90-92) and merely iterate over 'self'
+    #: (synthesize.py:59-61); the self maps cost L*B*H*t_max^2 floats of HBM (7.4 GB at B=32, t_max=1100; 98 GB at
+    #: B=128, T=2000), so the default records 'encdec' only and returns an empty 'self' list.  Set to "all" to get
+    #: the reference's full structure.
+    record_alignments = "encdec"
 
     def __init__(self, hparams):
         super().__init__()

@@ -53,7 +53,7 @@ class DecodeSession:
     """Device state of one autoregressive batch: self/cross K/V caches, frames, lengths.
     Layout and meaning of every buffer: include/tts_b200.h (TtsDecodeState)."""
 
-    def __init__(self, engine, batch, mem_len, t_max, record_align="all"):
+    def __init__(self, engine, batch, mem_len, t_max, record_align="encdec"):
         cfg, dev = engine.cfg, engine.device
         L, D, H, M = cfg.n_decoder_layer, cfg.decoder_hidden, cfg.n_attention_head, cfg.num_mels
         dh = D // H
@@ -101,7 +101,9 @@ class DecodeSession:
         self.t = 0
 
     def step(self, n_steps=1, update_state=True, impl=0):
-        assert self.t + n_steps <= self.t_max, "decode session overflow (t=%d + %d > %d)" % (self.t, n_steps, self.t_max)
+        if self.t + n_steps > self.t_max:   # the kernels also clamp against the DEVICE step counter and report -2
+            raise RuntimeError("tts_b200: decode session overflow (t=%d + %d steps > t_max=%d)"
+                               % (self.t, n_steps, self.t_max))
         N.check(N.load().tts_decode_steps(C.byref(self.engine.decoder_weights()), C.byref(self._st), n_steps, None, 0,
                                           1 if update_state else 0, impl, N.stream_ptr(self.engine.device)),
                 "decode_steps")
@@ -433,7 +435,7 @@ class TtsEngine:
         return {"mel_bef": mel_bef, "mel_aft": mel_aft, "stop_logits": stop, "alignments": align, "memory": mem}
 
     # ---- autoregressive synthesis (synthesize.py:17-72 as one call) ------------------------------
-    def new_session(self, batch, mem_len, t_max, record_align="all"):
+    def new_session(self, batch, mem_len, t_max, record_align="encdec"):
         self.decoder_weights(t_max)  # make sure the PE table covers t_max before pointers are taken
         return DecodeSession(self, batch, mem_len, t_max, record_align)
 
@@ -454,8 +456,10 @@ class TtsEngine:
             sess.step(n, update_state=True, impl=impl)
             done += n
             left = int(sess.counters[1].item())  # one 4-byte D2H per chunk instead of one per frame
+            if left == -2:
+                raise RuntimeError("tts_b200: decode stepped past the session's t_max (device step counter)")
             if left < 0:
-                raise RuntimeError("tts_b200: the fused decode kernel reported a grid-barrier timeout")
+                raise RuntimeError("tts_b200: the decode kernel reported a grid-barrier timeout")
             if left == 0:
                 all_finished = True
                 break

@@ -67,7 +67,7 @@ def sinusoid_table(length: int, channels: int, dtype=torch.float32) -> torch.Ten
 
 def _length_mask(lengths: torch.Tensor, n: int) -> torch.Tensor:
     """[B, n] bool, True where position < length (transformer/common.py:51-70)."""
-    return torch.arange(n)[None, :] < lengths[:, None]
+    return torch.arange(n, device=lengths.device)[None, :] < lengths[:, None]
 
 
 def _ln(x, params: Params, prefix: str):
@@ -131,7 +131,7 @@ def encoder_forward(params: Params, cfg: ModelConfig, inputs, input_lengths,
     mask = _length_mask(input_lengths, S)
     x = x * mask[..., None]                                                    # modules.py:50-51
     bias = ((~mask).to(dtype) * NEG_BIAS)[:, None, None, :]                    # common.py:44-46
-    x = x + sinusoid_table(S, E, dtype) * params["encoder.encoder.pe_scale"].to(dtype)
+    x = x + sinusoid_table(S, E, dtype).to(x.device) * params["encoder.encoder.pe_scale"].to(dtype)
     p = "encoder.encoder."
     for i in range(cfg.n_encoder_layer):
         y, _ = attention(params, f"{p}self_attentions.{i}", _ln(x, params, f"{p}attn_layer_norms.{i}"),
@@ -289,17 +289,25 @@ def eval_batch_uncached(params: Params, cfg: ModelConfig, batch, max_frames: Opt
 
 
 def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optional[int] = None,
-                      dtype=torch.float32, return_trace: bool = False):
+                      dtype=torch.float32, return_trace: bool = False, resume: Optional[dict] = None,
+                      memory: Optional[torch.Tensor] = None):
     """Mathematically identical K/V-cached restatement of the same loop (SURVEY.md
-    Appendix A): one decoder *row* per step; self K/V appended to a cache, cross K/V of
-    the encoder memory computed once.  Used by tests to localise per-step kernel bugs and
+    Appendix A): one decoder *row* per step; self K/V appended to a (preallocated) cache, cross
+    K/V of the encoder memory computed once.  Used by tests to localise per-step kernel bugs and
     to reach long horizons on the CPU in reasonable time; validated against
-    ``eval_batch_uncached`` in tests/test_oracle_golden.py."""
+    ``eval_batch_uncached`` in tests/test_oracle_golden.py and against the reference's own
+    640-frame eval_batch output (tests/golden/full_ar_long.npz).
+
+    ``resume`` = {"t": t0, "self_k": [L x [B,H,t0,dh]], "self_v": ..., "prev": [B,M],
+    "lengths": [B] int32, "finished": [B] bool} continues a decode from step t0 with the given
+    state (tests use it to check late steps of very long decodes without replaying all of them);
+    ``max_frames`` is then the absolute step to stop at."""
     max_frames = cfg.max_generation_frames if max_frames is None else max_frames
     B = batch["inputs"].shape[0]
     Hn, L, D, M = cfg.n_attention_head, cfg.n_decoder_layer, cfg.decoder_hidden, cfg.num_mels
-    mem = encoder_forward(params, cfg, batch["inputs"], batch["input_lengths"],
-                          batch.get("input_spk_ids"), batch.get("input_language_vecs"), dtype)
+    mem = memory if memory is not None else encoder_forward(
+        params, cfg, batch["inputs"], batch["input_lengths"], batch.get("input_spk_ids"),
+        batch.get("input_language_vecs"), dtype)
     S = mem.shape[1]
     p = "decoder.decoder."
     dh = D // Hn
@@ -307,20 +315,30 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
     for l in range(L):
         kv = mem @ params[f"{p}encdec_attentions.{l}.kv_transform.weight"].to(dtype).t()
         k, v = kv.split([D, D], dim=-1)
-        cross_k.append(_heads(k, Hn))
-        cross_v.append(_heads(v, Hn))
+        cross_k.append(_heads(k, Hn).contiguous())
+        cross_v.append(_heads(v, Hn).contiguous())
     key_bias = ((~_length_mask(batch["input_lengths"], S)).to(dtype) * NEG_BIAS)[:, None, None, :]
-    pe = sinusoid_table(max_frames, D, dtype) * params[p + "pe_scale"].to(dtype)
-    self_k = [torch.zeros(B, Hn, 0, dh, dtype=dtype) for _ in range(L)]
-    self_v = [torch.zeros(B, Hn, 0, dh, dtype=dtype) for _ in range(L)]
-    lengths = torch.ones(B, dtype=torch.int32)
-    finished = torch.zeros(B, dtype=torch.bool)
-    prev = torch.zeros(B, M, dtype=dtype)
-    frames, logits, trace = [], [], []
+    dev = mem.device   # CPU in every test; bench.py's gpu_eager_baseline runs the same code on cuda (cuBLAS fp32)
+    pe = sinusoid_table(max_frames, D, dtype).to(dev) * params[p + "pe_scale"].to(dtype)
+    kbuf = [torch.zeros(B, Hn, max_frames, dh, dtype=dtype, device=dev) for _ in range(L)]
+    vbuf = [torch.zeros(B, Hn, max_frames, dh, dtype=dtype, device=dev) for _ in range(L)]
+    lengths = torch.ones(B, dtype=torch.int32, device=dev)
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    prev = torch.zeros(B, M, dtype=dtype, device=dev)
     t = 0
+    if resume is not None:
+        t = int(resume["t"])
+        for l in range(L):
+            kbuf[l][:, :, :t] = resume["self_k"][l].to(dtype)
+            vbuf[l][:, :, :t] = resume["self_v"][l].to(dtype)
+        lengths = resume["lengths"].to(torch.int32).clone()
+        finished = resume["finished"].to(torch.bool).clone()
+        prev = resume["prev"].to(dtype).clone()
+    t_first = t
+    frames, logits, trace = [], [], []
     while not bool(finished.all()) and t < max_frames:
         if t == 0:
-            x = torch.zeros(B, D, dtype=dtype)
+            x = torch.zeros(B, D, dtype=dtype, device=dev)
         else:
             x = prenet(params, prev) * ((t - 1) < lengths)[:, None].to(dtype)
         x = x + pe[t]
@@ -328,11 +346,11 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
             h = _ln(x, params, f"{p}attn_layer_norms.{l}")
             qkv = h @ params[f"{p}self_attentions.{l}.qkv_transform.weight"].to(dtype).t()
             q, k, v = qkv.split([D, D, D], dim=-1)
-            self_k[l] = torch.cat([self_k[l], k.view(B, Hn, 1, dh)], dim=2)
-            self_v[l] = torch.cat([self_v[l], v.view(B, Hn, 1, dh)], dim=2)
+            kbuf[l][:, :, t] = k.view(B, Hn, dh)
+            vbuf[l][:, :, t] = v.view(B, Hn, dh)
             q = q.view(B, Hn, 1, dh) * dh ** -0.5
-            w = torch.softmax(q @ self_k[l].transpose(2, 3), dim=-1)
-            a = (w @ self_v[l]).reshape(B, D)
+            w = torch.softmax(q @ kbuf[l][:, :, :t + 1].transpose(2, 3), dim=-1)
+            a = (w @ vbuf[l][:, :, :t + 1]).reshape(B, D)
             x = x + a @ params[f"{p}self_attentions.{l}.output_transform.weight"].to(dtype).t()
             h = _ln(x, params, f"{p}encdec_layer_norms.{l}")
             q = (h @ params[f"{p}encdec_attentions.{l}.q_transform.weight"].to(dtype).t())
@@ -354,11 +372,13 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
         finished = finished | (logit > 0)
         lengths = torch.where(finished, lengths, lengths + 1)
         t += 1
-    mels = torch.stack(frames, dim=1) if frames else torch.zeros(B, 0, M, dtype=dtype)
-    mel_aft = mels + postnet_forward(params, cfg, mels, lengths)
-    out = {"mel_pre": mels, "mel_aft": mel_aft, "generated_lengths": lengths, "memory": mem,
+    mels = torch.stack(frames, dim=1) if frames else torch.zeros(B, 0, M, dtype=dtype, device=dev)
+    out = {"mel_pre": mels, "generated_lengths": lengths, "memory": mem, "first_step": t_first,
            "stop_logits": torch.stack(logits, dim=1) if logits else torch.zeros(B, 0, dtype=dtype),
-           "self_k": self_k, "self_v": self_v, "cross_k": cross_k, "cross_v": cross_v}
+           "self_k": [k[:, :, :t] for k in kbuf], "self_v": [v[:, :, :t] for v in vbuf],
+           "cross_k": cross_k, "cross_v": cross_v}
+    if resume is None:   # mel_aft needs every frame from 0 on (synthesize.py:56)
+        out["mel_aft"] = mels + postnet_forward(params, cfg, mels, lengths)
     if return_trace:
         out["trace"] = trace
     return out

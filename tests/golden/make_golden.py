@@ -80,9 +80,26 @@ def stop_margin(model, cfg, params, batch, max_frames):
     return float(lg.abs()[live].min()) if live.any() else float("nan")
 
 
+def long_ar(n_frames=640):
+    """G6: the reference's own eval_batch over a LONG horizon (B=2, text 64 tokens, stop disabled): pins the
+    K/V-cached formulation (oracle and CUDA) against the reference's uncached O(T^2) loop across hundreds of
+    dependent steps.  ~10 minutes of CPU; run with `python tests/golden/make_golden.py long`."""
+    cfg = O.ModelConfig()
+    params = O.synth_params(cfg, seed=0)
+    params["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    model = ref_model(cfg, params).eval()
+    batch = O.synth_batch(cfg, batch=2, text_len=64, n_frames=4, seed=9, ragged=True)
+    res = run_eval_batch(cfg, model, batch, n_frames)
+    print("G6 generated_lengths", res["generated_lengths"], res["mel_pre"].shape)
+    save("full_ar_long.npz", max_frames=np.int64(n_frames), mel_pre=res["mel_pre"], mel_aft=res["mel_aft"],
+         generated_lengths=np.asarray(res["generated_lengths"], dtype=np.int32))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "long":
+        return long_ar()
 
     # ---- G1: cfg 1 — full model, B=1, 120-byte text -> 400 frames, teacher forced ------------
     cfg = O.ModelConfig()

@@ -127,3 +127,28 @@ def test_reference_lr_schedule(golden_dir):
     ref = json.load(open(os.path.join(golden_dir, "ref_init_seed0.json")))["lr_factor"]
     for step, want in ref.items():
         assert abs(O.learning_rate_factor(int(step)) - want) < 1e-12
+
+
+def test_cached_oracle_vs_reference_over_640_frames(golden_dir, full_params):
+    """The K/V-cached restatement against the REAL reference's uncached eval_batch over a long horizon
+    (tests/golden/full_ar_long.npz: B=2, 640 dependent steps), plus the `resume` entry point used by the GPU tests."""
+    cfg, params = full_params
+    z = np.load(os.path.join(golden_dir, "full_ar_long.npz"))
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    batch = O.synth_batch(cfg, batch=2, text_len=64, n_frames=4, seed=9, ragged=True)
+    T = int(z["max_frames"])
+    with torch.no_grad():
+        out = O.eval_batch_cached(p, cfg, batch, T)
+    assert out["generated_lengths"].tolist() == z["generated_lengths"].tolist()
+    e1 = np.abs(_np(out["mel_pre"]) - z["mel_pre"]).max()
+    e2 = np.abs(_np(out["mel_aft"]) - z["mel_aft"]).max()
+    print("cached oracle vs reference, 640 frames: mel_pre %.2e mel_aft %.2e" % (e1, e2))
+    assert e1 < 1e-4 and e2 < 1e-4
+    t0 = 600
+    state = {"t": t0, "self_k": [k[:, :, :t0] for k in out["self_k"]], "self_v": [v[:, :, :t0] for v in out["self_v"]],
+             "prev": out["mel_pre"][:, t0 - 1], "lengths": torch.full((2,), t0 + 1, dtype=torch.int32),
+             "finished": torch.zeros(2, dtype=torch.bool)}
+    with torch.no_grad():
+        tail = O.eval_batch_cached(p, cfg, batch, T, resume=state, memory=out["memory"])
+    assert torch.equal(tail["mel_pre"], out["mel_pre"][:, t0:])

@@ -1,5 +1,5 @@
-"""Diagnostic (not a test): a short fused-decode run for ncu.
-    ncu --set full -k regex:fused_decode_kernel -s 1 -c 1 -o gpurun_out/fused python tests/tools_ncu_target.py"""
+"""Diagnostic (not a test): a short decode run for ncu or compute-sanitizer.
+    ncu --set full -k regex:pipelined_decode_kernel -s 1 -c 1 -o gpurun_out/pipe python tests/tools_ncu_target.py"""
 import os
 import sys
 
