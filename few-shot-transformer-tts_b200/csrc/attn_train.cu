@@ -1,0 +1,532 @@
+// Flash-style multi-head attention for the teacher-forced TRAINING path: forward, dQ and dK/dV kernels on the tensor
+// cores (bf16 mma.sync m16n8k16, fp32 accumulation), masks computed from indices / lengths, Philox dropout on the
+// attention weights regenerated in the backward pass.  No [B,H,Tq,Tk] tensor is ever written: the reference
+// materialises logits, weights and the dropout mask (transformer/attention.py:83-91; 2.05 GB per layer at B=64,
+// T=1000) and autograd keeps them for backward.
+//
+//   forward : O = dropout(softmax(Q K^T * scale + mask)) V, saves L = log2-sum-exp per (b, h, query)
+//   dQ      : one CTA per 64 queries, loops over key blocks: S, dP = dO V^T, dS = P (keep dP / (1-p) - delta), dQ += dS K;
+//             also produces delta = rowsum(dO o O) for the dK/dV kernel
+//   dK / dV : one CTA per 64 keys, loops over query blocks with the TRANSPOSED products (S^T = K Q^T, dP^T = V dO^T), so
+//             P^T and dS^T are already in A-fragment layout for dV += P^T dO and dK += dS^T Q: no shared-memory
+//             round trip, no atomics, deterministic
+// Reference semantics: transformer/attention.py:72-122 (scale on q :113-114, additive -1e20 bias :84-85 == exclusion
+// from the softmax, dropout on the weights :89), masks of transformer/modules.py:50-52,109-112.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace tts {
+namespace attn {
+
+constexpr int kThreads = 128;   // 4 warps x 16 rows
+constexpr int BQ = 64, BKV = 64;
+
+struct Args {
+  const __nv_bfloat16 *q, *k, *v;
+  long long ldq, ldk, ldv;
+  __nv_bfloat16* o; long long ldo;
+  float* lse;                       // [B][H][Tq], log2 domain
+  int B, H, Tq, Tk;
+  float scale_log2;                 // head_dim^-0.5 * log2(e)
+  float scale;                      // head_dim^-0.5
+  int causal;
+  const int32_t* key_len;           // [B] or NULL
+  float drop_scale; uint32_t drop_thresh; unsigned long long seed; uint32_t stream;
+  // backward
+  const __nv_bfloat16* d_o; long long lddo;
+  float* delta;                     // [B][H][Tq]
+  __nv_bfloat16 *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// [ROWS][DH] bf16 tile -> shared memory rows of DH + 8 elements (16 bytes of padding: ldmatrix conflict-free); rows at or
+// beyond `rows_valid` are zero-filled
+template <int DH, int ROWS>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int row0, int rows_total) {
+  constexpr int LDS = DH + 8, CPR = DH / 8;   // 16-byte chunks per row
+  for (int c = threadIdx.x; c < ROWS * CPR; c += kThreads) {
+    const int r = c / CPR, cc = c - r * CPR;
+    const bool ok = row0 + r < rows_total;
+    const __nv_bfloat16* g = src + (long long)(ok ? row0 + r : 0) * ld + cc * 8;
+    const uint32_t d = smem_u32(dst + r * LDS + cc * 8);
+    const int bytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(bytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// A fragments (16 rows x DH) of one warp from a shared-memory tile: a[ks] covers k = 16 ks .. 16 ks + 15
+template <int DH>
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[DH / 16][4], const __nv_bfloat16* tile, int row0) {
+  constexpr int LDS = DH + 8;
+  const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
+  const uint32_t base = smem_u32(tile + (row0 + r + (mi & 1) * 8) * LDS + (mi >> 1) * 8);
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks) ldsm_x4(a[ks], base + ks * 32);
+}
+
+// C[16 x 64] += A[16 x DH] . T[64 x DH]^T: the tile rows are the n index, contraction over DH (non-transposed ldmatrix)
+template <int DH, int NT>
+__device__ __forceinline__ void mma_a_tt(float (&c)[NT][4], const uint32_t (&a)[DH / 16][4], const __nv_bfloat16* tile, int n_row0) {
+  constexpr int LDS = DH + 8;
+  const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
+  const uint32_t base = smem_u32(tile + (n_row0 + r + (mi >> 1) * 8) * LDS + (mi & 1) * 8);
+#pragma unroll
+  for (int ks = 0; ks < DH / 16; ++ks)
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4(b, base + (np * 16 * LDS + ks * 16) * 2);
+      mma_bf16(c[2 * np], a[ks], b[0], b[1]);
+      mma_bf16(c[2 * np + 1], a[ks], b[2], b[3]);
+    }
+}
+
+// C[16 x DH] += P[16 x KN] . T[KN x DH]: the tile rows are the contraction index (transposed ldmatrix); P comes from
+// fp32 accumulator fragments p[KN/8][4] converted on the fly
+template <int DH, int KNT>
+__device__ __forceinline__ void mma_p_t(float (&c)[DH / 8][4], const float (&p)[KNT][4], const __nv_bfloat16* tile, int k_row0) {
+  constexpr int LDS = DH + 8;
+  const int lane = threadIdx.x & 31, mi = lane >> 3, r = lane & 7;
+  const uint32_t base = smem_u32(tile + (k_row0 + r + (mi & 1) * 8) * LDS + (mi >> 1) * 8);
+#pragma unroll
+  for (int ks = 0; ks < KNT / 2; ++ks) {
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+    a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+    a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+    a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+#pragma unroll
+    for (int np = 0; np < DH / 16; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, base + (ks * 16 * LDS + np * 16) * 2);
+      mma_bf16(c[2 * np], a, b[0], b[1]);
+      mma_bf16(c[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// keep flags of the 8 weights a thread holds in one 16 x 16 block (two neighbouring n-tiles); TR: the accumulator rows are
+// keys and the columns queries (dK/dV kernel).  bit e of the result <-> (n-tile parity e >> 2, accumulator register e & 3)
+template <bool TR>
+__device__ __forceinline__ uint32_t keep_bits(const Args& a, unsigned long long bh, int n_iblk, int n_jblk, int row0, int col0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = TR ? col0 + t2 + e : row0 + g, j = TR ? row0 + g : col0 + t2 + e;
+    const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, i, j), a.stream);
+    // word = 2 * (i bit 3) + (j bit 3); accumulator register = 2 * (row bit 3) + e, n-tile parity = column bit 3
+    if (!TR) {
+      bits |= (w.x >= a.drop_thresh ? 1u : 0u) << (0 + e);        // (i, j)      : tile 0, reg e
+      bits |= (w.y >= a.drop_thresh ? 1u : 0u) << (4 + e);        // (i, j+8)    : tile 1, reg e
+      bits |= (w.z >= a.drop_thresh ? 1u : 0u) << (2 + e);        // (i+8, j)    : tile 0, reg 2+e
+      bits |= (w.w >= a.drop_thresh ? 1u : 0u) << (6 + e);        // (i+8, j+8)  : tile 1, reg 2+e
+    } else {
+      bits |= (w.x >= a.drop_thresh ? 1u : 0u) << (0 + e);        // (i, j)      : row j, col i     -> tile 0, reg e
+      bits |= (w.y >= a.drop_thresh ? 1u : 0u) << (2 + e);        // (i, j+8)    : row j+8          -> tile 0, reg 2+e
+      bits |= (w.z >= a.drop_thresh ? 1u : 0u) << (4 + e);        // (i+8, j)    : col i+8          -> tile 1, reg e
+      bits |= (w.w >= a.drop_thresh ? 1u : 0u) << (6 + e);        // (i+8, j+8)                     -> tile 1, reg 2+e
+    }
+  }
+  return bits;
+}
+
+__device__ __forceinline__ bool key_ok(const Args& a, int i, int j, int klen) {
+  return j < klen && (!a.causal || j <= i);
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Args a) {
+  constexpr int LDS = DH + 8;
+  extern __shared__ __align__(16) __nv_bfloat16 sm[];
+  __nv_bfloat16 *sQ = sm, *sK = sQ + BQ * LDS, *sV = sK + BKV * LDS;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  const unsigned long long bh = (unsigned long long)b * a.H + h;
+  const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
+  const int n_iblk = (a.Tq + 15) >> 4, n_jblk = (a.Tk + 15) >> 4;
+  const __nv_bfloat16* qg = a.q + (long long)b * a.Tq * a.ldq + h * DH;
+  const __nv_bfloat16* kg = a.k + (long long)b * a.Tk * a.ldk + h * DH;
+  const __nv_bfloat16* vg = a.v + (long long)b * a.Tk * a.ldv + h * DH;
+
+  load_tile<DH, BQ>(sQ, qg, a.ldq, q0, a.Tq);
+  cp_wait_all();
+  __syncthreads();
+  uint32_t qf[DH / 16][4];
+  load_a_frags<DH>(qf, sQ, warp * 16);
+
+  float o[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
+  const int i0 = q0 + warp * 16 + g;
+  const int k_end = a.causal ? min(klen, q0 + BQ) : klen;
+
+  for (int kb = 0; kb < k_end; kb += BKV) {
+    __syncthreads();   // everyone is done with the previous K/V tiles
+    load_tile<DH, BKV>(sK, kg, a.ldk, kb, a.Tk);
+    load_tile<DH, BKV>(sV, vg, a.ldv, kb, a.Tk);
+    cp_wait_all();
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    mma_a_tt<DH, 8>(s, qf, sK, 0);
+    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
+        s[n][e] = key_ok(a, i, j, klen) ? s[n][e] * a.scale_log2 : -CUDART_INF_F;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float mn = fmaxf(m[r], mx[r]);
+      const float mu = mn == -CUDART_INF_F ? 0.f : mn;
+      const float corr = ex2(m[r] - mu);   // exp2(-inf) = 0 on the first block
+      m[r] = mn;
+      l[r] *= corr;
+#pragma unroll
+      for (int n = 0; n < DH / 8; ++n) {
+        o[n][2 * r] *= corr;
+        o[n][2 * r + 1] *= corr;
+      }
+      mx[r] = mu;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[n][e] = ex2(s[n][e] - mx[e >> 1]);
+        l[e >> 1] += s[n][e];
+      }
+    if (a.drop_thresh != 0u) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        const uint32_t bits = keep_bits<false>(a, bh, n_iblk, n_jblk, q0 + warp * 16, kb + np * 16);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (!((bits >> e) & 1u)) s[2 * np + (e >> 2)][e & 3] = 0.f;
+      }
+    }
+    mma_p_t<DH, 8>(o, s, sV, 0);
+  }
+  // finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i >= a.Tq) continue;
+    const float inv = l[r] > 0.f ? a.drop_scale / l[r] : 0.f;
+    __nv_bfloat16* op = a.o + ((long long)b * a.Tq + i) * a.ldo + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n)
+      *reinterpret_cast<uint32_t*>(op + n * 8 + t2) = pack_bf16(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    if ((lane & 3) == 0 && a.lse != nullptr) a.lse[(bh * a.Tq) + i] = m[r] + log2f(l[r]);
+  }
+}
+
+// =====================================================================================================================
+// backward: dQ (+ delta)
+// =====================================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
+  constexpr int LDS = DH + 8;
+  extern __shared__ __align__(16) __nv_bfloat16 sm[];
+  __nv_bfloat16 *sQ = sm, *sDO = sQ + BQ * LDS, *sK = sDO + BQ * LDS, *sV = sK + BKV * LDS;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  const unsigned long long bh = (unsigned long long)b * a.H + h;
+  const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
+  const int n_iblk = (a.Tq + 15) >> 4, n_jblk = (a.Tk + 15) >> 4;
+  const __nv_bfloat16* qg = a.q + (long long)b * a.Tq * a.ldq + h * DH;
+  const __nv_bfloat16* dog = a.d_o + (long long)b * a.Tq * a.lddo + h * DH;
+  const __nv_bfloat16* og = a.o + (long long)b * a.Tq * a.ldo + h * DH;
+  const __nv_bfloat16* kg = a.k + (long long)b * a.Tk * a.ldk + h * DH;
+  const __nv_bfloat16* vg = a.v + (long long)b * a.Tk * a.ldv + h * DH;
+  const int i0 = q0 + warp * 16 + g;
+
+  // delta = rowsum(dO o O) (fp32), O staged through the K tile buffer
+  load_tile<DH, BQ>(sQ, qg, a.ldq, q0, a.Tq);
+  load_tile<DH, BQ>(sDO, dog, a.lddo, q0, a.Tq);
+  load_tile<DH, BQ>(sK, og, a.ldo, q0, a.Tq);
+  cp_wait_all();
+  __syncthreads();
+  float dl[2];
+  {
+    // thread (row = tid / 2, half = tid % 2) sums half a row; pairs combine by shuffle
+    const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int d = half * (DH / 2); d < (half + 1) * (DH / 2); ++d)
+      acc += __bfloat162float(sDO[row * LDS + d]) * __bfloat162float(sK[row * LDS + d]);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    float* sdelta = reinterpret_cast<float*>(sV);   // 64 floats
+    if (half == 0) {
+      sdelta[row] = acc;
+      if (q0 + row < a.Tq) a.delta[bh * a.Tq + q0 + row] = acc;
+    }
+    __syncthreads();
+    dl[0] = sdelta[warp * 16 + g];
+    dl[1] = sdelta[warp * 16 + g + 8];
+  }
+  float lse[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) lse[r] = i0 + r * 8 < a.Tq ? a.lse[bh * a.Tq + i0 + r * 8] : 0.f;
+
+  uint32_t qf[DH / 16][4], dof[DH / 16][4];
+  load_a_frags<DH>(qf, sQ, warp * 16);
+  load_a_frags<DH>(dof, sDO, warp * 16);
+  float dq[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+  const int k_end = a.causal ? min(klen, q0 + BQ) : klen;
+
+  for (int kb = 0; kb < k_end; kb += BKV) {
+    __syncthreads();
+    load_tile<DH, BKV>(sK, kg, a.ldk, kb, a.Tk);
+    load_tile<DH, BKV>(sV, vg, a.ldv, kb, a.Tk);
+    cp_wait_all();
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+    mma_a_tt<DH, 8>(s, qf, sK, 0);
+    mma_a_tt<DH, 8>(dp, dof, sV, 0);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bits = 0xffu;
+      if (a.drop_thresh != 0u) bits = keep_bits<false>(a, bh, n_iblk, n_jblk, q0 + warp * 16, kb + np * 16);
+#pragma unroll
+      for (int e8 = 0; e8 < 8; ++e8) {
+        const int n = 2 * np + (e8 >> 2), e = e8 & 3;
+        const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
+        const float p = key_ok(a, i, j, klen) ? ex2(s[n][e] * a.scale_log2 - lse[e >> 1]) : 0.f;
+        const float dpe = ((bits >> e8) & 1u) ? dp[n][e] * a.drop_scale : 0.f;
+        s[n][e] = p * (dpe - dl[e >> 1]) * a.scale;   // dS (scaled: dQ = scale * dS K)
+      }
+    }
+    mma_p_t<DH, 8>(dq, s, sK, 0);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = i0 + r * 8;
+    if (i >= a.Tq) continue;
+    __nv_bfloat16* dp_ = a.dq + ((long long)b * a.Tq + i) * a.lddq + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) *reinterpret_cast<uint32_t*>(dp_ + n * 8 + t2) = pack_bf16(dq[n][2 * r], dq[n][2 * r + 1]);
+  }
+}
+
+// =====================================================================================================================
+// backward: dK, dV (transposed products)
+// =====================================================================================================================
+template <int DH>
+__global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
+  constexpr int LDS = DH + 8, BQ2 = 32;
+  extern __shared__ __align__(16) __nv_bfloat16 sm[];
+  __nv_bfloat16 *sK = sm, *sV = sK + BKV * LDS, *sQ = sV + BKV * LDS, *sDO = sQ + BQ2 * LDS;
+  float* sL = reinterpret_cast<float*>(sDO + BQ2 * LDS);   // [32] lse, [32] delta
+  const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  const unsigned long long bh = (unsigned long long)b * a.H + h;
+  const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
+  const int n_iblk = (a.Tq + 15) >> 4, n_jblk = (a.Tk + 15) >> 4;
+  const __nv_bfloat16* qg = a.q + (long long)b * a.Tq * a.ldq + h * DH;
+  const __nv_bfloat16* dog = a.d_o + (long long)b * a.Tq * a.lddo + h * DH;
+  const __nv_bfloat16* kg = a.k + (long long)b * a.Tk * a.ldk + h * DH;
+  const __nv_bfloat16* vg = a.v + (long long)b * a.Tk * a.ldv + h * DH;
+  const int jr = j0 + warp * 16 + g;   // this thread's key rows: jr, jr + 8
+
+  load_tile<DH, BKV>(sK, kg, a.ldk, j0, a.Tk);
+  load_tile<DH, BKV>(sV, vg, a.ldv, j0, a.Tk);
+  cp_wait_all();
+  __syncthreads();
+  uint32_t kf[DH / 16][4], vf[DH / 16][4];
+  load_a_frags<DH>(kf, sK, warp * 16);
+  load_a_frags<DH>(vf, sV, warp * 16);
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) {
+    dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+  }
+  const bool any_key = j0 < klen;
+  const int q_begin = a.causal ? (j0 / BQ2) * BQ2 : 0;   // queries before the first key of the block never see it
+
+  for (int qb = q_begin; qb < a.Tq && any_key; qb += BQ2) {
+    __syncthreads();
+    load_tile<DH, BQ2>(sQ, qg, a.ldq, qb, a.Tq);
+    load_tile<DH, BQ2>(sDO, dog, a.lddo, qb, a.Tq);
+    if (threadIdx.x < BQ2) {
+      const int i = qb + threadIdx.x;
+      sL[threadIdx.x] = i < a.Tq ? a.lse[bh * a.Tq + i] : 0.f;
+      sL[BQ2 + threadIdx.x] = i < a.Tq ? a.delta[bh * a.Tq + i] : 0.f;
+    }
+    cp_wait_all();
+    __syncthreads();
+    float st[4][4], dpt[4][4];   // S^T and dP^T: rows = keys, columns = the 32 queries of the block
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+      dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
+    }
+    mma_a_tt<DH, 4>(st, kf, sQ, 0);
+    mma_a_tt<DH, 4>(dpt, vf, sDO, 0);
+    float pt[4][4];
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bits = 0xffu;
+      if (a.drop_thresh != 0u) bits = keep_bits<true>(a, bh, n_iblk, n_jblk, j0 + warp * 16, qb + np * 16);
+#pragma unroll
+      for (int e8 = 0; e8 < 8; ++e8) {
+        const int n = 2 * np + (e8 >> 2), e = e8 & 3;
+        const int j = jr + (e >> 1) * 8, il = n * 8 + t2 + (e & 1), i = qb + il;
+        const bool ok = i < a.Tq && j < a.Tk && key_ok(a, i, j, klen);
+        const float p = ok ? ex2(st[n][e] * a.scale_log2 - sL[il]) : 0.f;
+        const bool keep = (bits >> e8) & 1u;
+        pt[n][e] = keep ? p * a.drop_scale : 0.f;                         // dropped-and-scaled weights: dV = P_drop^T dO
+        const float dpe = keep ? dpt[n][e] * a.drop_scale : 0.f;
+        st[n][e] = p * (dpe - sL[BQ2 + il]) * a.scale;                   // dS^T (scaled: dK = scale * dS^T Q)
+      }
+    }
+    mma_p_t<DH, 4>(dv, pt, sDO, 0);
+    mma_p_t<DH, 4>(dk, st, sQ, 0);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = jr + r * 8;
+    if (j >= a.Tk) continue;
+    __nv_bfloat16* kp = a.dk + ((long long)b * a.Tk + j) * a.lddk + h * DH;
+    __nv_bfloat16* vp = a.dv + ((long long)b * a.Tk + j) * a.lddv + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(kp + n * 8 + t2) = pack_bf16(dk[n][2 * r], dk[n][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(vp + n * 8 + t2) = pack_bf16(dv[n][2 * r], dv[n][2 * r + 1]);
+    }
+  }
+}
+
+template <int DH>
+static int launch_fwd(const Args& a, cudaStream_t s) {
+  const size_t smem = (size_t)(BQ + 2 * BKV) * (DH + 8) * 2;
+  TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_fwd_kernel<DH><<<dim3(ceil_div(a.Tq, BQ), a.H, a.B), kThreads, smem, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  return 0;
+}
+template <int DH>
+static int launch_bwd(const Args& a, cudaStream_t s) {
+  const size_t smem_q = (size_t)(2 * BQ + 2 * BKV) * (DH + 8) * 2;
+  const size_t smem_kv = (size_t)(2 * BKV + 2 * 32) * (DH + 8) * 2 + 64 * sizeof(float);
+  TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+  TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+  attn_bwd_dq_kernel<DH><<<dim3(ceil_div(a.Tq, BQ), a.H, a.B), kThreads, smem_q, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  attn_bwd_dkv_kernel<DH><<<dim3(ceil_div(a.Tk, BKV), a.H, a.B), kThreads, smem_kv, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  return 0;
+}
+
+static int fill(Args& a, const TtsAttnTrain* t) {
+  TTS_REQUIRE(t && t->q && t->k && t->v && t->out && t->lse, "attn_train: null argument");
+  TTS_REQUIRE(t->batch > 0 && t->n_heads > 0 && t->tq > 0 && t->tk > 0, "attn_train: empty problem");
+  TTS_REQUIRE(t->head_dim == 32 || t->head_dim == 64 || t->head_dim == 96, "attn_train: head_dim %d not in {32,64,96}", t->head_dim);
+  TTS_REQUIRE(t->ldq % 8 == 0 && t->ldk % 8 == 0 && t->ldv % 8 == 0 && t->ldo % 8 == 0, "attn_train: row strides must be multiples of 8");
+  TTS_REQUIRE(!t->causal || t->tq == t->tk, "attn_train: causal needs tq == tk");
+  memset(&a, 0, sizeof(a));
+  a.q = reinterpret_cast<const __nv_bfloat16*>(t->q); a.k = reinterpret_cast<const __nv_bfloat16*>(t->k);
+  a.v = reinterpret_cast<const __nv_bfloat16*>(t->v);
+  a.ldq = t->ldq; a.ldk = t->ldk; a.ldv = t->ldv;
+  a.o = reinterpret_cast<__nv_bfloat16*>(t->out); a.ldo = t->ldo;
+  a.lse = t->lse;
+  a.B = t->batch; a.H = t->n_heads; a.Tq = t->tq; a.Tk = t->tk;
+  a.scale = 1.f / sqrtf((float)t->head_dim);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.causal = t->causal; a.key_len = t->key_len;
+  a.drop_scale = 1.f;
+  if (t->drop_p > 0.f) {
+    TTS_REQUIRE(t->drop_p < 1.f, "attn_train: drop_p must be < 1");
+    a.drop_thresh = drop_threshold(t->drop_p);
+    a.drop_scale = 1.f / (1.f - t->drop_p);
+    a.seed = t->seed; a.stream = t->rng_stream;
+  }
+  return 0;
+}
+
+}  // namespace attn
+}  // namespace tts
+
+using namespace tts;
+
+extern "C" int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream) {
+  attn::Args a;
+  int rc = attn::fill(a, t);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (t->head_dim) {
+    case 32: return attn::launch_fwd<32>(a, s);
+    case 64: return attn::launch_fwd<64>(a, s);
+    default: return attn::launch_fwd<96>(a, s);
+  }
+}
+
+extern "C" int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream) {
+  attn::Args a;
+  int rc = attn::fill(a, t);
+  if (rc) return rc;
+  TTS_REQUIRE(t->d_out && t->delta && t->dq && t->dk && t->dv, "attn_train_bwd: null gradient buffers");
+  TTS_REQUIRE(t->lddo % 8 == 0 && t->lddq % 8 == 0 && t->lddk % 8 == 0 && t->lddv % 8 == 0, "attn_train_bwd: row strides must be multiples of 8");
+  a.d_o = reinterpret_cast<const __nv_bfloat16*>(t->d_out); a.lddo = t->lddo;
+  a.delta = t->delta;
+  a.dq = reinterpret_cast<__nv_bfloat16*>(t->dq); a.dk = reinterpret_cast<__nv_bfloat16*>(t->dk);
+  a.dv = reinterpret_cast<__nv_bfloat16*>(t->dv);
+  a.lddq = t->lddq; a.lddk = t->lddk; a.lddv = t->lddv;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (t->head_dim) {
+    case 32: return attn::launch_bwd<32>(a, s);
+    case 64: return attn::launch_bwd<64>(a, s);
+    default: return attn::launch_bwd<96>(a, s);
+  }
+}

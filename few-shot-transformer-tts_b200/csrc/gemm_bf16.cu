@@ -1,0 +1,498 @@
+// bf16 tcgen05 GEMM of the teacher-forced TRAINING path (forward, dgrad and wgrad of every nn.Linear / nn.Conv1d of
+// transformer/attention.py:43-47, modules.py:11-19, tacotron.py:50-52,78,103-105 - the reference runs them as fp32
+// cuBLAS / cuDNN calls through autograd).
+//
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ),  A and B bf16, fp32 accumulation in tensor memory.
+//
+// Blackwell-native structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0     TMA producer: cp.async.bulk.tensor.2d tiles (128-byte swizzle) into a 4/6-stage shared-memory ring,
+//              completion on mbarriers (SASS: UTMALDG)
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16; SASS UTCHMMA)
+//              from shared-memory descriptors, tcgen05.commit releases ring stages and publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld (LDTM) 32 lanes x 32 columns at a time, fused bias / ReLU / Philox dropout /
+//              residual / length mask / ReLU-gate (backward) / bf16 or fp32 store / split-K fp32 reduction
+//   tensor memory holds TWO accumulators (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Operands may be K-major (row-major [rows][K], the forward layout) or MN-major (row-major [K][rows]): dgrad reads the
+// weight [N][K] as the MN-major B operand of dX = dY W, wgrad reads dY and X as MN-major operands of dW = dY^T X, so
+// no transposed copy of a weight or an activation is ever written.  A k5 Conv1d runs as 5 accumulated taps over a
+// zero-padded channels-last buffer (the producer shifts the A row coordinate per tap).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace tts {
+namespace bf {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kThreads = 192;
+constexpr int kABytes = BM * BK * 2;   // 16 KB
+constexpr long long kTimeout = 2LL << 30;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+};
+
+struct Params {
+  int M, N;
+  int taps, kb_per_tap, tap_b_stride;   // contraction = taps x kb_per_tap k-blocks; tap t: A rows + t, B k + t * tap_b_stride
+  int a_mn, b_mn;                       // operand stored MN-major ([K][rows])
+  int split_k, n_mblk, n_nblk;
+  void* C; long long ldc; int out_bf16;
+  const float* bias; int act; float alpha;
+  const float* residual; long long ldr;
+  float drop_scale; uint32_t drop_thresh; unsigned long long seed; uint32_t stream;
+  const __nv_bfloat16* gate; long long ldg; float gate_scale;
+  const int32_t* row_len; int rows_per_batch, valid_rows, out_rows_per_batch, out_row_offset;
+};
+
+__device__ int g_err;   // sticky: a barrier wait timed out (read by tts_gemm_bf16_status)
+
+struct Shared {
+  uint64_t full[8], empty[8], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {   // false on timeout: never hangs the GPU
+  long long t0 = 0, spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return true;
+    if ((++spins & 1023) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeout) {
+        atomicExch(&g_err, 1);
+        return false;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor; canonical layouts
+// in cute/atom/mma_traits_sm100.hpp).  K-major: rows of 128 bytes (64 bf16 of K), 8-row atoms SBO = 1024 bytes apart.
+// MN-major: rows of 128 bytes hold 64 consecutive MN elements of one k, 8-k atoms SBO = 1024 bytes apart, the next 64
+// MN elements LBO = 64 k-rows x 128 bytes = 8192 bytes away.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;   // descriptor version (sm_100)
+  d |= 2ull << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct Unit {
+  int m0, n0, kb0, kb1;
+};
+__device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
+  const int n_tiles = p.n_mblk * p.n_nblk;
+  const int split = u / n_tiles, tile = u - split * n_tiles;   // split slowest: concurrent CTAs share operand slices in L2
+  const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+  const int total = p.taps * p.kb_per_tap, per = (total + p.split_k - 1) / p.split_k;
+  Unit r;
+  r.m0 = mb * BM;
+  r.kb0 = split * per;
+  r.kb1 = min(total, r.kb0 + per);
+  r.n0 = nb;   // scaled by BN by the caller
+  return r;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Shared* sh = reinterpret_cast<Shared*>(smem + C::kStages * C::kStage);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_units = p.n_mblk * p.n_nblk * p.split_k;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sh->tfull[s], 1);
+      mbar_init(&sh->tempty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // the MMA warp owns the tensor-memory allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = sh->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
+        const Unit un = decode_unit(p, u);
+        const int n0 = un.n0 * BN;
+        for (int kb = un.kb0; kb < un.kb1 && ok; ++kb, ++it) {
+          const int s = it % C::kStages;
+          ok = mbar_wait(&sh->empty[s], ((it / C::kStages) & 1u) ^ 1u);
+          uint64_t* bar = &sh->full[s];
+          mbar_expect_tx(bar, (unsigned)C::kStage);
+          const uint32_t a_dst = smem_u32(smem + s * C::kStage), b_dst = a_dst + kABytes;
+          const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
+          const int ka = kc * BK, kbc = tap * p.tap_b_stride + kc * BK;
+          if (!p.a_mn) {
+            tma_2d(a_dst, &tmA, ka, un.m0 + tap, bar);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_2d(a_dst + j * 8192, &tmA, un.m0 + 64 * j, ka, bar);
+          }
+          if (!p.b_mn) {
+            tma_2d(b_dst, &tmB, kbc, n0, bar);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_2d(b_dst + j * 8192, &tmB, n0 + 64 * j, kbc, bar);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, per-operand major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K = 16
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      uint32_t it = 0, lu = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, ++lu) {
+        const Unit un = decode_unit(p, u);
+        const uint32_t as = lu & 1u;
+        ok = mbar_wait(&sh->tempty[as], ((lu >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_d + as * BN;
+        for (int kb = un.kb0; kb < un.kb1 && ok; ++kb, ++it) {
+          const int s = it % C::kStages;
+          ok = mbar_wait(&sh->full[s], (it / C::kStages) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_u32(smem + s * C::kStage), b_base = a_base + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(acc, make_desc(a_base + k * a_step, a_lbo, 1024u), make_desc(b_base + k * b_step, b_lbo, 1024u), idesc,
+                      (kb > un.kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it
+        }
+        umma_commit(&sh->tfull[as]);    // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps: TMEM lane quadrant = warp % 4, thread = output row =================
+    const int quad = warp & 3;
+    const int rpb = p.rows_per_batch > 0 ? p.rows_per_batch : p.M;
+    const int valid = p.valid_rows > 0 ? p.valid_rows : rpb;
+    const int orpb = p.out_rows_per_batch > 0 ? p.out_rows_per_batch : rpb;
+    uint32_t lu = 0;
+    bool ok = true;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++lu) {
+      const Unit un = decode_unit(p, u);
+      const int n0 = un.n0 * BN;
+      const uint32_t as = lu & 1u;
+      if (ok) ok = mbar_wait(&sh->tfull[as], (lu >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = un.m0 + quad * 32 + lane;
+      const int b = m / rpb, r = m - b * rpb;
+      const bool row_ok = ok && m < p.M && r < valid && un.kb1 > un.kb0;
+      const bool dead = row_ok && p.row_len != nullptr && r >= p.row_len[b];
+      const size_t orow = (size_t)b * orpb + r + p.out_row_offset;
+      for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + as * BN + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+        const int n = n0 + c0;
+        const bool full = n + 32 <= p.N;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n + j < p.N) x[j] += __ldg(p.bias + n + j);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (p.gate != nullptr) {   // backward of ReLU (+ dropout): the saved forward output is > 0 exactly where both kept it
+          const __nv_bfloat16* gp = p.gate + orow * p.ldg + n;
+          if (full && (p.ldg & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gp) + q);
+              const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // bf16 > 0: sign clear and magnitude non-zero
+                const uint32_t lo = w[e] & 0xffffu, hi = w[e] >> 16;
+                x[q * 8 + 2 * e] = (lo != 0u && lo < 0x8000u) ? x[q * 8 + 2 * e] * p.gate_scale : 0.f;
+                x[q * 8 + 2 * e + 1] = (hi != 0u && hi < 0x8000u) ? x[q * 8 + 2 * e + 1] * p.gate_scale : 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) x[j] = __bfloat162float(gp[j]) > 0.f ? x[j] * p.gate_scale : 0.f;
+          }
+        }
+        if (p.drop_thresh != 0u) {   // nn.Dropout on the product (before the residual add: modules.py:132,138,141)
+          const unsigned long long e0 = (unsigned long long)orow * (unsigned long long)p.N + (unsigned long long)n;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint4 rw = dropout_words_linear(p.seed, p.stream, (e0 >> 2) + q);
+            x[4 * q + 0] = rw.x >= p.drop_thresh ? x[4 * q + 0] * p.drop_scale : 0.f;
+            x[4 * q + 1] = rw.y >= p.drop_thresh ? x[4 * q + 1] * p.drop_scale : 0.f;
+            x[4 * q + 2] = rw.z >= p.drop_thresh ? x[4 * q + 2] * p.drop_scale : 0.f;
+            x[4 * q + 3] = rw.w >= p.drop_thresh ? x[4 * q + 3] * p.drop_scale : 0.f;
+          }
+        }
+        if (p.residual != nullptr) {
+          const float* rp = p.residual + orow * p.ldr + n;
+          if (full && (p.ldr & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rp) + q);
+              x[4 * q] += rv.x; x[4 * q + 1] += rv.y; x[4 * q + 2] += rv.z; x[4 * q + 3] += rv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) x[j] += rp[j];
+          }
+        }
+        if (dead) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.f;
+        }
+        if (p.split_k > 1) {   // fp32 reduction of the K splits into a zero-initialised C
+          float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n + j < p.N) atomicAdd(cp + j, x[j]);
+        } else if (p.out_bf16) {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n;
+          if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(x[8 * q], x[8 * q + 1]), t1 = __floats2bfloat162_rn(x[8 * q + 2], x[8 * q + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(x[8 * q + 4], x[8 * q + 5]), t3 = __floats2bfloat162_rn(x[8 * q + 6], x[8 * q + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+              reinterpret_cast<uint4*>(cp)[q] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) cp[j] = __float2bfloat16_rn(x[j]);
+          }
+        } else {
+          float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + n;
+          if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(cp)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) cp[j] = x[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tempty[as]);   // this warp's quadrant of the accumulator is free again
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)C::kTmemCols) : "memory");
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static std::atomic<EncodeTiledFn> fn{nullptr};
+  EncodeTiledFn f = fn.load(std::memory_order_acquire);
+  if (f == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && ptr != nullptr) {
+      f = reinterpret_cast<EncodeTiledFn>(ptr);
+      fn.store(f, std::memory_order_release);
+    }
+  }
+  return f;
+}
+
+// operand stored row-major [outer][inner] with `ld` elements between rows; box = [box_outer][64 inner elements]
+static int make_map(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn f = encode_fn();
+  TTS_REQUIRE(f != nullptr, "gemm_bf16: cuTensorMapEncodeTiled is not available from this driver");
+  TTS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+              "gemm_bf16: operands need 16-byte aligned base pointers and row strides (ld=%lld)", ld);
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult rc = f(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TTS_REQUIRE(rc == CUDA_SUCCESS, "gemm_bf16: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)rc,
+              inner, outer, ld);
+  return 0;
+}
+
+static int sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t s) {
+  using C = Cfg<BN>;
+  const size_t smem = (size_t)C::kStages * C::kStage + sizeof(Shared) + 1024 + 64;
+  static std::atomic<unsigned long long> configured{0ull};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  const int units = p.n_mblk * p.n_nblk * p.split_k;
+  const int grid = units < sm_count() ? units : sm_count();
+  gemm_bf16_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mb, p);
+  TTS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace bf
+}  // namespace tts
+
+using namespace tts;
+
+extern "C" int tts_gemm_bf16(const TtsGemmBf16* g, void* stream) {
+  TTS_REQUIRE(g != nullptr && g->A && g->B && g->C, "gemm_bf16: null operand");
+  TTS_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", g->M, g->N, g->K);
+  const int taps = g->taps > 0 ? g->taps : 1;
+  TTS_REQUIRE(taps == 1 || (!g->a_mn_major && !g->b_mn_major), "gemm_bf16: taps need K-major operands");
+  bf::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M; p.N = g->N;
+  p.taps = taps;
+  p.kb_per_tap = (g->K + bf::BK - 1) / bf::BK;
+  p.tap_b_stride = g->K;
+  p.a_mn = g->a_mn_major ? 1 : 0;
+  p.b_mn = g->b_mn_major ? 1 : 0;
+  const int bn = g->N > 128 ? 256 : 128;
+  p.n_mblk = (g->M + bf::BM - 1) / bf::BM;
+  p.n_nblk = (g->N + bn - 1) / bn;
+  const int total_kb = taps * p.kb_per_tap;
+  int split = g->split_k > 0 ? g->split_k : 1;
+  if (split > total_kb) split = total_kb;
+  while (split > 1 && ((total_kb + split - 1) / split) * (split - 1) >= total_kb) --split;   // no empty split
+  p.split_k = split;
+  TTS_REQUIRE(split == 1 || (!g->out_bf16 && !g->bias && !g->residual && g->act == 0 && g->drop_p == 0.f && !g->gate),
+              "gemm_bf16: split-K supports only a plain fp32 reduction into a zeroed C");
+  p.C = g->C; p.ldc = g->ldc; p.out_bf16 = g->out_bf16;
+  p.bias = g->bias; p.act = g->act; p.alpha = g->alpha == 0.f ? 1.f : g->alpha;
+  p.residual = g->residual; p.ldr = g->ldr;
+  if (g->drop_p > 0.f) {
+    TTS_REQUIRE(g->drop_p < 1.f && g->N % 4 == 0, "gemm_bf16: dropout needs p < 1 and N %% 4 == 0");
+    p.drop_thresh = drop_threshold(g->drop_p);
+    p.drop_scale = 1.f / (1.f - g->drop_p);
+    p.seed = g->seed; p.stream = g->rng_stream;
+  }
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(g->gate); p.ldg = g->ldg; p.gate_scale = g->gate_scale == 0.f ? 1.f : g->gate_scale;
+  p.row_len = g->row_len; p.rows_per_batch = g->rows_per_batch; p.valid_rows = g->valid_rows;
+  p.out_rows_per_batch = g->out_rows_per_batch; p.out_row_offset = g->out_row_offset;
+
+  // A: M rows (+ taps - 1 for the shifted conv reads), contraction K;  B: N rows, contraction taps * K
+  CUtensorMap ma, mb;
+  int rc;
+  const long long a_rows = g->a_rows > 0 ? g->a_rows : (long long)g->M + taps - 1;
+  if (!p.a_mn) rc = bf::make_map(&ma, g->A, g->K, a_rows, g->lda, bf::BM);
+  else rc = bf::make_map(&ma, g->A, g->M, g->K, g->lda, 64);
+  if (rc) return rc;
+  if (!p.b_mn) rc = bf::make_map(&mb, g->B, (long long)taps * g->K, g->N, g->ldb, bn);
+  else rc = bf::make_map(&mb, g->B, g->N, g->K, g->ldb, 64);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bn == 256 ? bf::launch<256>(ma, mb, p, s) : bf::launch<128>(ma, mb, p, s);
+}
+
+extern "C" int tts_gemm_bf16_status(void) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, bf::g_err, sizeof(int)) != cudaSuccess) return -1;
+  return v;
+}

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
 TTS_MAX_LAYERS = 16
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -25,6 +25,30 @@ class GemmEpilogue(C.Structure):
                 ("rows_per_batch", C.c_int32), ("valid_rows", C.c_int32), ("out_rows_per_batch", C.c_int32),
                 ("out_row_offset", C.c_int32), ("head_dim", C.c_int32), ("n_heads", C.c_int32),
                 ("head_rows", C.c_int32), ("out_v", C.c_void_p)]
+
+
+class GemmBf16(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32), ("a_rows", C.c_int64),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("out_bf16", C.c_int32),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("taps", C.c_int32), ("split_k", C.c_int32),
+                ("bias", C.c_void_p), ("act", C.c_int32), ("alpha", C.c_float),
+                ("residual", C.c_void_p), ("ldr", C.c_int64),
+                ("drop_p", C.c_float), ("seed", C.c_uint64), ("rng_stream", C.c_uint32),
+                ("gate", C.c_void_p), ("ldg", C.c_int64), ("gate_scale", C.c_float),
+                ("row_len", C.c_void_p), ("rows_per_batch", C.c_int32), ("valid_rows", C.c_int32),
+                ("out_rows_per_batch", C.c_int32), ("out_row_offset", C.c_int32)]
+
+
+class AttnTrain(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ldq", C.c_int64), ("ldk", C.c_int64),
+                ("ldv", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
+                ("batch", C.c_int32), ("n_heads", C.c_int32), ("tq", C.c_int32), ("tk", C.c_int32),
+                ("head_dim", C.c_int32), ("causal", C.c_int32), ("key_len", C.c_void_p),
+                ("drop_p", C.c_float), ("seed", C.c_uint64), ("rng_stream", C.c_uint32),
+                ("d_out", C.c_void_p), ("lddo", C.c_int64), ("delta", C.c_void_p),
+                ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64), ("lddk", C.c_int64),
+                ("lddv", C.c_int64)]
 
 
 class DecLayerWeights(C.Structure):
@@ -59,6 +83,30 @@ _EXPORTS = {
     "tts_gemm_nt": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                               C.c_int32, C.c_int32, C.POINTER(GemmEpilogue), C.c_void_p]),
     "tts_gemm_use_tensor_cores": (C.c_int, [C.c_int]),
+    "tts_gemm_bf16": (C.c_int, [C.POINTER(GemmBf16), C.c_void_p]),
+    "tts_gemm_bf16_status": (C.c_int, []),
+    "tts_attn_train_fwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
+    "tts_attn_train_bwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
+    "tts_ln_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tts_ln_bwd_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tts_ln_bwd_scratch_floats": (C.c_size_t, [C.c_int32]),
+    "tts_dropout_cast": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tts_multi_cast_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "tts_multi_chunk_elems": (C.c_int32, []),
+    "tts_embed_train_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "tts_embed_train_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "tts_shift_pe_train_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "tts_shift_pe_train_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "tts_colsum_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "tts_sum_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tts_rowdot_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "tts_bn_scratch_floats": (C.c_size_t, [C.c_int32]),
+    "tts_bn_train_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tts_bn_train_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tts_pad_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tts_loss_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tts_sumsq_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "tts_adam_multi": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "tts_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_embed_pe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 8
+#define TTS_ABI_VERSION 9
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -118,6 +118,120 @@ int tts_attention(const float* q, int32_t ldq, const float* k, int32_t ldk, cons
                   int32_t ldv, float* ctx, float* align, int32_t batch, int32_t n_heads,
                   int32_t tq, int32_t tk, int32_t head_dim, float q_scale, int32_t causal,
                   const int32_t* key_len, void* stream);
+
+/* ---- teacher-forced TRAINING path: bf16 tensor-core GEMM ---------------------------------------
+ * C[M,N] = epilogue( sum over taps t, k < K of A[m + t][k] * B[n][t*K + k] ), bf16 operands, fp32 accumulation in
+ * tensor memory (tcgen05.mma kind::f16, TMA-fed).  Replaces, for the training step of train.py:171-174, the forward,
+ * input-gradient and weight-gradient products of every nn.Linear / nn.Conv1d (transformer/attention.py:43-47,63-68,
+ * 119; modules.py:11-19; tacotron.py:50-52,56-64,78,85,112,114) that autograd runs as fp32 cuBLAS / cuDNN calls.
+ *   operands: bf16 bit patterns (uint16_t).  K-major = row-major [rows][K] (ld = row stride in elements);
+ *             MN-major = row-major [K][rows].  dgrad passes the weight [N][K] as the MN-major B of dX = dY W; wgrad
+ *             passes dY [R][N] and X [R][K] as MN-major A and B of dW = dY^T X (contraction over the R rows).
+ *   epilogue (in this order): alpha; + bias[n]; ReLU (act 1); * gate_scale where gate[m][n] > 0 else 0 (backward of
+ *             ReLU+dropout through the saved bf16 forward output); Philox dropout(drop_p) keyed by (seed, rng_stream,
+ *             output element); + residual[m][n] (fp32); rows at or beyond row_len[b] zeroed; row remapping exactly
+ *             as TtsGemmEpilogue (the k5 Conv1d over a zero-padded buffer: taps = 5, K = C_in).
+ *   split_k > 1: the contraction is cut into split_k slices reduced with fp32 atomics into a ZERO-INITIALISED fp32 C
+ *             (weight gradients: tiny outputs, contraction over all B x T rows).
+ * Base pointers and row strides of A and B must be 16-byte aligned (ld % 8 == 0). */
+typedef struct TtsGemmBf16 {
+  const uint16_t* A; int64_t lda; int32_t a_mn_major; int64_t a_rows;   /* a_rows: rows of the K-major A buffer (0 = M + taps - 1) */
+  const uint16_t* B; int64_t ldb; int32_t b_mn_major;
+  void* C; int64_t ldc; int32_t out_bf16;                              /* C: bf16 (out_bf16 != 0) or fp32 */
+  int32_t M, N, K, taps, split_k;
+  const float* bias; int32_t act; float alpha;                          /* alpha 0 = 1 */
+  const float* residual; int64_t ldr;
+  float drop_p; uint64_t seed; uint32_t rng_stream;
+  const uint16_t* gate; int64_t ldg; float gate_scale;
+  const int32_t* row_len; int32_t rows_per_batch, valid_rows, out_rows_per_batch, out_row_offset;
+} TtsGemmBf16;
+int tts_gemm_bf16(const TtsGemmBf16* g, void* stream);
+/* 0 = no barrier timeout has been recorded by any tts_gemm_bf16 kernel so far (synchronous device read) */
+int tts_gemm_bf16_status(void);
+
+/* Flash-style attention of the training path on bf16 tensor cores (mma.sync m16n8k16), masks from indices / lengths,
+ * Philox dropout on the weights regenerated in backward; nothing of size [B,H,Tq,Tk] is written.  Replaces
+ * transformer/attention.py:72-122 (minus the projections) and its autograd backward.  q/k/v/out/dq/dk/dv are bf16,
+ * addressed as ptr[(b*rows + r)*ld + h*head_dim + d]; lse / delta are fp32 [B][H][Tq] (lse in the log2 domain).
+ * causal: key j allowed iff j <= i (modules.py:112); key_len: key j allowed iff j < key_len[b] (modules.py:50-52). */
+typedef struct TtsAttnTrain {
+  const uint16_t *q, *k, *v; int64_t ldq, ldk, ldv;
+  uint16_t* out; int64_t ldo;
+  float* lse;
+  int32_t batch, n_heads, tq, tk, head_dim, causal;
+  const int32_t* key_len;
+  float drop_p; uint64_t seed; uint32_t rng_stream;
+  /* backward only */
+  const uint16_t* d_out; int64_t lddo;
+  float* delta;
+  uint16_t *dq, *dk, *dv; int64_t lddq, lddk, lddv;
+} TtsAttnTrain;
+int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream);
+int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream);
+
+/* LayerNorm of the training path (modules.py:36,43,47,88,95,102,106): y (bf16, feeds the next GEMM) = LN(x) gamma + beta,
+ * rows at or beyond row_len zeroed (modules.py:144); mean / rstd saved for backward. */
+int tts_ln_fwd_train(const float* x, uint16_t* y, int64_t ldy, const float* gamma, const float* beta, float* mean,
+                     float* rstd, int32_t rows, int32_t channels, float eps, const int32_t* row_len,
+                     int32_t rows_per_batch, void* stream);
+/* dx = LN'(dy) (+ dres: the gradient arriving over the residual connection), dgamma, dbeta.  scratch: tts_ln_bwd_scratch_floats. */
+int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x, const float* mean, const float* rstd,
+                     const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, float* scratch,
+                     int32_t rows, int32_t channels, const int32_t* row_len, int32_t rows_per_batch, void* stream);
+size_t tts_ln_bwd_scratch_floats(int32_t channels);
+/* dst (bf16) = keep(seed, stream, element) ? src / (1 - p) : 0: the backward of an epilogue dropout, or (p = 0) a cast. */
+int tts_dropout_cast(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int32_t channels,
+                     float drop_p, uint64_t seed, uint32_t rng_stream, const int32_t* row_len, int32_t rows_per_batch,
+                     void* stream);
+/* fp32 -> bf16 copies of many tensors in one launch; table_dev: device array of {const float* src; uint16_t* dst;
+ * int64 n; int64 first_chunk} with chunks of tts_multi_chunk_elems() elements. */
+int tts_multi_cast_bf16(const void* table_dev, int32_t n_entries, int64_t n_chunks, void* stream);
+int32_t tts_multi_chunk_elems(void);
+/* Encoder / decoder prologues with dropout and their backward (tacotron.py:34; modules.py:49-55,114-120). */
+int tts_embed_train_fwd(const int64_t* ids, const int32_t* lengths, const float* embed, const float* pe,
+                        const float* pe_scale, float* out, int32_t batch, int32_t seq, int32_t channels, int32_t vocab,
+                        float drop_p, uint64_t seed, uint32_t rng_stream, void* stream);
+int tts_embed_train_bwd(const float* dx, const int64_t* ids, const int32_t* lengths, const float* pe, float* d_embed,
+                        float* d_pe_scale, int32_t batch, int32_t seq, int32_t channels, int32_t vocab, float drop_p,
+                        uint64_t seed, uint32_t rng_stream, void* stream);
+int tts_shift_pe_train_fwd(const float* pre, const int32_t* lengths, const float* pe, const float* pe_scale, float* out,
+                           int32_t batch, int32_t frames, int32_t channels, float drop_p, uint64_t seed,
+                           uint32_t rng_stream, void* stream);
+int tts_shift_pe_train_bwd(const float* dx, const int32_t* lengths, const float* pe, uint16_t* dpre, float* d_pe_scale,
+                           int32_t batch, int32_t frames, int32_t channels, float drop_p, uint64_t seed,
+                           uint32_t rng_stream, void* stream);
+/* out[c] += sum_r row_weight[r] * x[r][c] (bias gradients; the stop head's weight gradient); out must be initialised. */
+int tts_colsum_bf16(const uint16_t* x, int64_t ldx, const float* row_weight, float* out, int64_t rows, int32_t channels,
+                    void* stream);
+int tts_sum_f32(const float* x, int64_t n, float* out, void* stream);
+/* stop head (tacotron.py:114-115): out[r] = (x[r] . w + bias) masked by row_len. */
+int tts_rowdot_bf16(const uint16_t* x, int64_t ldx, const float* w, const float* bias, const int32_t* row_len,
+                    int32_t rows_per_batch, float* out, int64_t rows, int32_t k, void* stream);
+/* Postnet BatchNorm1d in train() mode: batch statistics over all B x T positions, running-stat update, tanh, dropout,
+ * length mask into the next layer's zero-padded bf16 input (tacotron.py:83-89). */
+size_t tts_bn_scratch_floats(int32_t channels);
+int tts_bn_train_fwd(const float* z, const float* gamma, const float* beta, float* mean, float* invstd,
+                     float* running_mean, float* running_var, int64_t* num_batches, float momentum, float eps,
+                     int32_t act_tanh, float drop_p, uint64_t seed, uint32_t rng_stream, const int32_t* lengths,
+                     int32_t batch, int32_t frames, int32_t channels, uint16_t* out_pad, float* out_f32,
+                     const float* residual, float* scratch, void* stream);
+int tts_bn_train_bwd(const float* z, const float* dout, const float* gamma, const float* beta, const float* mean,
+                     const float* invstd, int32_t act_tanh, float drop_p, uint64_t seed, uint32_t rng_stream,
+                     const int32_t* lengths, int32_t mask_rows, int32_t batch, int32_t frames, int32_t channels,
+                     uint16_t* dz_pad, float* dgamma, float* dbeta, float* scratch, void* stream);
+int tts_pad_cast_bf16(const float* x, const int32_t* lengths, uint16_t* out, int32_t batch, int32_t frames,
+                      int32_t channels, int32_t only_pads, void* stream);
+/* compute_loss (tacotron.py:136-158) without the L2 term: sums3 = {sum mse_bef, sum mse_aft, sum bce} over valid frames,
+ * per-sample after-loss sums, and the gradients of bef_loss + aft_loss + stop_loss w.r.t. the three model outputs. */
+int tts_loss_train(const float* mel_bef, const float* mel_aft, const float* stop_logits, const float* targets,
+                   const int32_t* lengths, const int32_t* total_len, int32_t batch, int32_t frames, int32_t n_mels,
+                   float pos_weight, float* sums3, float* aft_per_sample, float* d_bef, float* d_aft, float* d_stop,
+                   void* stream);
+/* Multi-tensor L2 term and fused Adam over a device table of {float* p; const float* g; float* m; float* v; int64 n;
+ * int64 first_chunk; int32 decay; int32 pad} (train.py:130-131,188; tacotron.py:144-146). */
+int tts_sumsq_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, float* out, void* stream);
+int tts_adam_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, float lr, float beta1, float beta2,
+                   float eps, int64_t step, float reg_weight, float grad_scale, void* stream);
 
 /* ---- autoregressive decode (the hot path) ------------------------------------------------ */
 
