@@ -32,21 +32,47 @@ def engine_for(module, prefix, hparams):
     return eng
 
 
+_TRAIN_ENGINES = weakref.WeakKeyDictionary()
+
+
+def train_engine_for(module, prefix, hparams):
+    """The TrainEngine (bf16 tensor-core forward + backward) serving `module`; same keying as engine_for."""
+    from tts_b200.engine_train import TrainEngine
+    tensors = dict(module.named_parameters())
+    tensors.update(dict(module.named_buffers()))
+    first = next(iter(tensors.values()))
+    if not first.is_cuda:
+        raise RuntimeError("tts_b200: the model is on %s; this implementation has no CPU path - move it to a CUDA "
+                           "device (model.to('cuda'))" % first.device)
+    hit = _TRAIN_ENGINES.get(module)
+    if hit is not None and hit[1] == first.device and all(hit[0].w.get(prefix + k) is v for k, v in tensors.items()):
+        return hit[0]
+    eng = TrainEngine({prefix + k: v for k, v in tensors.items()}, hparams, first.device)
+    _TRAIN_ENGINES[module] = (eng, first.device)
+    return eng
+
+
 def needs_backward(module, *inputs):
-    """True when this call is part of a training step (train() mode with autograd recording).
-    Inference calls (eval(), or anything under torch.no_grad() such as synthesize.eval_batch with
-    its `decoder.train()`) are served; their outputs carry no autograd graph."""
-    if not (torch.is_grad_enabled() and module.training):
+    """True when autograd is recording and something this call touches requires a gradient - in train() AND in eval()
+    mode (fine-tuning with frozen dropout must not silently return detached outputs).  Calls under torch.no_grad()
+    (synthesize.eval_batch, also with its `decoder.train()`) are inference calls."""
+    if not torch.is_grad_enabled():
         return False
     return any(p.requires_grad for p in module.parameters()) or any(
         torch.is_tensor(t) and t.requires_grad for t in inputs)
 
 
 def no_backward(module, what, *inputs):
+    """The differentiable entry points are Tacotron / Encoder / Decoder / Postnet (tts_b200.autograd); the smaller
+    building blocks are inference-only when called on their own."""
     if needs_backward(module, *inputs):
         raise NotImplementedError(
-            "tts_b200: %s has no backward pass yet (teacher-forced training kernels are the next milestone, see "
-            "DESIGN.md); call it under torch.no_grad()" % what)
+            "tts_b200: %s called on its own has no backward pass (the differentiable entry points are Tacotron, Encoder, "
+            "Decoder and Postnet); call it under torch.no_grad() or freeze its parameters" % what)
+
+
+def param_names(module, prefix):
+    return [prefix + n for n, _ in module.named_parameters()]
 
 
 class FFNLayer(nn.Module):

@@ -15,7 +15,9 @@ from torch.nn import functional as F
 from tts_b200 import _native as N
 from tts_b200 import ops
 from transformer.common import impute, mask_reduce, truncated_normal, variance_scaling_initializer
-from transformer.modules import TransformerDecoder, TransformerEncoder, engine_for, no_backward
+from tts_b200 import autograd as AG
+from transformer.modules import (TransformerDecoder, TransformerEncoder, engine_for, needs_backward, no_backward,
+                                 param_names, train_engine_for)
 
 
 class Encoder(nn.Module):
@@ -50,7 +52,10 @@ class Encoder(nn.Module):
 
     def forward(self, inputs, input_lengths, input_spk_ids=None, input_language_vecs=None):
         """[B,S] token ids -> encoder memory [B,S,encoder_hidden(+spk)(+lang)] (reference tacotron.py:33-44)."""
-        no_backward(self, "Encoder")
+        if needs_backward(self):   # training step: bf16 tensor-core forward, hand-written backward behind autograd
+            eng = train_engine_for(self, "encoder.", self.hparams)
+            return AG.EncoderFn.apply(eng, param_names(self, "encoder."), self.training, inputs, input_lengths, input_spk_ids,
+                                      input_language_vecs, *self.parameters())
         eng = engine_for(self, "encoder.", self.hparams)
         if self.training and self.hparams.transformer_dropout_rate > 0:
             eng.warn_dropout("Encoder")
@@ -91,12 +96,22 @@ class Postnet(nn.Module):
             self.batchnorm_layers.append(nn.BatchNorm1d(cout))
 
     def forward(self, inputs, input_lengths):
-        """[B,T,M] -> residual [B,T,M]: 5 x (impute, conv k5, BatchNorm, tanh) (reference tacotron.py:81-90)."""
-        no_backward(self, "Postnet", inputs)
-        if self.training:
-            raise NotImplementedError("tts_b200: Postnet in train() mode (batch-statistics BatchNorm + dropout) is "
-                                      "part of the training path, not built yet; call .eval()")
-        return engine_for(self, "postnet.", self.hparams).postnet(inputs, input_lengths)
+        """[B,T,M] -> residual [B,T,M]: 5 x (impute, conv k5, BatchNorm, tanh, dropout) (reference tacotron.py:81-90)."""
+        return self._run(inputs, input_lengths, add_input=False)
+
+    def _run(self, inputs, input_lengths, add_input):
+        if self.training or needs_backward(self, inputs):
+            # batch-statistics BatchNorm + dropout (train() mode), differentiable when autograd is recording
+            if not self.training:
+                raise NotImplementedError("tts_b200: a differentiable Postnet with frozen (eval-mode) BatchNorm statistics "
+                                          "is not built; call postnet.train() or run under torch.no_grad()")
+            eng = train_engine_for(self, "postnet.", self.hparams)
+            if needs_backward(self, inputs):
+                return AG.PostnetFn.apply(eng, param_names(self, "postnet."), True, add_input, inputs, input_lengths,
+                                          *self.parameters())
+            with torch.no_grad():
+                return eng.postnet_fwd(inputs, input_lengths, True, add_input)[0]
+        return engine_for(self, "postnet.", self.hparams).postnet(inputs, input_lengths, add_input=add_input)
 
 
 class Decoder(nn.Module):
@@ -154,7 +169,13 @@ class Decoder(nn.Module):
 
     def forward(self, encoder_outputs, input_lengths, targets, target_lengths, leave_one=False):
         """-> (mels [B,T,M], stop_logits [B,T], {'self': [...], 'encdec': [...]})  (reference tacotron.py:107-116)."""
-        no_backward(self, "Decoder", encoder_outputs, targets)
+        if needs_backward(self, encoder_outputs):
+            # training step.  The attention maps are not materialised (flash attention; train.py never reads them):
+            # the alignment lists are returned empty (SURVEY.md §7.8).
+            eng = train_engine_for(self, "decoder.", self.hparams)
+            mels, stop = AG.DecoderFn.apply(eng, param_names(self, "decoder."), self.training, leave_one, encoder_outputs,
+                                            input_lengths, targets, target_lengths, *self.parameters())
+            return mels, stop, {"self": [], "encdec": []}
         eng = engine_for(self, "decoder.", self.hparams)
         if self.training and (self.hparams.decoder_dropout_rate > 0 or self.hparams.transformer_dropout_rate > 0):
             eng.warn_dropout("Decoder")
@@ -177,35 +198,46 @@ class Tacotron(nn.Module):
         """Teacher-forced pass (reference tacotron.py:126-133)."""
         enc_outputs = self.encoder(inputs, input_lengths, input_spk_ids, input_language_vecs)
         mel_bef, stop_logits, alignments = self.decoder(enc_outputs, input_lengths, mel_targets, target_lengths)
-        no_backward(self.postnet, "Postnet", mel_bef)
-        if self.postnet.training:
-            raise NotImplementedError("tts_b200: Postnet in train() mode is part of the training path, not built yet")
-        mel_aft = engine_for(self.postnet, "postnet.", self.postnet.hparams).postnet(mel_bef, target_lengths,
-                                                                                   add_input=True)
+        # mel_aft = mel_bef + postnet(mel_bef): the add is fused into the last Postnet layer's epilogue
+        mel_aft = self.postnet._run(mel_bef, target_lengths, add_input=True)
         return {"mel_bef": mel_bef, "mel_aft": mel_aft, "stop_logits": stop_logits, "alignments": alignments}
+
+
+def _l2_selected(model):
+    """The tensors the reference's L2 term covers, selected by name exactly as tacotron.py:144-146."""
+    return [p for n, p in model.named_parameters()
+            if "weight" in n and "layer_norm" not in n and "batchnorm" not in n
+            and "encoder.speaker_embed" not in n and "encoder.embed" not in n]
+
+
+_L2_TABLES = {}
 
 
 def compute_loss(model, mel_targets, target_lengths, outputs, hparams):
     """The 7-key loss dict of the reference (tacotron.py:136-158): length-masked MSE before/after the
     Postnet, per-sample after-loss, stop BCE (pos_weight 5) and L2 on the name-selected weights.
-    Host-side torch ops for now: fusing it is SURVEY.md §8(f) rank 2."""
-    def frame_mse(pred):
-        return ((pred - mel_targets) ** 2).mean(-1)
-
-    bef, aft = frame_mse(outputs["mel_bef"]), frame_mse(outputs["mel_aft"])
-    bef_loss = mask_reduce(bef, target_lengths)
-    aft_losses = mask_reduce(aft, target_lengths, per_sample=True)
-    aft_loss = mask_reduce(aft, target_lengths)
-    decayed = [p for n, p in model.named_parameters()
-               if "weight" in n and "layer_norm" not in n and "batchnorm" not in n
-               and "encoder.speaker_embed" not in n and "encoder.embed" not in n]
-    l2 = hparams.reg_weight * sum((p ** 2).sum() / 2 for p in decayed)
-    frames = torch.arange(mel_targets.shape[1], device=target_lengths.device)
-    stop_target = (frames[None, :] == (target_lengths[:, None] - 1)).float()
-    pos_weight = torch.full((1,), 5.0, device=stop_target.device)
-    ce = F.binary_cross_entropy_with_logits(outputs["stop_logits"], stop_target, reduction="none",
-                                            pos_weight=pos_weight)
-    stop_loss = mask_reduce(ce, target_lengths)
+    On CUDA the masked losses and their gradients come from ONE fused kernel (tts_loss_train) and the L2 term from one
+    multi-tensor launch; both are differentiable through tts_b200.autograd.  `hparams.l2_in_optimizer = True` (not a
+    reference key) reports the L2 value without a graph, for optimizers that apply reg_weight * W themselves
+    (tts_b200.optim.FusedAdam: exactly the same gradient)."""
+    if not outputs["mel_bef"].is_cuda:
+        raise RuntimeError("tts_b200: compute_loss expects CUDA tensors (no CPU path)")
+    bef_loss, aft_loss, stop_loss, aft_losses = AG.LossFn.apply(outputs["mel_bef"], outputs["mel_aft"], outputs["stop_logits"],
+                                                                mel_targets, target_lengths)
+    decayed = _l2_selected(model)
+    key = tuple(p.data_ptr() for p in decayed)
+    hit = _L2_TABLES.get(id(model))
+    if hit is None or hit[0] != key:
+        from tts_b200 import train_ops as TO
+        tab = TO.MultiTable(decayed[0].device)
+        tab.build_opt([(p.detach(), None, None, None, True) for p in decayed])
+        hit = (key, tab)
+        _L2_TABLES[id(model)] = hit
+    if getattr(hparams, "l2_in_optimizer", False):
+        with torch.no_grad():
+            l2 = AG.L2Fn.apply(float(hparams.reg_weight), hit[1], *decayed)
+    else:
+        l2 = AG.L2Fn.apply(float(hparams.reg_weight), hit[1], *decayed)
     return {"loss": bef_loss + aft_loss + l2 + stop_loss, "bef_loss": bef_loss, "aft_loss": aft_loss,
             "aft_losses": aft_losses, "mse_loss": (bef_loss + aft_loss) / 2, "l2": l2, "stop_loss": stop_loss}
 

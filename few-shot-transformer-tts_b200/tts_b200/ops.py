@@ -152,7 +152,7 @@ def attention(q, ldq, k, ldk, v, ldv, batch, n_heads, tq, tk, head_dim, causal, 
 # ---------------------------------------------------------------------------------------------------------------------
 # training path (bf16 operands, fp32 accumulation): include/tts_b200.h "teacher-forced TRAINING path"
 # ---------------------------------------------------------------------------------------------------------------------
-def gemm_bf16(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None, out_dtype=torch.bfloat16, bias=None,
+def gemm_bf16(a, b, *, a_mn=False, b_mn=False, m=None, n=None, k=None, out=None, out_dtype=torch.bfloat16, bias=None,
               act=ACT_NONE, alpha=1.0, residual=None, drop_p=0.0, seed=0, rng_stream=0, gate=None, gate_scale=1.0,
               taps=1, split_k=1, row_len=None, rows_per_batch=0, valid_rows=0, out_rows_per_batch=0, out_row_offset=0,
               out_rows=None, a_rows=0):
@@ -160,23 +160,20 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, M=None, N=None, K=None, out=None,
     operands are [rows][K], MN-major ones ([a_mn] / [b_mn]) are [K][rows].  Returns the output tensor."""
     lib = N.load()
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(-1) == 1 and b.stride(-1) == 1
-    if M is None:
-        M = a.shape[1] if a_mn else a.shape[0]
-    if N is None:
-        N = b.shape[1] if b_mn else b.shape[0]
-    if K is None:
-        K = a.shape[0] if a_mn else a.shape[1]
+    M = m if m is not None else (a.shape[1] if a_mn else a.shape[0])
+    Nn = n if n is not None else (b.shape[1] if b_mn else b.shape[0])
+    K = k if k is not None else (a.shape[0] if a_mn else a.shape[1])
     if out is None:
         rows = out_rows if out_rows is not None else M
         if split_k > 1:
-            out = torch.zeros((rows, N), device=a.device, dtype=torch.float32)
+            out = torch.zeros((rows, Nn), device=a.device, dtype=torch.float32)
         else:
-            out = torch.empty((rows, N), device=a.device, dtype=out_dtype)
+            out = torch.empty((rows, Nn), device=a.device, dtype=out_dtype)
     g = N.GemmBf16()
     g.A, g.lda, g.a_mn_major, g.a_rows = a.data_ptr(), a.stride(0), 1 if a_mn else 0, a_rows
     g.B, g.ldb, g.b_mn_major = b.data_ptr(), b.stride(0), 1 if b_mn else 0
     g.C, g.ldc, g.out_bf16 = out.data_ptr(), out.stride(0), 1 if out.dtype == torch.bfloat16 else 0
-    g.M, g.N, g.K, g.taps, g.split_k = M, N, K, taps, split_k
+    g.M, g.N, g.K, g.taps, g.split_k = M, Nn, K, taps, split_k
     g.bias, g.act, g.alpha = N.ptr(bias), act, alpha
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.stride(-1) == 1

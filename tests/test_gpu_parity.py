@@ -552,6 +552,7 @@ def test_module_api_unchanged_synthesis_loop(tiny_params, golden_dir, ops):
     p["decoder.stop_net.bias"] = torch.tensor([float(z["stop_bias"])])
     m.load_state_dict(p, strict=True)
     m.to(DEV).eval()
+    m.decoder.record_alignments = "all"   # the reference's full structure (default: 'encdec' only, 'self' list empty)
     batch = {k: (_dev(v) if torch.is_tensor(v) else v)
              for k, v in O.synth_batch(cfg, batch=5, text_len=24, n_frames=4, seed=7, ragged=True).items()}
     out = _eval_loop_like_synthesize(m, batch, hp.max_generation_frames, cfg.num_mels)

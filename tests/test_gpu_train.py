@@ -1,0 +1,186 @@
+"""GPU parity of the teacher-forced TRAINING step (train.py:171-174: forward, compute_loss, loss.backward(), Adam) through
+the drop-in transformer/ API on the bf16 tensor-core kernels.
+
+References: (1) tests/golden/tiny_forward_loss_grad.npz - the REAL reference's train()-mode forward, loss and gradients
+(dropout 0, batch-statistics BatchNorm); (2) the CPU oracle differentiated by torch autograd in fp64, for every
+parameter gradient element-wise.  Tolerances (stated per tensor below): the kernels compute in bf16 with fp32
+accumulation while the reference is fp32, so outputs agree to ~1e-2 absolute on O(1) mel frames and gradients to a few
+percent of their Frobenius norm (SURVEY.md hard part 11: "report, don't pretend 1e-3")."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tts_oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    return True
+
+
+def _model(cfg, params, drop=False):
+    from tts_b200.config import hparams_from
+    from transformer import tacotron
+    hp = hparams_from(cfg)
+    if not drop:
+        hp.transformer_dropout_rate = 0.0
+        hp.decoder_dropout_rate = 0.0
+    m = tacotron.Tacotron(hp)
+    m.load_state_dict(params, strict=True)
+    return m.to(DEV), hp, tacotron
+
+
+def _batch(cfg, **kw):
+    b = O.synth_batch(cfg, **kw)
+    return b, {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+
+def _oracle_grads(cfg, params, batch):
+    p64 = {k: (v.double().requires_grad_() if v.dtype.is_floating_point else v) for k, v in params.items()}
+    out = O.tacotron_forward(p64, cfg, batch, dtype=torch.float64, batch_stats=True)
+    loss = O.compute_loss(p64, cfg, batch["mel_targets"].double(), batch["target_lengths"], out)
+    loss["loss"].backward()
+    return out, loss, {k: v.grad for k, v in p64.items() if v.dtype.is_floating_point and v.grad is not None}
+
+
+def test_tiny_train_step_vs_reference_golden_and_oracle(built, tiny_params, golden_dir):
+    cfg, params = tiny_params
+    z = np.load(os.path.join(golden_dir, "tiny_forward_loss_grad.npz"))
+    m, hp, tacotron = _model(cfg, params)
+    cpu_batch, batch = _batch(cfg, batch=3, text_len=20, n_frames=30, seed=6, ragged=True)
+    m.train()
+    out = m(**batch)
+    losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
+    losses["loss"].backward()
+    assert out["alignments"] == {"self": [], "encdec": []}
+    # forward / loss vs the REAL reference (train() mode, dropout 0)
+    e_aft = float((out["mel_aft"].detach().cpu() - torch.from_numpy(z["train_mel_aft"])).abs().max())
+    e_loss = abs(float(losses["loss"]) - float(z["train_loss"])) / float(z["train_loss"])
+    print("tiny train: max|mel_aft diff| %.3e, relative loss error %.3e" % (e_aft, e_loss))
+    assert e_aft < 5e-2 and e_loss < 1e-2
+    got = {n: p.grad for n, p in m.named_parameters()}
+    assert all(g is not None for g in got.values()), [n for n, g in got.items() if g is None]
+    norms = dict(zip([str(s) for s in z["grad_names"]], z["grad_norms"]))
+    worst = 0.0
+    for n, g in got.items():
+        rel = abs(float(g.double().norm()) - norms[n]) / max(norms[n], 1e-8)
+        worst = max(worst, rel)
+        assert rel < 6e-2, (n, rel, norms[n])
+    g0 = got["decoder.prenet.dense0.weight"].cpu().double()
+    ref0 = torch.from_numpy(z["grad_prenet_dense0"]).double()
+    assert float((g0 - ref0).norm() / ref0.norm()) < 6e-2
+    # element-wise vs the fp64 oracle, every parameter
+    _, oloss, ograds = _oracle_grads(cfg, params, cpu_batch)
+    rels = {}
+    for n, g in got.items():
+        ref = ograds[n]
+        rels[n] = float((g.cpu().double() - ref).norm() / max(float(ref.norm()), 1e-12))
+    bad = {n: r for n, r in rels.items() if r > 6e-2}
+    print("tiny train: worst |grad - ref|_F / |ref|_F = %.3e (%s); worst norm error vs reference %.3e"
+          % (max(rels.values()), max(rels, key=rels.get), worst))
+    assert not bad, bad
+    for k in ("bef_loss", "aft_loss", "stop_loss", "l2"):
+        assert abs(float(losses[k]) - float(oloss[k])) < 2e-2 * max(abs(float(oloss[k])), 1e-3), k
+    assert float((losses["aft_losses"].cpu().double() - oloss["aft_losses"]).abs().max()) < 3e-2
+
+
+def test_full_model_train_forward_backward_runs_and_matches_oracle(built, full_params):
+    """Full-size model (83.5 M parameters), ragged batch, dropout 0: outputs vs the oracle's train()-mode forward and the
+    gradient of the largest tensors vs fp64 autograd."""
+    cfg, params = full_params
+    m, hp, tacotron = _model(cfg, params)
+    cpu_batch, batch = _batch(cfg, batch=3, text_len=40, n_frames=64, seed=2, ragged=True)
+    m.train()
+    out = m(**batch)
+    losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
+    losses["loss"].backward()
+    want, oloss, ograds = _oracle_grads(cfg, params, cpu_batch)
+    e_bef = float((out["mel_bef"].detach().cpu().double() - want["mel_bef"].detach()).abs().max())
+    e_aft = float((out["mel_aft"].detach().cpu().double() - want["mel_aft"].detach()).abs().max())
+    e_stop = float((out["stop_logits"].detach().cpu().double() - want["stop_logits"].detach()).abs().max())
+    rel_loss = abs(float(losses["loss"]) - float(oloss["loss"])) / float(oloss["loss"])
+    print("full train fwd: mel_bef %.3e mel_aft %.3e stop %.3e, loss rel %.3e" % (e_bef, e_aft, e_stop, rel_loss))
+    assert e_bef < 8e-2 and e_aft < 1.5e-1 and e_stop < 8e-2 and rel_loss < 2e-2
+    rels = {}
+    for n, p in m.named_parameters():
+        ref = ograds[n]
+        rels[n] = float((p.grad.cpu().double() - ref).norm() / max(float(ref.norm()), 1e-12))
+    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:5]
+    print("full train grads: worst relative errors", [(n, "%.3f" % r) for n, r in worst])
+    assert max(rels.values()) < 1.2e-1, worst
+    assert np.median(list(rels.values())) < 3e-2
+
+
+def test_dropout_modes_and_determinism(built, tiny_params):
+    """train() with dropout: outputs change from call to call (new seed per forward) but backward replays the forward's
+    masks (gradient check by finite differences is meaningless in bf16; instead: a second backward through a retained
+    forward with the same seed reproduces the gradients bit for bit).  eval() + grad: dropout off, BatchNorm running
+    statistics -> NotImplementedError for the Postnet, encoder/decoder differentiable."""
+    cfg, params = tiny_params
+    m, hp, tacotron = _model(cfg, params, drop=True)
+    _, batch = _batch(cfg, batch=3, text_len=20, n_frames=30, seed=6, ragged=True)
+    m.train()
+    a = m(**batch)["mel_bef"].detach().clone()
+    b = m(**batch)["mel_bef"].detach().clone()
+    assert not torch.equal(a, b)
+    eng = tacotron.train_engine_for(m.decoder, "decoder.", hp)
+    mem = m.encoder(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"]).detach()
+    step = eng._step
+    gs = []
+    for _ in range(2):
+        eng._step = step            # same seed -> same dropout masks
+        m.zero_grad()
+        mels, stop, _ = m.decoder(mem, batch["input_lengths"], batch["mel_targets"], batch["target_lengths"])
+        (mels.square().mean() + stop.square().mean()).backward()
+        gs.append({n: p.grad.clone() for n, p in m.decoder.named_parameters()})
+    assert all(torch.equal(gs[0][n], gs[1][n]) for n in gs[0])
+    m.eval()
+    with pytest.raises(NotImplementedError):
+        m(**batch)
+    mels, _, _ = m.decoder(mem, batch["input_lengths"], batch["mel_targets"], batch["target_lengths"])
+    assert mels.requires_grad
+    with torch.no_grad():
+        ev = m(**batch)
+    assert not ev["mel_bef"].requires_grad and ev["alignments"]["encdec"]
+
+
+def test_training_loop_like_train_py_reduces_the_loss(built, tiny_params):
+    """The loop body of train.py:165-191 (forward, compute_loss, zero_grad, backward, Adam step, LambdaLR) with torch.optim.Adam
+    on our parameters, then the same with the fused optimizer (L2 folded in): the loss goes down and both agree."""
+    from tts_b200.optim import FusedAdam, l2_selected_names
+    cfg, params = tiny_params
+    _, batch = _batch(cfg, batch=4, text_len=20, n_frames=40, seed=3, ragged=True)
+    curves = []
+    for fused in (False, True):
+        m, hp, tacotron = _model(cfg, params)
+        m.train()
+        hp.reg_weight = 1e-6
+        if fused:
+            hp.l2_in_optimizer = True
+            sel = l2_selected_names(m)
+            opt = FusedAdam(m.parameters(), lr=hp.max_lr, eps=hp.adam_eps, reg_weight=hp.reg_weight,
+                            l2_params=[p for n, p in m.named_parameters() if n in sel])
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=hp.max_lr, eps=hp.adam_eps)
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: tacotron.learning_rate_schedule(s, hp))
+        vals = []
+        for _ in range(12):
+            out = m(**batch)
+            losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
+            opt.zero_grad()
+            losses["loss"].backward()
+            opt.step()
+            sched.step()
+            vals.append(float(losses["loss"]))
+        curves.append(vals)
+    print("loss curves:", ["%.4f" % v for v in curves[0]], ["%.4f" % v for v in curves[1]])
+    assert curves[0][-1] < 0.8 * curves[0][0] and curves[1][-1] < 0.8 * curves[1][0]
+    assert abs(curves[0][-1] - curves[1][-1]) < 5e-2 * curves[0][0]

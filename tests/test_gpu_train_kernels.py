@@ -94,7 +94,7 @@ def test_gemm_bf16_epilogues(ops):
     lens = torch.tensor([3, 37, 0], dtype=torch.int32, device=DEV)
     got = ops.gemm_bf16(a, b, out_dtype=torch.float32, row_len=lens, rows_per_batch=111)
     mask = (torch.arange(111)[None, :] < lens.cpu()[:, None]).reshape(-1, 1)
-    assert _err(got, acc * mask) < 5e-4
+    assert _err(got, acc * mask.to(DEV)) < 5e-4
     assert _status() == 0
 
 
@@ -110,7 +110,7 @@ def test_gemm_bf16_conv5_taps(ops, B, T, cin, cout):
     wp = w.permute(0, 2, 1).reshape(cout, 5 * cin).contiguous()
     want = F.conv1d(x.double().transpose(1, 2), w.double(), padding=2).transpose(1, 2)
     M = B * (T + 4) - 4
-    got = ops.gemm_bf16(xpad.to(DEV).view(-1, cin), wp.to(DEV), M=M, K=cin, taps=5, out_dtype=torch.float32,
+    got = ops.gemm_bf16(xpad.to(DEV).view(-1, cin), wp.to(DEV), m=M, k=cin, taps=5, out_dtype=torch.float32,
                         rows_per_batch=T + 4, valid_rows=T, out_rows_per_batch=T, out_rows=B * T, a_rows=B * (T + 4))
     assert _err(got.view(B, T, cout), want) < 2e-3
     assert _status() == 0

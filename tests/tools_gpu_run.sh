@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 mode=${1:-tests}
 case $mode in
   tests)      # whole GPU suite
-    python -m pytest tests -m gpu -x -q -s 2>&1 | tail -60 > gpurun_out/r2_gputest.log; tail -5 gpurun_out/r2_gputest.log ;;
+    python -m pytest tests -m gpu -q -s > gpurun_out/r2_gputest_full.log 2>&1; grep -E "passed|failed|horizon|staggered|golden:|cfg5|tiny train|full train|loss curves|FAILED|Error" gpurun_out/r2_gputest_full.log | tail -40 ;;
   sanitize)   # compute-sanitizer on the decode kernel: split K/V streams (B=3), two groups (B=32), partial last group (B=40)
     for B in 3 32 40; do
       for tool in memcheck racecheck synccheck; do
