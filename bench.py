@@ -403,6 +403,15 @@ def run_ours(args):
                 "launch_seconds": dec_secs / n_launch, "us_per_decode_step": 1e6 * dec_secs / args.frames,
                 "share_of_job": dec_secs / (secs / args.steps)}
 
+    train = None
+    if not args.no_train:
+        try:
+            del sess, eng
+            torch.cuda.empty_cache()
+            train = run_train_step(args, dev, rank, world)
+        except Exception as exc:   # the headline line must survive a failure of the secondary workload
+            import traceback
+            train = {"error": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
     line = None
     if rank == 0:
         # Baselines are timed at N=1 only: under torchrun the other ranks would spin in an NCCL barrier for the
@@ -421,12 +430,119 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "gpu_eager_baseline": eager, "decode_impl": args.decode_impl}
+                "gpu_eager_baseline": eager, "decode_impl": args.decode_impl, "train_step": train}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
+
+
+
+def train_flops(S, T, B):
+    """Algorithmic FLOPs of one teacher-forced training step per GPU: forward per SURVEY.md §8d (dense contractions +
+    attention with causal skipping credited + Postnet), backward = 2 x forward."""
+    fwd = B * (S * (37.75e6 + 4 * S * 512 * 6 + 14.16e6) + T * (99.09e6 + 4 * T * 768 * 6 * 0.5 + 4 * S * 768 * 6 + 0.565e6
+                                                                + 0.124e6 + 8.68e6))
+    return 3.0 * fwd
+
+
+def run_train_step(args, dev, rank, world):
+    """BASELINE.json metric 2 / configs[2]: the teacher-forced TRAINING step (train.py:165-191: forward, compute_loss,
+    backward, gradient all-reduce, Adam) at per-GPU batch 64 x 1000 mel frames, 258 text tokens, bf16 tensor-core
+    kernels with fp32 master weights, dropout ON, through the drop-in transformer/ API.  Data parallel: one process
+    per GPU, the 83.5 M gradients (333.9 MB fp32) all-reduced over NCCL every step (weak scaling: 64 per GPU)."""
+    import torch.distributed as dist
+    from tts_b200 import synthetic as O
+    from tts_b200 import _native
+    from tts_b200.config import hparams_from
+    from tts_b200.dist import GradBuckets
+    from tts_b200.optim import FusedAdam, l2_selected_names
+    from transformer import tacotron
+    cfg = O.ModelConfig()
+    hp = hparams_from(cfg)
+    hp.l2_in_optimizer = True
+    torch.manual_seed(0)
+    m = tacotron.Tacotron(hp)
+    m.load_state_dict(O.synth_params(cfg, seed=0), strict=True)
+    m.to(dev).train()
+    B, S, T = args.tf_batch, args.text_len, args.frames
+    host = O.synth_batch(cfg, batch=B, text_len=S, n_frames=T, seed=100 + rank)
+    keys = ("inputs", "input_lengths", "mel_targets", "target_lengths", "input_spk_ids", "input_language_vecs")
+    pinned = {k: host[k].pin_memory() for k in keys}
+    sel = l2_selected_names(m)
+    opt = FusedAdam(m.parameters(), lr=hp.max_lr, eps=hp.adam_eps, reg_weight=hp.reg_weight,
+                    l2_params=[p for n, p in m.named_parameters() if n in sel])
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: tacotron.learning_rate_schedule(s, hp))
+    ddp = None
+    buckets = None
+    if world > 1:
+        if args.dp == "ddp":
+            ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[dev.index], output_device=dev.index)
+        else:
+            buckets = GradBuckets(m.parameters())
+            buckets.broadcast_parameters(0)
+    fwd = ddp if ddp is not None else m
+    lib = _native.load()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    ar_ms = []
+
+    def step(timed_ar=False):
+        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}   # dict_send_to (utils/__init__.py:3)
+        out = fwd(**batch)
+        losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
+        opt.zero_grad(set_to_none=False)
+        losses["loss"].backward()
+        if buckets is not None:
+            if timed_ar:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                buckets.allreduce_mean()
+                e1.record()
+                ar_ms.append((e0, e1))
+            else:
+                buckets.allreduce_mean()
+        opt.step()
+        sched.step()
+        loss_host.copy_(losses["loss"].detach(), non_blocking=True)
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib.tts_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = step(timed_ar=True)
+    e1.record()
+    barrier()
+    ms = reduce_max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
+    launches = int(lib.tts_launch_count()) // max(args.steps, 1)
+    flops = train_flops(S, T, B)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ar = [a.elapsed_time(b) for a, b in ar_ms]
+    n_params = sum(p.numel() for p in m.parameters())
+    return {"metric": "teacher-forced train step ms", "value": ms, "unit": "ms", "higher_is_better": False, "n_gpus": world,
+            "steps": args.steps, "scaling": "weak", "dtype": "bf16 (fp32 accumulate, fp32 master weights and optimizer state)",
+            "config": {"workload": "teacher-forced train step, per-GPU batch=%d x %d mel frames, %d text tokens, dropout on "
+                                   "(BASELINE.json configs[2])" % (B, T, S), "global_batch": B * world,
+                       "parallelism": "dp%d (%s)" % (world, "single GPU" if world == 1 else
+                                                     ("DistributedDataParallel" if ddp is not None else "bucketed NCCL all-reduce, 64 MB buckets"))},
+            "frames_per_s": B * T * world / (ms / 1e3), "loss": float(loss_host),
+            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()), "d2h_bytes_per_step": 4,
+            "gpu_launches_per_step": launches,
+            "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
+                         "flops_per_step_per_gpu": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "allreduce": None if not ar else {"bytes": 4 * n_params, "ms_median": statistics.median(ar),
+                                              "note": "CUDA events around the bucketed all-reduce (exposed time, not overlapped)"}}
 
 
 def run_forward(args):
@@ -470,6 +586,28 @@ def run_forward(args):
     return 0
 
 
+def run_train_only(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    with ClockSampler(local) as clocks:
+        line = run_train_step(args, dev, rank, world)
+    line["clocks"] = clocks.summary()
+    line["data"] = "synthetic"
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,12 +623,17 @@ def main():
     ap.add_argument("--ref-horizon", type=int, default=96, help="frames of the CPU reference sample")
     ap.add_argument("--eager-horizon", type=int, default=300, help="frames of the torch-eager-on-GPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="decode", choices=["decode", "forward"],
-                    help="decode = the headline (default); forward = teacher-forced forward pass only (secondary)")
+    ap.add_argument("--workload", default="decode", choices=["decode", "forward", "train"],
+                    help="decode = the headline (default, also reports train_step); train = only the teacher-forced "
+                         "training step (BASELINE metric 2); forward = teacher-forced forward pass only")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step measurement of the default run")
+    ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"], help="gradient exchange of the train step at N > 1")
     ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")
     args = ap.parse_args()
     if args.workload == "forward":
         return run_forward(args)
+    if args.workload == "train":
+        return run_train_only(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

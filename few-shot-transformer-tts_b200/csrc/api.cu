@@ -27,6 +27,12 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int enqueue_step_phases(const TtsDecoderWeights* w, const TtsDecodeState* st, int update_state, cudaStream_t s);
 int decode_reset(const TtsDecodeState* st, cudaStream_t s);
 size_t decode_scratch_floats(const TtsDecoderWeights* w, int B);
+// pipelined2.cu
+int launch_pipelined2_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
+                            cudaStream_t s);
+size_t pipelined2_scratch_floats(const TtsDecoderWeights* w, int B);
+bool pipelined2_supported(const TtsDecoderWeights* w, const TtsDecodeState* st);
+int pipelined2_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, long long* out_host, int max_entries);
 // pipelined.cu
 int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int n_steps, int update_state,
                            cudaStream_t s);
@@ -128,8 +134,10 @@ extern "C" size_t tts_decode_scratch_bytes(const TtsDecoderWeights* w, int32_t b
   (void)mem_len;
   (void)t_max;
   if (!w || batch <= 0) return 0;
-  const size_t a = decode_scratch_floats(w, batch), c = pipelined_scratch_floats(w, batch);
-  return (a > c ? a : c) * sizeof(float) + 256;
+  const size_t a = decode_scratch_floats(w, batch), c = pipelined_scratch_floats(w, batch),
+               e = pipelined2_scratch_floats(w, batch);
+  const size_t m = a > c ? (a > e ? a : e) : (c > e ? c : e);
+  return m * sizeof(float) + 256;
 }
 
 extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void* stream) {
@@ -157,7 +165,8 @@ extern "C" int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState
 extern "C" int tts_decode_profile(const TtsDecoderWeights* w, const TtsDecodeState* st, int64_t* out_host,
                                   int32_t max_entries) {
   TTS_REQUIRE(w && st && out_host && max_entries > 0, "decode_profile: bad arguments");
-  TTS_REQUIRE(g_last_impl == 4, "decode_profile: only the pipelined kernel (impl 4) records phase stamps");
+  TTS_REQUIRE(g_last_impl == 4 || g_last_impl == 5, "decode_profile: only the pipelined kernels (impl 4 / 5) record phase stamps");
+  if (g_last_impl == 5) return pipelined2_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
   return pipelined_profile(w, st, reinterpret_cast<long long*>(out_host), max_entries);
 }
 
@@ -177,8 +186,9 @@ extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState
                                        (size_t)st->batch, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 0) impl = pipelined_supported(w, st) ? 4 : 2;
+  if (impl == 0) impl = pipelined2_supported(w, st) ? 5 : (pipelined_supported(w, st) ? 4 : 2);
   g_last_impl = impl;
+  if (impl == 5) return launch_pipelined2_steps(w, st, n_steps, update_state, s);
   if (impl == 4) return launch_pipelined_steps(w, st, n_steps, update_state, s);
   if (impl == 1) {
     for (int i = 0; i < n_steps; ++i)

@@ -456,7 +456,7 @@ class TtsEngine:
             sess.step(n, update_state=True, impl=impl)
             done += n
             left = int(sess.counters[1].item())  # one 4-byte D2H per chunk instead of one per frame
-            if left == -2:
+            if left == -2 or left <= -(1 << 29):
                 raise RuntimeError("tts_b200: decode stepped past the session's t_max (device step counter)")
             if left < 0:
                 raise RuntimeError("tts_b200: the decode kernel reported a grid-barrier timeout")

@@ -49,4 +49,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self.state[p]["step"] = step
             b1, b2 = group["betas"]
             TO.adam_multi(hit[1], float(group["lr"]), b1, b2, float(group["eps"]), step, self.reg_weight, self.grad_scale)
+            # the kernel wrote through raw pointers: bump the version counters so that everything keyed on them (the bf16
+            # operand copies of engine_train, the packed decode weights of engine) sees the update
+            torch._C._increment_version(ps)
         return loss

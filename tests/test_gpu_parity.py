@@ -266,9 +266,11 @@ def test_full_autoregressive_vs_reference_golden(full_params, golden_dir, ops, i
 
 @pytest.mark.parametrize("B,split_note", [(1, "split-KV over 18 CTAs per head"), (3, "split-KV"), (32, "one CTA per head"),
                                           (40, "two row blocks, second one partial"), (64, "two full row blocks")])
-@pytest.mark.parametrize("impl", [1, 4])
+@pytest.mark.parametrize("impl", [1, 4, 5])
 def test_full_decode_steps_vs_oracle_batches(full_engine, full_params, B, split_note, impl):
     """Decode at several batch sizes (different split-KV factors), 24 steps, vs the cached oracle."""
+    if impl == 5 and B <= 16:
+        pytest.skip("impl 5 (two CTAs per SM, one row group each) serves batches of more than one row group")
     cfg, params = full_params
     p = dict(params)
     p["decoder.stop_net.bias"] = torch.tensor([-1e4])
@@ -296,7 +298,7 @@ def test_decode_properties_at_baseline_shape(full_params, ops):
     a = eng.generate(batch, max_frames=T, record_align="none", memory=mem)
     b = eng.generate(batch, max_frames=T, record_align="none", memory=mem, session=a["session"])   # reuse buffers
     assert torch.equal(a["mel_pre"], b["mel_pre"]) and torch.equal(a["generated_lengths"], b["generated_lengths"])
-    for other in (1,):   # the per-phase kernels agree with the default (pipelined) one
+    for other in (1, 4):   # the per-phase kernels and the first-generation pipelined kernel agree with the default (impl 5)
         c = eng.generate(batch, max_frames=T, record_align="none", memory=mem, impl=other)
         assert _err(a["mel_pre"], c["mel_pre"]) < 1e-4 and torch.equal(a["generated_lengths"], c["generated_lengths"])
     perm = torch.randperm(32, generator=torch.Generator().manual_seed(0))
@@ -331,6 +333,7 @@ def test_pipelined_group_size_override(full_params, ops, rows):
     os.environ["TTS_GROUP_ROWS"] = str(rows)
     try:
         got = eng.generate(batch, max_frames=20, record_align="encdec", memory=mem, chunk=20, impl=4)
+        got5 = eng.generate(batch, max_frames=20, record_align="encdec", memory=mem, chunk=20, impl=5)
     finally:
         if old is None:
             del os.environ["TTS_GROUP_ROWS"]
@@ -339,6 +342,8 @@ def test_pipelined_group_size_override(full_params, ops, rows):
     assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4
     assert _err(got["mel_aft"], want["mel_aft"]) < 2e-4
     assert _err(got["alignments"]["encdec"][5], ref["alignments"]["encdec"][5]) < 1e-5
+    assert _err(got5["mel_pre"], want["mel_pre"]) < 2e-4     # impl 5: groups of 8 / 11 rows spread over the two CTA slots
+    assert _err(got5["alignments"]["encdec"][5], ref["alignments"]["encdec"][5]) < 1e-5
 
 
 def test_tcgen05_gemm_vs_float64(ops):
@@ -510,6 +515,28 @@ def test_decode_contract_frames_are_inputs_and_bounds(full_params, ops):
         torch.cuda.synchronize()
         assert int(sess.counters[1].item()) == -2 and int(sess.counters[0].item()) == 4
         assert torch.equal(before, sess.frames) and float(guard.min()) == 7.0
+    # the same two contracts on the two-CTAs-per-SM kernel (impl 5, three row groups over two slots)
+    wide = O.synth_batch(cfg, batch=40, text_len=33, n_frames=4, seed=13, ragged=True)
+    wmem = eng.encode(wide["inputs"], wide["input_lengths"], wide["input_spk_ids"], wide["input_language_vecs"])
+    outs = []
+    for impl in (5, 1):
+        sess = eng.new_session(40, 33, 8, "none")
+        sess.begin(wmem, wide["input_lengths"].to(DEV))
+        sess.step(3, impl=impl)
+        sess.frames[:, 2] += 0.01 * torch.arange(40, device=DEV)[:, None]
+        sess.step(1, impl=impl)
+        sess.step(2, impl=1 if impl == 5 else 5)
+        outs.append(sess.frames[:, :6].clone())
+    assert _err(outs[0], outs[1]) < 2e-4
+    sess = eng.new_session(40, 33, 4, "none")
+    sess.begin(wmem, wide["input_lengths"].to(DEV))
+    sess.step(4, impl=5)
+    sess.t = 0
+    before = sess.frames.clone()
+    sess.step(2, impl=5)
+    torch.cuda.synchronize()
+    assert int(sess.counters[1].item()) <= -(1 << 29) and int(sess.counters[0].item()) == 4
+    assert torch.equal(before, sess.frames)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -15,4 +15,27 @@ case $mode in
     done ;;
   bench)
     python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cut -c1-2500 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err ;;
+  train)      # BASELINE metric 2: the teacher-forced training step at configs[2], plus its launch list
+    python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/r2_train_bench.json 2> gpurun_out/r2_train_bench.err; cut -c1-1800 gpurun_out/r2_train_bench.json; tail -5 gpurun_out/r2_train_bench.err
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 > /dev/null 2>&1
+    python - <<'PY'
+import csv, collections
+rows = list(csv.reader(open("gpurun_out/r2_train_launches.csv")))
+hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+h = rows[hdr]; kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+agg = collections.Counter(); cnt = collections.Counter()
+data = rows[hdr + 2:]
+n = len(data)
+# the last quarter of the launches is the single timed step (3 warm-up steps + 1)
+for r in data[3 * n // 4:]:
+    try:
+        agg[r[kn][:70]] += float(r[mv].replace(",", "")); cnt[r[kn][:70]] += 1
+    except (ValueError, IndexError):
+        pass
+tot = sum(agg.values())
+for k, v in agg.most_common(25):
+    print("%8.3f ms %5.1f%% x%4d %s" % (v / 1e6, 100 * v / tot, cnt[k], k))
+print("total %.3f ms over %d launches" % (tot / 1e6, sum(cnt.values())))
+PY
+    ;;
 esac
