@@ -1,6 +1,7 @@
 // C-ABI entry points of libtts_b200.so that are not pure kernels: diagnostics, the decode
 // session calls and the CUDA-graph cache that replays one decode step per launch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -186,7 +187,10 @@ extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState
                                        (size_t)st->batch, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 0) impl = pipelined2_supported(w, st) ? 5 : (pipelined_supported(w, st) ? 4 : 2);
+  if (impl == 0) {   // default: the pipelined kernel; TTS_DECODE_V2=1 opts into the two-CTAs-per-SM experiment (measured slower)
+    static const bool v2 = getenv("TTS_DECODE_V2") != nullptr && atoi(getenv("TTS_DECODE_V2")) != 0;
+    impl = (v2 && pipelined2_supported(w, st)) ? 5 : (pipelined_supported(w, st) ? 4 : 2);
+  }
   g_last_impl = impl;
   if (impl == 5) return launch_pipelined2_steps(w, st, n_steps, update_state, s);
   if (impl == 4) return launch_pipelined_steps(w, st, n_steps, update_state, s);

@@ -81,6 +81,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
   }
 }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
 // A fragments (16 rows x DH) of one warp from a shared-memory tile: a[ks] covers k = 16 ks .. 16 ks + 15
 template <int DH>
@@ -170,8 +171,9 @@ template <int DH>
 __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Args a) {
   constexpr int LDS = DH + 8;
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
-  __nv_bfloat16 *sQ = sm, *sK = sQ + BQ * LDS, *sV = sK + BKV * LDS;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  __nv_bfloat16 *sQ = sm, *sK = sQ + BQ * LDS, *sV = sK + 2 * BKV * LDS;
+  // heavy (late) query blocks of a causal problem first: the tail of the grid is made of short CTAs
+  const int q0 = (a.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BQ, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
   const unsigned long long bh = (unsigned long long)b * a.H + h;
   const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
@@ -180,38 +182,56 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Args a) {
   const __nv_bfloat16* kg = a.k + (long long)b * a.Tk * a.ldk + h * DH;
   const __nv_bfloat16* vg = a.v + (long long)b * a.Tk * a.ldv + h * DH;
 
+  const int i0 = q0 + warp * 16 + g;
+  const int k_end = a.causal ? min(klen, q0 + BQ) : klen;
+  // K/V tiles are double buffered: tile it+1 streams in (cp.async) while tile it is multiplied
   load_tile<DH, BQ>(sQ, qg, a.ldq, q0, a.Tq);
-  cp_wait_all();
-  __syncthreads();
-  uint32_t qf[DH / 16][4];
-  load_a_frags<DH>(qf, sQ, warp * 16);
-
+  if (k_end > 0) {
+    load_tile<DH, BKV>(sK, kg, a.ldk, 0, a.Tk);
+    load_tile<DH, BKV>(sV, vg, a.ldv, 0, a.Tk);
+  }
+  cp_commit();
   float o[DH / 8][4];
 #pragma unroll
   for (int n = 0; n < DH / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m[2] = {-CUDART_INF_F, -CUDART_INF_F}, l[2] = {0.f, 0.f};
-  const int i0 = q0 + warp * 16 + g;
-  const int k_end = a.causal ? min(klen, q0 + BQ) : klen;
+  uint32_t qf[DH / 16][4];
 
-  for (int kb = 0; kb < k_end; kb += BKV) {
-    __syncthreads();   // everyone is done with the previous K/V tiles
-    load_tile<DH, BKV>(sK, kg, a.ldk, kb, a.Tk);
-    load_tile<DH, BKV>(sV, vg, a.ldv, kb, a.Tk);
+  for (int kb = 0, it = 0; kb < k_end; kb += BKV, ++it) {
     cp_wait_all();
-    __syncthreads();
+    __syncthreads();   // tile `it` has landed for everyone, and everyone is done with the buffer tile it+1 goes into
+    if (it == 0) load_a_frags<DH>(qf, sQ, warp * 16);
+    const __nv_bfloat16 *cK = sK + (it & 1) * BKV * LDS, *cV = sV + (it & 1) * BKV * LDS;
+    if (kb + BKV < k_end) {
+      load_tile<DH, BKV>(sK + ((it + 1) & 1) * BKV * LDS, kg, a.ldk, kb + BKV, a.Tk);
+      load_tile<DH, BKV>(sV + ((it + 1) & 1) * BKV * LDS, vg, a.ldv, kb + BKV, a.Tk);
+      cp_commit();
+    }
     float s[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-    mma_a_tt<DH, 8>(s, qf, sK, 0);
+    mma_a_tt<DH, 8>(s, qf, cK, 0);
     float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+    // interior tiles (every key of the tile visible to every query row of this warp) skip the mask arithmetic
+    const bool open_tile = kb + BKV <= klen && (!a.causal || kb + BKV - 1 <= q0 + warp * 16);
+    if (open_tile) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n)
+      for (int n = 0; n < 8; ++n)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
-        s[n][e] = key_ok(a, i, j, klen) ? s[n][e] * a.scale_log2 : -CUDART_INF_F;
-        mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
-      }
+        for (int e = 0; e < 4; ++e) {
+          s[n][e] *= a.scale_log2;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
+        }
+    } else {
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
+          s[n][e] = key_ok(a, i, j, klen) ? s[n][e] * a.scale_log2 : -CUDART_INF_F;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[n][e]);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Args a) {
           if (!((bits >> e) & 1u)) s[2 * np + (e >> 2)][e & 3] = 0.f;
       }
     }
-    mma_p_t<DH, 8>(o, s, sV, 0);
+    mma_p_t<DH, 8>(o, s, cV, 0);
   }
   // finalize
 #pragma unroll
@@ -272,8 +292,8 @@ template <int DH>
 __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
   constexpr int LDS = DH + 8;
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
-  __nv_bfloat16 *sQ = sm, *sDO = sQ + BQ * LDS, *sK = sDO + BQ * LDS, *sV = sK + BKV * LDS;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  __nv_bfloat16 *sQ = sm, *sDO = sQ + BQ * LDS, *sK = sDO + BQ * LDS, *sV = sK + 2 * BKV * LDS;
+  const int q0 = (a.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * BQ, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
   const unsigned long long bh = (unsigned long long)b * a.H + h;
   const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
@@ -319,21 +339,30 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
 #pragma unroll
   for (int n = 0; n < DH / 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
   const int k_end = a.causal ? min(klen, q0 + BQ) : klen;
+  __syncthreads();   // delta staging (O in the first K buffer, sums in the first V buffer) is finished
+  if (k_end > 0) {
+    load_tile<DH, BKV>(sK, kg, a.ldk, 0, a.Tk);
+    load_tile<DH, BKV>(sV, vg, a.ldv, 0, a.Tk);
+    cp_commit();
+  }
 
-  for (int kb = 0; kb < k_end; kb += BKV) {
-    __syncthreads();
-    load_tile<DH, BKV>(sK, kg, a.ldk, kb, a.Tk);
-    load_tile<DH, BKV>(sV, vg, a.ldv, kb, a.Tk);
+  for (int kb = 0, it = 0; kb < k_end; kb += BKV, ++it) {
     cp_wait_all();
     __syncthreads();
+    const __nv_bfloat16 *cK = sK + (it & 1) * BKV * LDS, *cV = sV + (it & 1) * BKV * LDS;
+    if (kb + BKV < k_end) {   // the next K/V tile streams in while this one is multiplied
+      load_tile<DH, BKV>(sK + ((it + 1) & 1) * BKV * LDS, kg, a.ldk, kb + BKV, a.Tk);
+      load_tile<DH, BKV>(sV + ((it + 1) & 1) * BKV * LDS, vg, a.ldv, kb + BKV, a.Tk);
+      cp_commit();
+    }
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
       dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
     }
-    mma_a_tt<DH, 8>(s, qf, sK, 0);
-    mma_a_tt<DH, 8>(dp, dof, sV, 0);
+    mma_a_tt<DH, 8>(s, qf, cK, 0);
+    mma_a_tt<DH, 8>(dp, dof, cV, 0);
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t bits = 0xffu;
@@ -347,7 +376,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
         s[n][e] = p * (dpe - dl[e >> 1]) * a.scale;   // dS (scaled: dQ = scale * dS K)
       }
     }
-    mma_p_t<DH, 8>(dq, s, sK, 0);
+    mma_p_t<DH, 8>(dq, s, cK, 0);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -366,8 +395,8 @@ template <int DH>
 __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
   constexpr int LDS = DH + 8, BQ2 = 32;
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
-  __nv_bfloat16 *sK = sm, *sV = sK + BKV * LDS, *sQ = sV + BKV * LDS, *sDO = sQ + BQ2 * LDS;
-  float* sL = reinterpret_cast<float*>(sDO + BQ2 * LDS);   // [32] lse, [32] delta
+  __nv_bfloat16 *sK = sm, *sV = sK + BKV * LDS, *sQ = sV + BKV * LDS, *sDO = sQ + 2 * BQ2 * LDS;
+  float* sL = reinterpret_cast<float*>(sDO + 2 * BQ2 * LDS);   // 2 x ([32] lse, [32] delta)
   const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
   const unsigned long long bh = (unsigned long long)b * a.H + h;
@@ -395,25 +424,35 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
   const bool any_key = j0 < klen;
   const int q_begin = a.causal ? (j0 / BQ2) * BQ2 : 0;   // queries before the first key of the block never see it
 
-  for (int qb = q_begin; qb < a.Tq && any_key; qb += BQ2) {
-    __syncthreads();
-    load_tile<DH, BQ2>(sQ, qg, a.ldq, qb, a.Tq);
-    load_tile<DH, BQ2>(sDO, dog, a.lddo, qb, a.Tq);
-    if (threadIdx.x < BQ2) {
-      const int i = qb + threadIdx.x;
-      sL[threadIdx.x] = i < a.Tq ? a.lse[bh * a.Tq + i] : 0.f;
-      sL[BQ2 + threadIdx.x] = i < a.Tq ? a.delta[bh * a.Tq + i] : 0.f;
+  auto load_q = [&](int qb, int buf) {   // Q / dO tiles and the per-query lse / delta of block qb -> buffer buf
+    load_tile<DH, BQ2>(sQ + buf * BQ2 * LDS, qg, a.ldq, qb, a.Tq);
+    load_tile<DH, BQ2>(sDO + buf * BQ2 * LDS, dog, a.lddo, qb, a.Tq);
+    if (threadIdx.x < 2 * BQ2) {
+      const int which = threadIdx.x >> 5, i = qb + (threadIdx.x & 31);
+      const float* src = which ? a.delta : a.lse;
+      const bool ok = i < a.Tq;
+      const uint32_t d = smem_u32(sL + buf * 2 * BQ2 + threadIdx.x);
+      const int bytes = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + bh * a.Tq + (ok ? i : 0)), "r"(bytes) : "memory");
     }
+    cp_commit();
+  };
+  if (any_key && q_begin < a.Tq) load_q(q_begin, 0);
+
+  for (int qb = q_begin, it = 0; qb < a.Tq && any_key; qb += BQ2, ++it) {
     cp_wait_all();
     __syncthreads();
+    const __nv_bfloat16 *cQ = sQ + (it & 1) * BQ2 * LDS, *cDO = sDO + (it & 1) * BQ2 * LDS;
+    const float* cL = sL + (it & 1) * 2 * BQ2;
+    if (qb + BQ2 < a.Tq) load_q(qb + BQ2, (it + 1) & 1);
     float st[4][4], dpt[4][4];   // S^T and dP^T: rows = keys, columns = the 32 queries of the block
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
       dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
     }
-    mma_a_tt<DH, 4>(st, kf, sQ, 0);
-    mma_a_tt<DH, 4>(dpt, vf, sDO, 0);
+    mma_a_tt<DH, 4>(st, kf, cQ, 0);
+    mma_a_tt<DH, 4>(dpt, vf, cDO, 0);
     float pt[4][4];
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
@@ -424,15 +463,15 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
         const int n = 2 * np + (e8 >> 2), e = e8 & 3;
         const int j = jr + (e >> 1) * 8, il = n * 8 + t2 + (e & 1), i = qb + il;
         const bool ok = i < a.Tq && j < a.Tk && key_ok(a, i, j, klen);
-        const float p = ok ? ex2(st[n][e] * a.scale_log2 - sL[il]) : 0.f;
+        const float p = ok ? ex2(st[n][e] * a.scale_log2 - cL[il]) : 0.f;
         const bool keep = (bits >> e8) & 1u;
         pt[n][e] = keep ? p * a.drop_scale : 0.f;                         // dropped-and-scaled weights: dV = P_drop^T dO
         const float dpe = keep ? dpt[n][e] * a.drop_scale : 0.f;
-        st[n][e] = p * (dpe - sL[BQ2 + il]) * a.scale;                   // dS^T (scaled: dK = scale * dS^T Q)
+        st[n][e] = p * (dpe - cL[BQ2 + il]) * a.scale;                   // dS^T (scaled: dK = scale * dS^T Q)
       }
     }
-    mma_p_t<DH, 4>(dv, pt, sDO, 0);
-    mma_p_t<DH, 4>(dk, st, sQ, 0);
+    mma_p_t<DH, 4>(dv, pt, cDO, 0);
+    mma_p_t<DH, 4>(dk, st, cQ, 0);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -450,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
 
 template <int DH>
 static int launch_fwd(const Args& a, cudaStream_t s) {
-  const size_t smem = (size_t)(BQ + 2 * BKV) * (DH + 8) * 2;
+  const size_t smem = (size_t)(BQ + 4 * BKV) * (DH + 8) * 2;
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_fwd_kernel<DH><<<dim3(ceil_div(a.Tq, BQ), a.H, a.B), kThreads, smem, s>>>(a);
   TTS_CHECK_LAUNCH();
@@ -458,8 +497,8 @@ static int launch_fwd(const Args& a, cudaStream_t s) {
 }
 template <int DH>
 static int launch_bwd(const Args& a, cudaStream_t s) {
-  const size_t smem_q = (size_t)(2 * BQ + 2 * BKV) * (DH + 8) * 2;
-  const size_t smem_kv = (size_t)(2 * BKV + 2 * 32) * (DH + 8) * 2 + 64 * sizeof(float);
+  const size_t smem_q = (size_t)(2 * BQ + 4 * BKV) * (DH + 8) * 2;
+  const size_t smem_kv = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 128 * sizeof(float);
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
   attn_bwd_dq_kernel<DH><<<dim3(ceil_div(a.Tq, BQ), a.H, a.B), kThreads, smem_q, s>>>(a);

@@ -1,4 +1,4 @@
-// Pipelined persistent decode kernel, generation 2 (impl 5, the default for batches of more than 16 rows): the design of
+// Pipelined persistent decode kernel, experiment 2 (impl 5, opt-in: impl = 5 or TTS_DECODE_V2=1; NOT the default): the design of
 // pipelined.cu (weight-stationary split of every projection over the CTAs, packed LayerNorm-folded weight rows, 3xTF32
 // mma.sync products, CTA-wide TMA-fed K/V ring, loader / signaler / feeder warps) re-cut so that TWO CTAs share every SM
 // and each CTA owns ONE 16-row group of the batch on its OWN phase clock:
@@ -20,6 +20,12 @@
 //   * each group's CTAs fetch their own copy of a phase's weight slice; the second fetch follows within ~10 us and is
 //     served by the 126 MB L2 (dram traffic per step is measured in profiles/).
 //   * no early exit inside a launch (the groups do not know each other's state): the host polls once per launch.
+// MEASURED (B=32, S=258, 1000 frames, profiles/r2_decode_v2_experiment.txt): 496-516 us per step against 414 us for
+// pipelined.cu.  The overlap works, but with one row group per CTA nothing inside the CTA hides the ~2 us grid-barrier
+// + tile-staging latency of each of the 57 phases any more (pipelined.cu hides it behind the OTHER group's group-phase),
+// and 4 consumer warps, a single weight buffer and no ring pre-fill lengthen every phase: each group's dependency chain
+// grows from ~310 us (a 16-row batch alone on pipelined.cu) to ~500 us.  Kept as a tested, opt-in implementation and
+// as the record of this experiment; DESIGN.md section 7 discusses what a version with dedicated attention warps needs.
 // Everything else - phase table, packed operands, epilogues, attention math, bit-reproducible static tile assignment -
 // is pipelined.cu's; reference semantics: transformer/tacotron.py:107-116, transformer/modules.py:108-145,
 // transformer/attention.py:53-122, synthesize.py:35-45.
@@ -1427,7 +1433,7 @@ bool pipelined2_supported(const TtsDecoderWeights* w, const TtsDecodeState* st) 
   if (w->pk_ksplit != ks) return false;
   if (F % ks != 0 || (F / ks) % 16 != 0 || F / ks > kKC || ks > G) return false;
   if (st->batch > kMaxBatch || st->batch <= kGroupRows) return false;   // a single group: pipelined.cu (8 consumer warps)
-  if (getenv("TTS_DECODE_V2") != nullptr && atoi(getenv("TTS_DECODE_V2")) == 0) return false;
+
   const int dh = D / w->n_heads;
   if (dh != 32 && dh != 64 && dh != 96) return false;
   auto rows = [&](long long N, int parts) { return (int)((N + parts - 1) / parts); };

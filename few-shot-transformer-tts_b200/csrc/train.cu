@@ -133,7 +133,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     const bool dead = row_len != nullptr && (row % rpb) >= row_len[row / rpb];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + (size_t)row * lddy);
-    float4 xh[kLnMaxV], gg[kLnMaxV];
+    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * C) : nullptr;
+    float4 xh[kLnMaxV], gg[kLnMaxV], rv[kLnMaxV];
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {   // the residual-path gradient is requested with the other operands, not after the reductions
+      const int c = lane + 32 * i;
+      rv[i] = (rr != nullptr && c < nv) ? rr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kLnMaxV; ++i) {
@@ -155,19 +161,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
     float4* ox = reinterpret_cast<float4*>(dx + (size_t)row * C);
-    const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * C) : nullptr;
 #pragma unroll
     for (int i = 0; i < kLnMaxV; ++i) {
       const int c = lane + 32 * i;
-      if (c < nv) {
-        float4 o = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2), rs * (gg[i].y - s1 - xh[i].y * s2),
-                               rs * (gg[i].z - s1 - xh[i].z * s2), rs * (gg[i].w - s1 - xh[i].w * s2));
-        if (rr) {
-          const float4 r = rr[c];
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
-        ox[c] = o;
-      }
+      if (c < nv)
+        ox[c] = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2) + rv[i].x, rs * (gg[i].y - s1 - xh[i].y * s2) + rv[i].y,
+                            rs * (gg[i].z - s1 - xh[i].z * s2) + rv[i].z, rs * (gg[i].w - s1 - xh[i].w * s2) + rv[i].w);
     }
   }
   // cross-warp reduction of the column partials through shared memory, one [2][C] record per CTA
@@ -636,7 +635,7 @@ extern "C" int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x
   TTS_REQUIRE(channels % 4 == 0 && channels <= 128 * tr::kLnMaxV && lddy % 4 == 0, "ln_bwd_train: channels %d unsupported", channels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int blocks = ceil_div(rows, 8);
-  if (blocks > 296) blocks = 296;
+  if (blocks > 1184) blocks = 1184;   // 8 CTAs of 8 warps per SM: enough rows in flight to cover the HBM latency
   const size_t smem = (size_t)16 * channels * sizeof(float);
   static bool attr = false;
   if (!attr || smem > 48 * 1024) {
@@ -650,7 +649,7 @@ extern "C" int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x
   TTS_CHECK_LAUNCH();
   return 0;
 }
-extern "C" size_t tts_ln_bwd_scratch_floats(int32_t channels) { return (size_t)296 * 2 * channels; }
+extern "C" size_t tts_ln_bwd_scratch_floats(int32_t channels) { return (size_t)1184 * 2 * channels; }
 
 extern "C" int tts_dropout_cast(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int32_t channels,
                                 float drop_p, uint64_t seed, uint32_t rng_stream, const int32_t* row_len, int32_t rows_per_batch,

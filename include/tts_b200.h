@@ -336,10 +336,10 @@ int tts_decode_begin(const TtsDecoderWeights* w, const TtsDecodeState* st, void*
  *   prev_mel / prev_mel_stride: where step t reads frame t-1 from.  NULL = st->frames.
  *   update_state: 1 = also perform synthesize.py:42-45 on device (finished |= stop>0,
  *                 lengths += !finished); 0 = the caller does it (unchanged eval_batch).
- *   impl: 0 = default (5 when supported, else 4, else 2),
+ *   impl: 0 = default (4 when the shape is supported, else 2),
  *         1 = per-phase kernels, 2 = per-phase kernels replayed from a CUDA graph,
  *         4 = pipelined persistent kernel (row-group pipelining, producer warp, 3xTF32 mma.sync),
- *         5 = its second generation: two CTAs per SM, one row group each on its own phase clock (batch > 16 rows).
+ *         5 = experiment: two CTAs per SM, one row group each on its own phase clock (batch > 16 rows; measured slower).
  * *st->n_unfinished after the call: rows still decoding (>= 0); < 0 = a barrier wait timed out; -2 or <= -2^29 = the
  * call asked for steps beyond t_max (nothing past t_max was touched). */
 int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState* st, int32_t n_steps,
