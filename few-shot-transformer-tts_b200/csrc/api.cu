@@ -192,6 +192,10 @@ extern "C" int tts_decode_steps(const TtsDecoderWeights* w, const TtsDecodeState
     impl = (v2 && pipelined2_supported(w, st)) ? 5 : (pipelined_supported(w, st) ? 4 : 2);
   }
   g_last_impl = impl;
+  TTS_REQUIRE(st->drop_p_prenet >= 0.f && st->drop_p_prenet < 1.f && st->drop_p_transformer >= 0.f && st->drop_p_transformer < 1.f,
+              "decode_steps: dropout rates must be in [0, 1)");
+  TTS_REQUIRE(impl == 4 || (st->drop_p_prenet == 0.f && st->drop_p_transformer == 0.f),
+              "decode_steps: train()-mode dropout is implemented by the pipelined kernel (impl 4) only, got impl %d", impl);
   if (impl == 5) return launch_pipelined2_steps(w, st, n_steps, update_state, s);
   if (impl == 4) return launch_pipelined_steps(w, st, n_steps, update_state, s);
   if (impl == 1) {

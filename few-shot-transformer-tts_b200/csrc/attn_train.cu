@@ -135,26 +135,33 @@ __device__ __forceinline__ void mma_p_t(float (&c)[DH / 8][4], const float (&p)[
 }
 
 // keep flags of the 8 weights a thread holds in one 16 x 16 block (two neighbouring n-tiles); TR: the accumulator rows are
-// keys and the columns queries (dK/dV kernel).  bit e of the result <-> (n-tile parity e >> 2, accumulator register e & 3)
+// keys and the columns queries (dK/dV kernel).  bit e of the result <-> (n-tile parity e >> 2, accumulator register e & 3).
+// philox.cuh: one call covers {i0, i0+8} x {j0, j0+1, j0+8, j0+9}, 16 bits per element, half-word 4*(i bit 3) + 2*(j bit 3) + (j bit 0)
 template <bool TR>
 __device__ __forceinline__ uint32_t keep_bits(const Args& a, unsigned long long bh, int n_iblk, int n_jblk, int row0, int col0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  const uint32_t thr = a.drop_thresh;   // 16-bit threshold
   uint32_t bits = 0;
+  if (!TR) {   // rows = queries {g, g+8}, columns = keys {t2, t2+1, t2+8, t2+9}: exactly one call
+    const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, row0 + g, col0 + t2), a.stream);
+    // half-words: x = (i, j) | (i, j+1); y = (i, j+8) | (i, j+9); z = (i+8, j) | (i+8, j+1); w = (i+8, j+8) | (i+8, j+9)
+    bits |= ((w.x & 0xffffu) >= thr ? 1u : 0u) << 0;   // tile 0, reg 0
+    bits |= ((w.x >> 16) >= thr ? 1u : 0u) << 1;       // tile 0, reg 1
+    bits |= ((w.z & 0xffffu) >= thr ? 1u : 0u) << 2;   // tile 0, reg 2 (row g+8)
+    bits |= ((w.z >> 16) >= thr ? 1u : 0u) << 3;
+    bits |= ((w.y & 0xffffu) >= thr ? 1u : 0u) << 4;   // tile 1, reg 0
+    bits |= ((w.y >> 16) >= thr ? 1u : 0u) << 5;
+    bits |= ((w.w & 0xffffu) >= thr ? 1u : 0u) << 6;
+    bits |= ((w.w >> 16) >= thr ? 1u : 0u) << 7;
+  } else {     // rows = keys {g, g+8}, columns = queries {t2, t2+1, t2+8, t2+9}: the two query parities are two calls
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    const int i = TR ? col0 + t2 + e : row0 + g, j = TR ? row0 + g : col0 + t2 + e;
-    const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, i, j), a.stream);
-    // word = 2 * (i bit 3) + (j bit 3); accumulator register = 2 * (row bit 3) + e, n-tile parity = column bit 3
-    if (!TR) {
-      bits |= (w.x >= a.drop_thresh ? 1u : 0u) << (0 + e);        // (i, j)      : tile 0, reg e
-      bits |= (w.y >= a.drop_thresh ? 1u : 0u) << (4 + e);        // (i, j+8)    : tile 1, reg e
-      bits |= (w.z >= a.drop_thresh ? 1u : 0u) << (2 + e);        // (i+8, j)    : tile 0, reg 2+e
-      bits |= (w.w >= a.drop_thresh ? 1u : 0u) << (6 + e);        // (i+8, j+8)  : tile 1, reg 2+e
-    } else {
-      bits |= (w.x >= a.drop_thresh ? 1u : 0u) << (0 + e);        // (i, j)      : row j, col i     -> tile 0, reg e
-      bits |= (w.y >= a.drop_thresh ? 1u : 0u) << (2 + e);        // (i, j+8)    : row j+8          -> tile 0, reg 2+e
-      bits |= (w.z >= a.drop_thresh ? 1u : 0u) << (4 + e);        // (i+8, j)    : col i+8          -> tile 1, reg e
-      bits |= (w.w >= a.drop_thresh ? 1u : 0u) << (6 + e);        // (i+8, j+8)                     -> tile 1, reg 2+e
+    for (int e = 0; e < 2; ++e) {
+      const int i = col0 + t2 + e, j = row0 + g;
+      const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, i, j), a.stream);
+      bits |= (attn_dropout_half(w, i, j) >= thr ? 1u : 0u) << (0 + e);           // (i, j)     : row j,   tile 0, reg e
+      bits |= (attn_dropout_half(w, i, j + 8) >= thr ? 1u : 0u) << (2 + e);       // (i, j+8)   : row j+8, tile 0, reg 2+e
+      bits |= (attn_dropout_half(w, i + 8, j) >= thr ? 1u : 0u) << (4 + e);       // (i+8, j)   : tile 1, reg e
+      bits |= (attn_dropout_half(w, i + 8, j + 8) >= thr ? 1u : 0u) << (6 + e);   // (i+8, j+8) : tile 1, reg 2+e
     }
   }
   return bits;
@@ -527,7 +534,7 @@ static int fill(Args& a, const TtsAttnTrain* t) {
   a.drop_scale = 1.f;
   if (t->drop_p > 0.f) {
     TTS_REQUIRE(t->drop_p < 1.f, "attn_train: drop_p must be < 1");
-    a.drop_thresh = drop_threshold(t->drop_p);
+    a.drop_thresh = drop_threshold16(t->drop_p);
     a.drop_scale = 1.f / (1.f - t->drop_p);
     a.seed = t->seed; a.stream = t->rng_stream;
   }

@@ -35,6 +35,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace tts {
 namespace pipe {
@@ -75,6 +76,10 @@ struct Args {
   int n_steps, update_state;
   int group_rows, n_groups, n_split, ksplit;
   int prefetch;         // L2 prefetch of upcoming K/V streams (TTS_PREFETCH=1 enables it)
+  // decoder.train() at synthesis time (eval.py:116-117): Philox dropout, p = decoder_dropout_rate after the two prenet
+  // ReLUs (tacotron.py:58,62) and p = transformer_dropout_rate after the PE add, on every attention weight, every
+  // residual-branch output and the FFN hidden (modules.py:120,132,138,141,18; attention.py:89).  0 = off.
+  uint32_t thr_d, thr_t; float sc_d, sc_t; unsigned long long seed;
   int ring_lo, n_slots, n_hi;   // K/V ring.  Slots [0, n_hi) sit above the weight tiles of the GEMM that precedes an
                                 // attention phase (from float ring_lo on, below the next GEMM's tiles): they may be
                                 // filled while that GEMM still runs.  Slots [n_hi, n_slots) reuse the space of those
@@ -90,6 +95,7 @@ struct Desc {
   float inv_k;          // 1 / K
   float* Y; long long ldy; const float* R; long long ldr; float out_scale;
   float* kcache; float* vcache;
+  uint32_t drop_thr; float drop_sc; uint32_t drop_site;   // dropout on the stored value (before the residual add); 0 = none
   // ---- attention over a K/V stream
   const float* kc; const float* vc; int rows_alloc, n_keys; const int32_t* key_len;
   float* align; long long align_bh_stride; int align_row_len;
@@ -221,6 +227,13 @@ __device__ __forceinline__ f32x4 ld4cg(const float* p) {
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// dropout of ONE value: element e of dropout site `site` (philox.cuh: four consecutive elements share a call)
+__device__ __forceinline__ float drop1(unsigned long long seed, uint32_t thr, float sc, uint32_t site, unsigned long long e, float v) {
+  const uint4 w = philox4x32(seed, e >> 2, site);
+  const uint32_t k = (uint32_t)(e & 3ull);
+  const uint32_t r = k == 0u ? w.x : (k == 1u ? w.y : (k == 2u ? w.z : w.w));
+  return r >= thr ? v * sc : 0.f;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -393,6 +406,8 @@ struct CState {
 template <int DH>
 __device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Smem& sm, const Slice& s, int b, int n, int t,
                                           float v, float res) {
+  if (d.drop_thr != 0u && d.mode != kFinal && d.mode != kPrenetOut)   // CTA-uniform: decode in decoder.train() mode only
+    v = drop1(a.seed, d.drop_thr, d.drop_sc, d.drop_site, ((unsigned long long)t * a.st.batch + b) * (unsigned)d.N + (unsigned)n, v);
   switch (d.mode) {
     case kPlain:
       d.Y[(size_t)b * d.ldy + n] = v * d.out_scale + res;
@@ -419,13 +434,22 @@ __device__ __forceinline__ void store_out(const Args& a, const Desc& d, const Sm
     } break;
     case kPrenetOut: {  // modules.py:114-118
       const bool have = t > 0 && (t - 1) < sm.len[b];
-      d.Y[(size_t)b * d.ldy + n] = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * d.N + n) * __ldg(a.w.pe_scale);
+      float o = (have ? v : 0.f) + __ldg(a.w.pe_table + (size_t)t * d.N + n) * __ldg(a.w.pe_scale);
+      if (d.drop_thr != 0u)   // modules.py:120: dropout on the sum
+        o = drop1(a.seed, d.drop_thr, d.drop_sc, d.drop_site, ((unsigned long long)t * a.st.batch + b) * (unsigned)d.N + (unsigned)n, o);
+      d.Y[(size_t)b * d.ldy + n] = o;
     } break;
     case kFinal: {  // modules.py:144, tacotron.py:112-115
       const bool on = t < sm.len[b];
       if (n < a.w.n_mels) a.st.frames[((size_t)b * a.st.t_max + t) * a.w.n_mels + n] = on ? v : 0.f;
       else if (n == a.w.n_mels) a.st.stop_logits[(size_t)b * a.st.t_max + t] = on ? v + __ldg(a.w.b_stop) : 0.f;
-      else a.p0[(size_t)b * (a.w.prenet_hidden + kXPad) + (n - a.w.n_mels - 1)] = fmaxf(v, 0.f);
+      else {   // first prenet layer of the NEXT step (its dropout uses that step's element index, site 1)
+        const int pn = n - a.w.n_mels - 1;
+        float o = fmaxf(v, 0.f);
+        if (a.thr_d != 0u)
+          o = drop1(a.seed, a.thr_d, a.sc_d, 1u, ((unsigned long long)(t + 1) * a.st.batch + b) * (unsigned)a.w.prenet_hidden + (unsigned)pn, o);
+        a.p0[(size_t)b * (a.w.prenet_hidden + kXPad) + pn] = o;
+      }
     } break;
   }
 }
@@ -583,14 +607,15 @@ __device__ __forceinline__ void gemm_group(const Args& a, const Desc& d, const S
 }
 
 // ---- reduce group-phase: x[b][n] += sum_s part[s][b][n] (FFN-out partials + residual) ------------------------
-__device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g) {
+__device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g, int t) {
   const int B = a.st.batch, G = gridDim.x, c = blockIdx.x;
   const int b0 = g * a.group_rows, rows = min(a.group_rows, B - b0);
   const int n_lo = d.s_n_lo, n_hi = d.s_n_hi, ncols = n_hi - n_lo;
   (void)G; (void)c;
   for (int idx = threadIdx.x; idx < rows * ncols; idx += kConsumers) {
     const int row = idx / ncols, n = n_lo + idx - row * ncols, b = b0 + row;
-    float v = __ldcg(d.Y + (size_t)b * d.ldy + n);
+    const float x0 = __ldcg(d.Y + (size_t)b * d.ldy + n);
+    float v = 0.f;
     for (int s0 = 0; s0 < d.n_parts; s0 += 4) {   // four independent loads in flight
       float pv[4];
 #pragma unroll
@@ -598,7 +623,9 @@ __device__ __forceinline__ void reduce_group(const Args& a, const Desc& d, int g
         pv[i] = s0 + i < d.n_parts ? __ldcg(d.part + ((size_t)(s0 + i) * B + b) * d.N + n) : 0.f;
       v += (pv[0] + pv[1]) + (pv[2] + pv[3]);
     }
-    d.Y[(size_t)b * d.ldy + n] = v;
+    if (d.drop_thr != 0u)   // modules.py:141: x + dropout(ffn(x))
+      v = drop1(a.seed, d.drop_thr, d.drop_sc, d.drop_site, ((unsigned long long)t * B + b) * (unsigned)d.N + (unsigned)n, v);
+    d.Y[(size_t)b * d.ldy + n] = x0 + v;
   }
 }
 
@@ -734,10 +761,13 @@ __device__ __forceinline__ void feed_group(const Args& a, const Smem& sm, const 
 }
 
 // one tile of 8 keys: scores, online softmax update, weighted V.  FULL: all 8 keys exist and none is masked.
+struct DropA {   // dropout on the attention weights of one stream (attention.py:89): element = ebase + key index
+  uint32_t thr; float sc; unsigned long long seed; uint32_t site; unsigned long long ebase;
+};
 template <int DH, bool FULL>
 __device__ __forceinline__ void attn_tile(const float* kt, const float* vt, const f32x4 (&qv)[DH / 32], int nk, int key0,
                                           int klen, float* logit_dst, float& m_run, float& l_run,
-                                          f32x2 (&o)[DH / 32][2], int kslot, int l8) {
+                                          f32x2 (&o)[DH / 32][2], int kslot, int l8, const DropA& da) {
   constexpr int F4 = DH / 32, kRounds = kTK / 4;
   float sv[kRounds];
 #pragma unroll
@@ -787,8 +817,9 @@ __device__ __forceinline__ void attn_tile(const float* kt, const float* vt, cons
   for (int r = 0; r < kRounds; ++r) {
     const int kl = r * 4 + kslot;
     const float p = (FULL || kl < nk) ? ex2(sv[r] - m_run) : 0.f;
-    if (l8 == 0) l_run += p;
-    const f32x2 pp = pack2(p, p);
+    if (l8 == 0) l_run += p;   // the softmax normaliser sums the weights BEFORE dropout (attention.py:87-89)
+    const float pd = da.thr != 0u ? drop1(da.seed, da.thr, da.sc, da.site, da.ebase + (unsigned)(key0 + kl), p) : p;
+    const f32x2 pp = pack2(pd, pd);
 #pragma unroll
     for (int i = 0; i < F4; ++i) {
       const f32x4 vv = ld4s(vt + kl * DH + 4 * (l8 + 8 * i));
@@ -851,6 +882,7 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
 #pragma unroll
     for (int i = 0; i < F4; ++i) o[i][0] = o[i][1] = 0ull;
     if (prof) prof[6] = clock64();
+    const DropA da{at.drop_thr, at.drop_sc, a.seed, at.drop_site, ((unsigned long long)t * (unsigned)(B * H) + (unsigned)item) << 16};
 
     // slot and use number of this warp's first tile; advanced incrementally (no division in the loop)
     unsigned slot = (seq_base + (unsigned)warp) % (unsigned)a.n_slots, use = (seq_base + (unsigned)warp) / (unsigned)a.n_slots;
@@ -861,9 +893,9 @@ __device__ __forceinline__ void attn_group(const Args& a, const Desc& at, const 
       const float* kt = slot_ptr<DH>(a, sm, slot);
       float* ldst = arow == nullptr ? nullptr : ((ns == 1 && sc_ok) ? sc + (key0 - j0) : arow + key0);
       if (nk == kTK && key0 + kTK <= klen)
-        attn_tile<DH, true>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8);
+        attn_tile<DH, true>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8, da);
       else
-        attn_tile<DH, false>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8);
+        attn_tile<DH, false>(kt, kt + kTile, qv, nk, key0, klen, ldst, m_run, l_run, o, kslot, l8, da);
       __syncwarp();   // every lane is done with this slot before it is refilled
       if (lane == 0)
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&sm.drained[slot])), "r"(use + 1u) : "memory");
@@ -1039,16 +1071,19 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
     d.X = a.st.frames + (size_t)(t > 0 ? t - 1 : 0) * M; d.ldx = (long long)T * M; d.zero_x = t == 0;
     d.K = M; d.N = P; d.W = a.w.pk_pre0; d.relu = 1;
     d.mode = kPlain; d.Y = a.p0; d.ldy = P + kXPad; d.hi = 1;
+    d.drop_thr = a.thr_d; d.drop_sc = a.sc_d; d.drop_site = 1u;
     return;
   }
   if (ph == 1) {
     d.X = a.p0; d.ldx = P + kXPad; d.K = P; d.N = P; d.W = a.w.pk_pre1;
     d.relu = 1; d.mode = kPlain; d.Y = a.p1; d.ldy = P + kXPad; d.hi = 0;
+    d.drop_thr = a.thr_d; d.drop_sc = a.sc_d; d.drop_site = 2u;
     return;
   }
   if (ph == 2) {         // + shift / mask / PE (modules.py:114-118)
     d.X = a.p1; d.ldx = P + kXPad; d.K = P; d.N = D; d.W = a.w.pk_pre2; d.mode = kPrenetOut;
     d.Y = a.x; d.ldy = D + kXPad; d.hi = 1;
+    d.drop_thr = a.thr_t; d.drop_sc = a.sc_t; d.drop_site = 3u;
     return;
   }
   if (ph == 3 + ppl * L) {  // final LN + mel / stop projections
@@ -1070,6 +1105,13 @@ __device__ __forceinline__ void get_phase_body(const Args& a, int ph, int t, flo
   const size_t self_off = (size_t)l * B * H * T * DH, cross_off = (size_t)l * B * H * S * DH;
   float* al_self = a.st.align_self ? a.st.align_self + (size_t)l * B * H * T * T : nullptr;
   float* al_cross = a.st.align_cross ? a.st.align_cross + (size_t)l * B * H * T * S : nullptr;
+  const uint32_t site0 = 16u + 8u * (uint32_t)l;   // dropout sites of layer l: +0 self weights, +1 self out, +2 cross weights,
+                                                   // +3 cross out, +4 FFN hidden, +5 FFN out
+  const bool drop_here = id == 1 || id == 3 || id == 5 || id == 7 || id == 8 || (id == 9 && !red) || id == 10;
+  if (drop_here) {
+    d.drop_thr = a.thr_t; d.drop_sc = a.sc_t;
+    d.drop_site = site0 + (id == 1 ? 0u : id == 3 ? 1u : id == 5 ? 2u : id == 7 ? 3u : id == 8 ? 4u : 5u);
+  }
   switch (id) {
     case 0:  // LN + QKV (attention.py:63-64), k/v appended at row t
       d.ln = 1; d.X = a.x; d.ldx = D + kXPad; d.K = D; d.N = 3 * D; d.W = lw.pk_qkv;
@@ -1272,7 +1314,7 @@ __global__ void __launch_bounds__(kThreads, 1) pipelined_decode_kernel(const __g
             if (lane == 0) mbar_arrive(sm.x_empty);
             if (prof && g == 0) prof[11] = clock64();
             if (d.kind == kAttn) attn_group<DH>(a, d, sm, cs, g, t, g == 0 ? prof : nullptr);
-            else if (d.kind == kReduce) reduce_group(a, d, g);
+            else if (d.kind == kReduce) reduce_group(a, d, g, t);
             else combine_group<DH>(a, d, sm, g, t);
           }
           consumer_bar();
@@ -1474,6 +1516,11 @@ int launch_pipelined_steps(const TtsDecoderWeights* w, const TtsDecodeState* st,
   a.n_split = split_for(w, a.group_rows, num_sms());
   a.ksplit = ksplit_for(w);
   a.prefetch = getenv("TTS_PREFETCH") != nullptr;   // off by default: it competes with the weight stream (measured -3 %)
+  a.thr_d = st->drop_p_prenet > 0.f ? drop_threshold(st->drop_p_prenet) : 0u;
+  a.sc_d = st->drop_p_prenet > 0.f ? 1.f / (1.f - st->drop_p_prenet) : 1.f;
+  a.thr_t = st->drop_p_transformer > 0.f ? drop_threshold(st->drop_p_transformer) : 0u;
+  a.sc_t = st->drop_p_transformer > 0.f ? 1.f / (1.f - st->drop_p_transformer) : 1.f;
+  a.seed = st->drop_seed;
   a.n_slots = ring_slots(w, num_sms(), &a.ring_lo, &a.n_hi);
   TTS_CHECK_CUDA(cudaMemsetAsync(c.bar, 0, (32 * kMaxGroups + 32) * sizeof(unsigned), s));  // counters + error flag
   switch (w->d_model / w->n_heads) {

@@ -154,7 +154,12 @@ class Decoder(nn.Module):
                 inc = {"engine": eng, "sess": eng.new_session(B, S, t_max, self.record_alignments),
                        "record": self.record_alignments}
                 self._inc = inc
-            inc["sess"].begin(encoder_outputs, input_lengths)
+            # `m.eval(); m.decoder.train()` (eval.py:116-117): live dropout in the decoder, eval everywhere else
+            hp = self.hparams
+            drop = None
+            if self.training and (hp.decoder_dropout_rate > 0 or hp.transformer_dropout_rate > 0):
+                drop = (hp.decoder_dropout_rate, hp.transformer_dropout_rate, eng.next_dropout_seed())
+            inc["sess"].begin(encoder_outputs, input_lengths, dropout=drop)
             inc["key"] = key
         elif (inc is None or inc["engine"] is not eng or inc.get("key") != key or inc["sess"].batch != B
               or inc["sess"].t + 1 != T or T > inc["sess"].t_max):
@@ -177,12 +182,12 @@ class Decoder(nn.Module):
                                             input_lengths, targets, target_lengths, *self.parameters())
             return mels, stop, {"self": [], "encdec": []}
         eng = engine_for(self, "decoder.", self.hparams)
-        if self.training and (self.hparams.decoder_dropout_rate > 0 or self.hparams.transformer_dropout_rate > 0):
-            eng.warn_dropout("Decoder")
         if leave_one:
             out = self._incremental(eng, encoder_outputs, input_lengths, targets, target_lengths)
             if out is not None:
                 return out
+        if self.training and (self.hparams.decoder_dropout_rate > 0 or self.hparams.transformer_dropout_rate > 0):
+            eng.warn_dropout("Decoder")
         return eng.decode_teacher_forced(encoder_outputs, input_lengths, targets, target_lengths, leave_one=leave_one)
 
 

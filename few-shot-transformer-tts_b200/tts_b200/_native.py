@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libtts_b200.so")
 TTS_MAX_LAYERS = 16
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -72,7 +72,8 @@ class DecodeState(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("batch", "mem_len", "t_max")] +
                 [(n, C.c_void_p) for n in ("memory", "input_lengths", "self_k", "self_v", "cross_k", "cross_v",
                                            "lengths", "finished", "frames", "stop_logits", "align_self", "align_cross",
-                                           "step_counter", "n_unfinished", "scratch")])
+                                           "step_counter", "n_unfinished", "scratch")] +
+                [("drop_p_prenet", C.c_float), ("drop_p_transformer", C.c_float), ("drop_seed", C.c_uint64)])
 
 
 _EXPORTS = {

@@ -77,6 +77,7 @@ class DecodeSession:
         self.input_lengths = None
         self.t = 0
         self._st = None
+        self.dropout = (0.0, 0.0, 0)   # (prenet rate, transformer rate, seed): decoder.train() at synthesis time
 
     def state(self):
         st = N.DecodeState()
@@ -88,10 +89,14 @@ class DecodeSession:
             setattr(st, name, N.ptr(getattr(self, name)))
         st.step_counter = self.counters.data_ptr()
         st.n_unfinished = self.counters.data_ptr() + 4
+        st.drop_p_prenet, st.drop_p_transformer, st.drop_seed = self.dropout
         return st
 
-    def begin(self, memory, input_lengths):
-        """Once per utterance batch: cross K/V from the encoder memory, reset lengths/finished/t."""
+    def begin(self, memory, input_lengths, dropout=None):
+        """Once per utterance batch: cross K/V from the encoder memory, reset lengths/finished/t.
+        dropout = (prenet rate, transformer rate, seed) decodes with the reference's `decoder.train()` semantics
+        (eval.py:116-117); None / zeros = deterministic."""
+        self.dropout = (0.0, 0.0, 0) if dropout is None else (float(dropout[0]), float(dropout[1]), int(dropout[2]))
         self.memory = N.f32c(memory)
         self.input_lengths = ops._i32(input_lengths)
         assert self.memory.shape == (self.batch, self.mem_len, self.engine.cfg.decoder_hidden), self.memory.shape
@@ -294,9 +299,13 @@ class TtsEngine:
 
     def warn_dropout(self, what):
         if not self._warned_dropout:
-            warnings.warn("tts_b200: %s is in train() mode under no_grad; the CUDA path does not apply dropout "
-                          "(deterministic output; the reference would sample dropout masks here)" % what)
+            warnings.warn("tts_b200: %s is in train() mode under no_grad on a full-sequence (non-incremental) call; this path "
+                          "does not apply dropout (the K/V-cached decode and the training step do)" % what)
             self._warned_dropout = True
+
+    def next_dropout_seed(self):
+        self._drop_calls = getattr(self, "_drop_calls", 0) + 1
+        return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + self._drop_calls * 0xD1B54A32D192ED03) & 0x7fffffffffffffff
 
     # ---- encoder (tacotron.py:33-44, modules.py:49-69) ------------------------------------------
     def encoder_stack(self, ids, embedded, input_lengths, batch, seq):
@@ -440,7 +449,7 @@ class TtsEngine:
         return DecodeSession(self, batch, mem_len, t_max, record_align)
 
     def generate(self, batch, max_frames=None, record_align="encdec", chunk=32, impl=0, session=None,
-                 memory=None):
+                 memory=None, dropout=None):
         cfg = self.cfg
         max_frames = cfg.max_generation_frames if max_frames is None else max_frames
         if memory is None:
@@ -448,7 +457,7 @@ class TtsEngine:
                                  batch.get("input_language_vecs"))
         B, S, _ = memory.shape
         sess = session if session is not None else self.new_session(B, S, max_frames, record_align)
-        sess.begin(memory, batch["input_lengths"].to(self.device))
+        sess.begin(memory, batch["input_lengths"].to(self.device), dropout=dropout)
         done = 0
         all_finished = False
         while done < max_frames:

@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define TTS_MAX_LAYERS 16
-#define TTS_ABI_VERSION 9
+#define TTS_ABI_VERSION 10
 
 /* ---- library / diagnostics -------------------------------------------------------------- */
 int tts_abi_version(void);
@@ -321,6 +321,13 @@ typedef struct TtsDecodeState {
   int32_t* step_counter;        /* device scalar: next step index t */
   int32_t* n_unfinished;        /* device scalar, refreshed every step */
   float* scratch;               /* tts_decode_scratch_bytes() bytes */
+  /* decoder.train() at synthesis time (eval.py:116-117, train.py:229-234): Philox dropout with rate drop_p_prenet after
+   * the two prenet ReLUs (tacotron.py:58,62) and drop_p_transformer after the position-encoding add, on the attention
+   * weights (after the softmax normalisation; the recorded alignment rows are pre-dropout like attention.py:88), on
+   * every residual-branch output and on the FFN hidden (modules.py:18,120,132,138,141).  Masks are a pure function of
+   * (drop_seed, site, step, row, element): csrc/philox.cuh.  0 / 0 = deterministic eval() semantics. */
+  float drop_p_prenet, drop_p_transformer;
+  uint64_t drop_seed;
 } TtsDecodeState;
 
 size_t tts_decode_scratch_bytes(const TtsDecoderWeights* w, int32_t batch, int32_t mem_len,

@@ -290,7 +290,7 @@ def eval_batch_uncached(params: Params, cfg: ModelConfig, batch, max_frames: Opt
 
 def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optional[int] = None,
                       dtype=torch.float32, return_trace: bool = False, resume: Optional[dict] = None,
-                      memory: Optional[torch.Tensor] = None):
+                      memory: Optional[torch.Tensor] = None, dropout=None):
     """Mathematically identical K/V-cached restatement of the same loop (SURVEY.md
     Appendix A): one decoder *row* per step; self K/V appended to a (preallocated) cache, cross
     K/V of the encoder memory computed once.  Used by tests to localise per-step kernel bugs and
@@ -301,8 +301,14 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
     ``resume`` = {"t": t0, "self_k": [L x [B,H,t0,dh]], "self_v": ..., "prev": [B,M],
     "lengths": [B] int32, "finished": [B] bool} continues a decode from step t0 with the given
     state (tests use it to check late steps of very long decodes without replaying all of them);
-    ``max_frames`` is then the absolute step to stop at."""
+    ``max_frames`` is then the absolute step to stop at.
+
+    ``dropout(site, layer, t, x)`` (optional) applies a caller-defined dropout mask at every place the reference's
+    ``decoder.train()`` mode does (eval.py:116-117): sites "pre0" / "pre1" (tacotron.py:58,62), "dec_in"
+    (modules.py:120), "self_w" / "cross_w" (attention.py:89, after the softmax), "self_out" / "cross_out" / "ffn_out"
+    (modules.py:132,138,141) and "ffn_hid" (modules.py:18).  Tests pass the masks of csrc/philox.cuh."""
     max_frames = cfg.max_generation_frames if max_frames is None else max_frames
+    drop = dropout if dropout is not None else (lambda site, layer, t, x: x)
     B = batch["inputs"].shape[0]
     Hn, L, D, M = cfg.n_attention_head, cfg.n_decoder_layer, cfg.decoder_hidden, cfg.num_mels
     mem = memory if memory is not None else encoder_forward(
@@ -339,9 +345,14 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
     while not bool(finished.all()) and t < max_frames:
         if t == 0:
             x = torch.zeros(B, D, dtype=dtype, device=dev)
-        else:
+        elif dropout is None:
             x = prenet(params, prev) * ((t - 1) < lengths)[:, None].to(dtype)
-        x = x + pe[t]
+        else:                                                                  # tacotron.py:55-65 with its dropouts
+            pp = "decoder.prenet."
+            h0 = drop("pre0", 0, t, torch.relu(prev @ params[pp + "dense0.weight"].to(dtype).t() + params[pp + "dense0.bias"].to(dtype)))
+            h1 = drop("pre1", 0, t, torch.relu(h0 @ params[pp + "dense1.weight"].to(dtype).t() + params[pp + "dense1.bias"].to(dtype)))
+            x = (h1 @ params[pp + "dense_final.weight"].to(dtype).t()) * ((t - 1) < lengths)[:, None].to(dtype)
+        x = drop("dec_in", 0, t, x + pe[t])                                    # modules.py:117-120
         for l in range(L):
             h = _ln(x, params, f"{p}attn_layer_norms.{l}")
             qkv = h @ params[f"{p}self_attentions.{l}.qkv_transform.weight"].to(dtype).t()
@@ -349,16 +360,18 @@ def eval_batch_cached(params: Params, cfg: ModelConfig, batch, max_frames: Optio
             kbuf[l][:, :, t] = k.view(B, Hn, dh)
             vbuf[l][:, :, t] = v.view(B, Hn, dh)
             q = q.view(B, Hn, 1, dh) * dh ** -0.5
-            w = torch.softmax(q @ kbuf[l][:, :, :t + 1].transpose(2, 3), dim=-1)
+            w = drop("self_w", l, t, torch.softmax(q @ kbuf[l][:, :, :t + 1].transpose(2, 3), dim=-1))
             a = (w @ vbuf[l][:, :, :t + 1]).reshape(B, D)
-            x = x + a @ params[f"{p}self_attentions.{l}.output_transform.weight"].to(dtype).t()
+            x = x + drop("self_out", l, t, a @ params[f"{p}self_attentions.{l}.output_transform.weight"].to(dtype).t())
             h = _ln(x, params, f"{p}encdec_layer_norms.{l}")
             q = (h @ params[f"{p}encdec_attentions.{l}.q_transform.weight"].to(dtype).t())
             q = q.view(B, Hn, 1, dh) * dh ** -0.5
-            w = torch.softmax(q @ cross_k[l].transpose(2, 3) + key_bias, dim=-1)
+            w = drop("cross_w", l, t, torch.softmax(q @ cross_k[l].transpose(2, 3) + key_bias, dim=-1))
             a = (w @ cross_v[l]).reshape(B, D)
-            x = x + a @ params[f"{p}encdec_attentions.{l}.output_transform.weight"].to(dtype).t()
-            x = x + ffn(params, f"{p}ffn_layers.{l}", _ln(x, params, f"{p}ffn_layer_norms.{l}"))
+            x = x + drop("cross_out", l, t, a @ params[f"{p}encdec_attentions.{l}.output_transform.weight"].to(dtype).t())
+            hid = torch.relu(_ln(x, params, f"{p}ffn_layer_norms.{l}") @ params[f"{p}ffn_layers.{l}.input_layer.weight"].to(dtype).t())
+            hid = drop("ffn_hid", l, t, hid)                                    # modules.py:14-19
+            x = x + drop("ffn_out", l, t, hid @ params[f"{p}ffn_layers.{l}.output_layer.weight"].to(dtype).t())
         live = (t < lengths)[:, None].to(dtype)
         o = _ln(x, params, p + "output_layer_norm") * live
         mel = (o @ params["decoder.mel_net.weight"].to(dtype).t()) * live

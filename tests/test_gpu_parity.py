@@ -656,3 +656,87 @@ def test_module_api_submodules(tiny_params, ops):
     want = O.encoder_forward(params, cfg, b["inputs"], b["input_lengths"], b["input_spk_ids"], b["input_language_vecs"])
     assert _err(memo, want) < KERNEL_TOL
     assert _err(emb, want[:, :, :cfg.encoder_hidden]) < KERNEL_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder.train() at synthesis time (eval.py:116-117): Philox dropout inside the decode kernel
+# ---------------------------------------------------------------------------------------------
+def _philox_np(seed, idx, stream):
+    idx = np.asarray(idx, dtype=np.uint64)
+    M32 = np.uint64(0xffffffff)
+    k0, k1 = np.uint64(seed & 0xffffffff), np.uint64(seed >> 32)
+    c0, c1 = idx & M32, idx >> np.uint64(32)
+    c2, c3 = np.full_like(idx, stream), np.full_like(idx, 0x5eed)
+    for _ in range(7):
+        p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & M32, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & M32
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M32, (k1 + np.uint64(0xBB67AE85)) & M32
+    return np.stack([c0, c1, c2, c3], axis=-1)
+
+
+def _keep(seed, site, e, p):
+    e = np.asarray(e, dtype=np.uint64)
+    w = _philox_np(seed, (e >> np.uint64(2)).reshape(-1), site)
+    r = np.take_along_axis(w, (e.reshape(-1) & np.uint64(3)).astype(np.int64)[:, None], axis=1)[:, 0]
+    return torch.from_numpy((r >= np.uint64(min(int(p * 4294967296.0), 0xffffffff))).reshape(e.shape))
+
+
+def test_decode_dropout_matches_oracle_with_the_same_masks(tiny_params, ops):
+    """`m.eval(); m.decoder.train()` semantics (SURVEY §8b "Modes"): the decode kernel's Philox dropout against the oracle
+    applying the SAME masks (csrc/philox.cuh restated in numpy) at every site the reference drops - placement, scaling and
+    the pre-dropout softmax normaliser are all pinned, not just a keep rate.  Also: keep rate, seed dependence, eval mode."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = tiny_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    batch = O.synth_batch(cfg, batch=5, text_len=24, n_frames=4, seed=7, ragged=True)
+    B, H, T = 5, cfg.n_attention_head, 12
+    pd, pt, seed = 0.5, 0.1, 0x1234abcd5678
+    names = {"self_w": 0, "self_out": 1, "cross_w": 2, "cross_out": 3, "ffn_hid": 4, "ffn_out": 5}
+    rates = []
+
+    def drop(site, layer, t, x):
+        if site in ("pre0", "pre1", "dec_in"):
+            sid, rate = {"pre0": 1, "pre1": 2, "dec_in": 3}[site], (pt if site == "dec_in" else pd)
+        else:
+            sid, rate = 16 + 8 * layer + names[site], pt
+        if site.endswith("_w"):      # [B,H,1,Tk]: element = ((t * B * H + bh) << 16) + key
+            Tk = x.shape[-1]
+            bh = np.arange(B * H, dtype=np.uint64)[:, None]
+            e = ((np.uint64(t) * np.uint64(B * H) + bh) << np.uint64(16)) + np.arange(Tk, dtype=np.uint64)[None, :]
+            keep = _keep(seed, sid, e, rate).view(B, H, 1, Tk)
+        else:                        # [B,N]: element = (t * B + b) * N + n
+            Nn = x.shape[-1]
+            e = (np.uint64(t) * np.uint64(B) + np.arange(B, dtype=np.uint64)[:, None]) * np.uint64(Nn) + np.arange(Nn, dtype=np.uint64)[None, :]
+            keep = _keep(seed, sid, e, rate)
+        rates.append((rate, float(keep.float().mean()), keep.numel()))
+        return x * keep.to(x.dtype) / (1 - rate)
+
+    want = O.eval_batch_cached(p, cfg, batch, T, dropout=drop)
+    got = eng.generate(batch, max_frames=T, record_align="encdec", chunk=5, dropout=(pd, pt, seed))
+    e = _err(got["mel_pre"], want["mel_pre"])
+    print("decode with dropout vs oracle with the same masks: max-abs %.2e" % e)
+    assert e < 2e-4 and _err(got["mel_aft"], want["mel_aft"]) < 2e-4
+    big = [(r, k) for r, k, n in rates if n >= 4096]
+    assert big and all(abs(k - (1 - r)) < 0.03 for r, k in big)
+    plain = eng.generate(batch, max_frames=T, record_align="encdec", chunk=5)
+    other = eng.generate(batch, max_frames=T, record_align="encdec", chunk=5, dropout=(pd, pt, seed + 1))
+    assert _err(plain["mel_pre"], got["mel_pre"]) > 1e-2 and _err(other["mel_pre"], got["mel_pre"]) > 1e-2
+    assert _err(plain["mel_pre"], O.eval_batch_cached(p, cfg, batch, T)["mel_pre"]) < 2e-4
+    with pytest.raises(RuntimeError):     # only the pipelined kernel implements it: no silent deterministic fallback
+        eng.generate(batch, max_frames=T, record_align="none", chunk=5, impl=1, dropout=(pd, pt, seed))
+    # through the module API: m.eval(); m.decoder.train() gives live dropout in the incremental decode path
+    from tts_b200.config import hparams_from
+    from transformer import tacotron
+    hp = hparams_from(cfg)
+    hp.max_generation_frames = T
+    m = tacotron.Tacotron(hp)
+    m.load_state_dict(p, strict=True)
+    m.to(DEV).eval()
+    dbatch = {k: (_dev(v) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    det = _eval_loop_like_synthesize(m, dbatch, T, cfg.num_mels)["mel_pre"]
+    m.decoder.train()
+    a = _eval_loop_like_synthesize(m, dbatch, T, cfg.num_mels)["mel_pre"]
+    b = _eval_loop_like_synthesize(m, dbatch, T, cfg.num_mels)["mel_pre"]
+    assert _err(a, det) > 1e-2 and _err(a, b) > 1e-2 and bool(torch.isfinite(a).all())

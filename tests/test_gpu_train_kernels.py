@@ -117,7 +117,7 @@ def test_gemm_bf16_conv5_taps(ops, B, T, cin, cout):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Philox4x32-10 restated in numpy: pins csrc/philox.cuh and lets the references apply the SAME dropout masks
+# Philox4x32-7 restated in numpy: pins csrc/philox.cuh and lets the references apply the SAME dropout masks
 # ---------------------------------------------------------------------------------------------------------------------
 def _philox(seed, idx, stream):
     import numpy as np
@@ -127,7 +127,7 @@ def _philox(seed, idx, stream):
     c0, c1 = idx & M32, idx >> np.uint64(32)
     c2 = np.full_like(idx, stream, dtype=np.uint64)
     c3 = np.full_like(idx, 0x5eed, dtype=np.uint64)
-    for _ in range(10):
+    for _ in range(7):
         p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
         hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & M32, p1 >> np.uint64(32), p1 & M32
         c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
@@ -149,15 +149,17 @@ def keep_linear(seed, stream, rows, cols, p):
 
 
 def keep_attn(seed, stream, BH, Tq, Tk, p):
-    """keep mask [BH, Tq, Tk] of the attention weights (philox.cuh attn_dropout_index)."""
+    """keep mask [BH, Tq, Tk] of the attention weights (philox.cuh attn_dropout_index / attn_dropout_half: 16 bits each)."""
     import numpy as np
+    u = np.uint64
     nI, nJ = (Tq + 15) // 16, (Tk + 15) // 16
-    bh, i, j = np.meshgrid(np.arange(BH, dtype=np.uint64), np.arange(Tq, dtype=np.uint64), np.arange(Tk, dtype=np.uint64), indexing="ij")
-    idx = (((bh * np.uint64(nI) + (i >> np.uint64(4))) * np.uint64(nJ) + (j >> np.uint64(4))) << np.uint64(6)) + (i & np.uint64(7)) * np.uint64(8) + (j & np.uint64(7))
-    word = (((i >> np.uint64(3)) & np.uint64(1)) * np.uint64(2) + ((j >> np.uint64(3)) & np.uint64(1))).astype(np.int64)
+    bh, i, j = np.meshgrid(np.arange(BH, dtype=u), np.arange(Tq, dtype=u), np.arange(Tk, dtype=u), indexing="ij")
+    idx = (((bh * u(nI) + (i >> u(4))) * u(nJ) + (j >> u(4))) << u(5)) + (i & u(7)) * u(4) + ((j & u(7)) >> u(1))
+    half = (u(4) * ((i >> u(3)) & u(1)) + u(2) * ((j >> u(3)) & u(1)) + (j & u(1))).astype(np.int64).reshape(-1)
     w = _philox(seed, idx.reshape(-1), stream)
-    r = np.take_along_axis(w, word.reshape(-1, 1), axis=1)[:, 0]
-    return torch.from_numpy((r >= np.uint64(_thresh(p))).reshape(BH, Tq, Tk))
+    word = np.take_along_axis(w, (half >> 1)[:, None], axis=1)[:, 0]
+    r = np.where(half & 1, word >> u(16), word & u(0xffff))
+    return torch.from_numpy((r >= u(min(int(p * 65536.0), 65535))).reshape(BH, Tq, Tk))
 
 
 def test_dropout_mask_is_the_documented_philox_function(ops):

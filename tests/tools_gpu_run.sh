@@ -38,4 +38,16 @@ for k, v in agg.most_common(25):
 print("total %.3f ms over %d launches" % (tot / 1e6, sum(cnt.values())))
 PY
     ;;
+  multi)      # N-GPU box: gradient equality (GradBuckets + DDP) and the train step at N GPUs ($2 = N)
+    N=${2:-2}
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/tools_multi_gpu.py 2>&1 | grep -E "PASS|FAIL|Error|error" | tail -8
+    for dp in buckets ddp; do
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 5 --warmup 3 --workload train --dp $dp > gpurun_out/r2_train_n${N}_${dp}.json 2> gpurun_out/r2_train_n${N}_${dp}.err
+      python -c "
+import json,sys
+d=json.loads([l for l in open('gpurun_out/r2_train_n${N}_${dp}.json') if l.startswith('{')][-1])
+print('N=${N} ${dp}: %.2f ms/step, %.0f frames/s, allreduce %s' % (d['value'], d['frames_per_s'], d.get('allreduce')))" || tail -5 gpurun_out/r2_train_n${N}_${dp}.err
+    done
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_n${N}.json 2> gpurun_out/r2_bench_n${N}.err; cut -c1-400 gpurun_out/r2_bench_n${N}.json
+    ;;
 esac
