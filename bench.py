@@ -216,6 +216,47 @@ def cpu_reference_sample(batch_size, text_len, horizon, repeats=1):
     return frames / min(times), times, frames
 
 
+def run_module_api_loop(args, dev, params, dev_batch):
+    """frames/s of the reference's own loop shape (synthesize.py:35-56) driving transformer.tacotron.Tacotron: encoder once,
+    then per frame torch.cat + Decoder.forward(leave_one=True) + stop bookkeeping + `torch.all(finished)` (a host sync)."""
+    from tts_b200.config import hparams_from
+    from tts_b200 import synthetic as O
+    from transformer import tacotron
+    cfg = O.ModelConfig(max_generation_frames=args.frames)
+    hp = hparams_from(cfg)
+    m = tacotron.Tacotron(hp)
+    m.load_state_dict(params, strict=True)
+    m.to(dev).eval()
+    horizon = min(args.frames, args.module_api_frames)
+    n = dev_batch["inputs"].shape[0]
+
+    def loop():
+        with torch.no_grad():
+            lengths = torch.ones([n], dtype=torch.int32, device=dev)
+            finished = torch.zeros([n], dtype=torch.bool, device=dev)
+            mels = torch.zeros([n, 0, cfg.num_mels], dtype=torch.float32, device=dev)
+            enc = m.encoder(dev_batch["inputs"], dev_batch["input_lengths"], dev_batch["input_spk_ids"], dev_batch["input_language_vecs"])
+            while not torch.all(finished) and mels.shape[1] < horizon:
+                dec_in = torch.cat([mels, torch.zeros([n, 1, cfg.num_mels], device=dev)], dim=1)
+                mel_bef, stop_logits, _ = m.decoder(enc, dev_batch["input_lengths"], dec_in, lengths, leave_one=True)
+                stop = stop_logits[:, -1] > 0
+                mels = torch.cat([mels, mel_bef[:, -1:]], dim=1)
+                finished = torch.logical_or(finished, stop)
+                lengths = torch.where(finished, lengths, lengths + 1)
+            return mels + m.postnet(mels, lengths)
+
+    loop()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    out = loop()
+    torch.cuda.synchronize(dev)
+    secs = time.perf_counter() - t0
+    return {"value": out.shape[0] * out.shape[1] / secs, "unit": UNIT, "frames": int(out.shape[1]),
+            "us_per_frame_step": 1e6 * secs / out.shape[1],
+            "note": "reference loop shape (synthesize.py:35-56) over transformer.tacotron.Tacotron: one cooperative launch, two "
+                    "torch.cat and one host sync per frame; first %d of %d frames (the torch.cat cost grows with t)" % (horizon, args.frames)}
+
+
 def gpu_eager_sample(dev, batch_size, text_len, horizon, frames):
     """the K/V-cached algorithm as plain PyTorch eager on the SAME B200 (cuBLAS fp32, TF32 off) -
     the de-facto existing Blackwell path for a K/V-cached decode, and the honest bar for our kernel.  This is the
@@ -403,6 +444,14 @@ def run_ours(args):
                 "launch_seconds": dec_secs / n_launch, "us_per_decode_step": 1e6 * dec_secs / args.frames,
                 "share_of_job": dec_secs / (secs / args.steps)}
 
+    # ---- the UNCHANGED synthesize.py call pattern (one Decoder.forward per frame through the drop-in module API, a
+    #      D2H sync per frame for `torch.all(finished)`), next to generate(): what a user who just swaps the package gets
+    module_api = None
+    if not args.no_module_api:
+        try:
+            module_api = run_module_api_loop(args, dev, params, dev_batch)
+        except Exception as exc:
+            module_api = {"error": repr(exc)[:300]}
     train = None
     if not args.no_train:
         try:
@@ -430,7 +479,8 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "gpu_eager_baseline": eager, "decode_impl": args.decode_impl, "train_step": train}
+                "gpu_eager_baseline": eager, "decode_impl": args.decode_impl, "module_api_loop": module_api,
+                "train_step": train}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
@@ -627,6 +677,8 @@ def main():
                     help="decode = the headline (default, also reports train_step); train = only the teacher-forced "
                          "training step (BASELINE metric 2); forward = teacher-forced forward pass only")
     ap.add_argument("--no-train", action="store_true", help="skip the train_step measurement of the default run")
+    ap.add_argument("--no-module-api", action="store_true", help="skip the per-frame module-API loop measurement")
+    ap.add_argument("--module-api-frames", type=int, default=300)
     ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"], help="gradient exchange of the train step at N > 1")
     ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")
     args = ap.parse_args()

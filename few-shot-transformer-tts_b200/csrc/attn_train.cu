@@ -370,6 +370,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
     }
     mma_a_tt<DH, 8>(s, qf, cK, 0);
     mma_a_tt<DH, 8>(dp, dof, cV, 0);
+    // interior tiles (every key visible to every query row of this warp) skip the mask arithmetic
+    const bool open_tile = kb + BKV <= klen && (!a.causal || kb + BKV - 1 <= q0 + warp * 16);
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       uint32_t bits = 0xffu;
@@ -377,8 +379,11 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_kernel(const Args a) {
 #pragma unroll
       for (int e8 = 0; e8 < 8; ++e8) {
         const int n = 2 * np + (e8 >> 2), e = e8 & 3;
-        const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
-        const float p = key_ok(a, i, j, klen) ? ex2(s[n][e] * a.scale_log2 - lse[e >> 1]) : 0.f;
+        float p = ex2(s[n][e] * a.scale_log2 - lse[e >> 1]);
+        if (!open_tile) {
+          const int i = i0 + (e >> 1) * 8, j = kb + n * 8 + t2 + (e & 1);
+          p = key_ok(a, i, j, klen) ? p : 0.f;
+        }
         const float dpe = ((bits >> e8) & 1u) ? dp[n][e] * a.drop_scale : 0.f;
         s[n][e] = p * (dpe - dl[e >> 1]) * a.scale;   // dS (scaled: dQ = scale * dS K)
       }
@@ -461,6 +466,15 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
     mma_a_tt<DH, 4>(st, kf, cQ, 0);
     mma_a_tt<DH, 4>(dpt, vf, cDO, 0);
     float pt[4][4];
+    // the per-query statistics of this thread's 8 columns, once per tile (not once per element)
+    float lq[4][2], dq_[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float2 l2 = *reinterpret_cast<const float2*>(cL + n * 8 + t2), d2 = *reinterpret_cast<const float2*>(cL + BQ2 + n * 8 + t2);
+      lq[n][0] = l2.x; lq[n][1] = l2.y; dq_[n][0] = d2.x; dq_[n][1] = d2.y;
+    }
+    // interior tiles: all 32 queries exist and see all 16 keys of this warp
+    const bool open_tile = qb + BQ2 <= a.Tq && j0 + warp * 16 + 16 <= klen && (!a.causal || j0 + warp * 16 + 15 <= qb);
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t bits = 0xffu;
@@ -468,13 +482,15 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
 #pragma unroll
       for (int e8 = 0; e8 < 8; ++e8) {
         const int n = 2 * np + (e8 >> 2), e = e8 & 3;
-        const int j = jr + (e >> 1) * 8, il = n * 8 + t2 + (e & 1), i = qb + il;
-        const bool ok = i < a.Tq && j < a.Tk && key_ok(a, i, j, klen);
-        const float p = ok ? ex2(st[n][e] * a.scale_log2 - cL[il]) : 0.f;
+        float p = ex2(st[n][e] * a.scale_log2 - lq[n][e & 1]);
+        if (!open_tile) {
+          const int j = jr + (e >> 1) * 8, i = qb + n * 8 + t2 + (e & 1);
+          p = (i < a.Tq && j < a.Tk && key_ok(a, i, j, klen)) ? p : 0.f;
+        }
         const bool keep = (bits >> e8) & 1u;
         pt[n][e] = keep ? p * a.drop_scale : 0.f;                         // dropped-and-scaled weights: dV = P_drop^T dO
         const float dpe = keep ? dpt[n][e] * a.drop_scale : 0.f;
-        st[n][e] = p * (dpe - cL[BQ2 + il]) * a.scale;                   // dS^T (scaled: dK = scale * dS^T Q)
+        st[n][e] = p * (dpe - dq_[n][e & 1]) * a.scale;                  // dS^T (scaled: dK = scale * dS^T Q)
       }
     }
     mma_p_t<DH, 4>(dv, pt, cDO, 0);

@@ -187,14 +187,29 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     part[(size_t)blockIdx.x * 2 * C + idx] = t;
   }
 }
-__global__ void colpart_finalize_kernel(const float* __restrict__ part, int n_blocks, int width, float* __restrict__ out0,
-                                        float* __restrict__ out1, int C) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= width) return;
-  float t = 0.f;
-  for (int b = 0; b < n_blocks; ++b) t += part[(size_t)b * width + idx];
-  if (idx < C) out0[idx] = t;
-  else if (out1) out1[idx - C] = t;
+// out[idx] = sum_b part[b][idx]: CTA = 32 columns x 8 block-groups (coalesced 128-byte reads, independent loads in flight)
+__global__ void __launch_bounds__(256) colpart_finalize_kernel(const float* __restrict__ part, int n_blocks, int width,
+                                                                float* __restrict__ out0, float* __restrict__ out1, int C) {
+  __shared__ float sh[8][33];
+  const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5, idx = blockIdx.x * 32 + cg;
+  float t0 = 0.f, t1 = 0.f;
+  if (idx < width) {
+    int b = rg;
+    for (; b + 8 < n_blocks; b += 16) {
+      t0 += part[(size_t)b * width + idx];
+      t1 += part[(size_t)(b + 8) * width + idx];
+    }
+    if (b < n_blocks) t0 += part[(size_t)b * width + idx];
+  }
+  sh[rg][cg] = t0 + t1;
+  __syncthreads();
+  if (rg == 0 && idx < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sh[r][cg];
+    if (idx < C) out0[idx] = t;
+    else if (out1) out1[idx - C] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -635,7 +650,7 @@ extern "C" int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x
   TTS_REQUIRE(channels % 4 == 0 && channels <= 128 * tr::kLnMaxV && lddy % 4 == 0, "ln_bwd_train: channels %d unsupported", channels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int blocks = ceil_div(rows, 8);
-  if (blocks > 1184) blocks = 1184;   // 8 CTAs of 8 warps per SM: enough rows in flight to cover the HBM latency
+  if (blocks > 592) blocks = 592;   // 4 CTAs of 8 warps per SM: enough rows in flight to cover the HBM latency
   const size_t smem = (size_t)16 * channels * sizeof(float);
   static bool attr = false;
   if (!attr || smem > 48 * 1024) {
@@ -645,11 +660,11 @@ extern "C" int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x
   tr::ln_bwd_kernel<<<blocks, 256, smem, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, mean, rstd, gamma, dres, dx, scratch, rows,
                                               channels, row_len, rows_per_batch > 0 ? rows_per_batch : rows);
   TTS_CHECK_LAUNCH();
-  tr::colpart_finalize_kernel<<<ceil_div(2 * channels, 256), 256, 0, s>>>(scratch, blocks, 2 * channels, dgamma, dbeta, channels);
+  tr::colpart_finalize_kernel<<<ceil_div(2 * channels, 32), 256, 0, s>>>(scratch, blocks, 2 * channels, dgamma, dbeta, channels);
   TTS_CHECK_LAUNCH();
   return 0;
 }
-extern "C" size_t tts_ln_bwd_scratch_floats(int32_t channels) { return (size_t)1184 * 2 * channels; }
+extern "C" size_t tts_ln_bwd_scratch_floats(int32_t channels) { return (size_t)592 * 2 * channels; }
 
 extern "C" int tts_dropout_cast(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int32_t channels,
                                 float drop_p, uint64_t seed, uint32_t rng_stream, const int32_t* row_len, int32_t rows_per_batch,
@@ -767,7 +782,7 @@ extern "C" int tts_bn_train_bwd(const float* z, const float* dout, const float* 
                                                   channels, scratch);
   TTS_CHECK_LAUNCH();
   float* sums = scratch + (size_t)592 * 2 * channels;   // [2][C]: sum dy (= dbeta), sum dy xhat (= dgamma)
-  tr::colpart_finalize_kernel<<<ceil_div(2 * channels, 256), 256, 0, s>>>(scratch, blocks, 2 * channels, sums, sums + channels, channels);
+  tr::colpart_finalize_kernel<<<ceil_div(2 * channels, 32), 256, 0, s>>>(scratch, blocks, 2 * channels, sums, sums + channels, channels);
   TTS_CHECK_LAUNCH();
   TTS_CHECK_CUDA(cudaMemcpyAsync(dbeta, sums, channels * sizeof(float), cudaMemcpyDeviceToDevice, s));
   TTS_CHECK_CUDA(cudaMemcpyAsync(dgamma, sums + channels, channels * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -138,3 +138,49 @@ def test_packed_rows_layout():
     assert q.shape == (2, 10, 48)
     assert q[1, 3, 4 * 2 + 1] == w[3, 32 + 2 + 4 * 1] and q[0, 3, 16 + 4 * 3 + 0] == w[3, 16 + 3]
     assert float(q[:, :, 32:].abs().max()) == 0.0
+
+
+def test_unmodified_reference_synthesize_runs_against_the_mirror(built, tiny_params):
+    """The reference's own synthesize.py (unmodified, imported from /root/reference) driving THIS transformer/ package:
+    import wiring, the hp / batch-dict plumbing and the call sequence up to the first kernel call, which on this
+    CPU-only container must fail loudly with our "no CPU path" error (there is no fallback to hide behind).  The GPU run
+    recipe is in INTEGRATION.md; the same loop on CUDA is tests/test_gpu_parity.py::test_module_api_unchanged_synthesis_loop."""
+    import importlib
+    import sys
+    from unittest import mock
+    ref = os.environ.get("TTS_REFERENCE", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "synthesize.py")):
+        pytest.skip("reference checkout not present (GPU box)")
+    from oracle import tts_oracle as O
+    from transformer import tacotron
+    cfg, params = tiny_params
+    saved = {k: sys.modules.get(k) for k in ("synthesize", "hyperparams", "utils", "utils.infolog", "utils.audio", "librosa", "soundfile",
+                                             "fastdtw", "matplotlib", "matplotlib.pyplot", "editdistance")}
+    for name in ("librosa", "librosa.filters", "librosa.effects", "soundfile", "fastdtw", "matplotlib", "matplotlib.pyplot", "editdistance"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    sys.path.append(ref)      # AFTER the repo: `transformer` resolves to this package, everything else to the reference
+    try:
+        synth = importlib.import_module("synthesize")
+        assert os.path.samefile(os.path.dirname(synth.__file__), ref)
+        import transformer
+        assert "few-shot-transformer-tts_b200" in transformer.__file__
+        hp = synth.hp
+        for k, v in vars(cfg).items():
+            hp.set_hparam(k, v)
+        m = tacotron.Tacotron(hp)                                  # reference HParams object -> our constructors
+        m.load_state_dict(params, strict=True)
+        m.eval()
+        batch = O.synth_batch(cfg, batch=2, text_len=12, n_frames=4, seed=1)
+        data = {k: batch[k] for k in ("inputs", "input_lengths", "input_spk_ids", "input_language_vecs", "names")}
+        with pytest.raises(RuntimeError, match="no CPU"):
+            synth.eval_batch(m, data, use_bar=False, bar_interval=-1)
+    finally:
+        sys.path.remove(ref)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            if getattr(sys.modules[k], "__file__", "") and ref in str(getattr(sys.modules[k], "__file__", "")):
+                sys.modules.pop(k, None)

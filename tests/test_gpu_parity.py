@@ -718,8 +718,8 @@ def test_decode_dropout_matches_oracle_with_the_same_masks(tiny_params, ops):
     e = _err(got["mel_pre"], want["mel_pre"])
     print("decode with dropout vs oracle with the same masks: max-abs %.2e" % e)
     assert e < 2e-4 and _err(got["mel_aft"], want["mel_aft"]) < 2e-4
-    big = [(r, k) for r, k, n in rates if n >= 4096]
-    assert big and all(abs(k - (1 - r)) < 0.03 for r, k in big)
+    big = [(r, k) for r, k, n in rates if n >= 600]
+    assert big and all(abs(k - (1 - r)) < 0.08 for r, k in big)
     plain = eng.generate(batch, max_frames=T, record_align="encdec", chunk=5)
     other = eng.generate(batch, max_frames=T, record_align="encdec", chunk=5, dropout=(pd, pt, seed + 1))
     assert _err(plain["mel_pre"], got["mel_pre"]) > 1e-2 and _err(other["mel_pre"], got["mel_pre"]) > 1e-2
@@ -740,3 +740,39 @@ def test_decode_dropout_matches_oracle_with_the_same_masks(tiny_params, ops):
     a = _eval_loop_like_synthesize(m, dbatch, T, cfg.num_mels)["mel_pre"]
     b = _eval_loop_like_synthesize(m, dbatch, T, cfg.num_mels)["mel_pre"]
     assert _err(a, det) > 1e-2 and _err(a, b) > 1e-2 and bool(torch.isfinite(a).all())
+
+
+def test_cfg4_multilingual_mixed_batch_share(full_params, ops):
+    """BASELINE configs[3]: 38-language / 128-speaker mixed ragged batch, global B=128 = 16 per GPU.  One GPU's share
+    (16 rows, text lengths spanning 32..258 in ONE batch, distinct languages and speakers per row): encoder memory,
+    conditioning columns, 48 decoded frames and the teacher-forced forward against the oracle at the ragged edges."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-1e4])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    g = torch.Generator().manual_seed(44)
+    B, S = 16, 258
+    lens = torch.randint(32, 259, (B,), generator=g)
+    lens[0], lens[1] = 32, 258                                   # both edges in the same batch
+    batch = O.synth_batch(cfg, batch=B, text_len=S, n_frames=4, seed=45)
+    batch["input_lengths"] = lens
+    for b in range(B):
+        batch["inputs"][b, int(lens[b]) - 1] = 1                 # eos at the ragged end, pad after it
+        batch["inputs"][b, int(lens[b]):] = 0
+    batch["input_spk_ids"] = (torch.arange(B) * 37 + 5) % 572   # distinct speakers
+    lang = torch.zeros(B, cfg.max_num_language)
+    lang[torch.arange(B), (torch.arange(B) * 7) % 38] = 1.0      # distinct languages out of 38
+    batch["input_language_vecs"] = lang
+    mem = eng.encode(batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
+    want_mem = O.encoder_forward(p, cfg, batch["inputs"], batch["input_lengths"], batch["input_spk_ids"], batch["input_language_vecs"])
+    live = (torch.arange(S)[None, :] < lens[:, None])[:, :, None]
+    assert _err(mem.cpu() * live, want_mem * live) < 2e-4        # valid positions (padded query rows are computed too,
+    assert _err(mem, want_mem) < 2e-3                            # the reference masks only the keys: modules.py:50-52)
+    assert _err(mem[:, :, cfg.encoder_hidden:], want_mem[:, :, cfg.encoder_hidden:]) < 1e-5   # speaker | language columns
+    want = O.eval_batch_cached(p, cfg, batch, 48)
+    got = eng.generate(batch, max_frames=48, record_align="encdec", chunk=48)
+    assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4 and _err(got["mel_aft"], want["mel_aft"]) < 2e-4
+    a = got["alignments"]["encdec"][5].cpu()                     # no attention mass beyond each row's text length
+    for b in (0, 1, 7):
+        assert float(a[b, :, int(lens[b]):, :].abs().max()) == 0.0 and abs(float(a[b, 0, :, 3].sum()) - 1.0) < 1e-4
