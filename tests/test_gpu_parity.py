@@ -775,4 +775,6 @@ def test_cfg4_multilingual_mixed_batch_share(full_params, ops):
     assert _err(got["mel_pre"], want["mel_pre"]) < 2e-4 and _err(got["mel_aft"], want["mel_aft"]) < 2e-4
     a = got["alignments"]["encdec"][5].cpu()                     # no attention mass beyond each row's text length
     for b in (0, 1, 7):
-        assert float(a[b, :, int(lens[b]):, :].abs().max()) == 0.0 and abs(float(a[b, 0, :, 3].sum()) - 1.0) < 1e-4
+        if int(lens[b]) < S:
+            assert float(a[b, :, int(lens[b]):, :].abs().max()) == 0.0
+        assert abs(float(a[b, 0, :, 3].sum()) - 1.0) < 1e-4
