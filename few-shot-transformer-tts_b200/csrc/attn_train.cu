@@ -153,15 +153,27 @@ __device__ __forceinline__ uint32_t keep_bits(const Args& a, unsigned long long 
     bits |= ((w.y >> 16) >= thr ? 1u : 0u) << 5;
     bits |= ((w.w & 0xffffu) >= thr ? 1u : 0u) << 6;
     bits |= ((w.w >> 16) >= thr ? 1u : 0u) << 7;
-  } else {     // rows = keys {g, g+8}, columns = queries {t2, t2+1, t2+8, t2+9}: the two query parities are two calls
+  } else {
+    // rows = keys {g, g+8}, columns = queries {t2, t2+1, t2+8, t2+9}.  The two query parities are two calls, but lanes g and
+    // g ^ 1 (same t) need the SAME two calls (their keys share a column pair of the call): each lane computes one and they
+    // swap the halves the other needs with two shuffles - one call per 8 weights here too.
+    const int ec = g & 1;                                  // the query parity whose call this lane computes
+    const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, col0 + t2 + ec, row0 + (g & ~1)), a.stream);
+    const uint32_t sh_mine = 16u * (uint32_t)ec;           // my keys are column parity g & 1 of the call's column pairs
+    const uint32_t sh_other = 16u - sh_mine;
+    // halves in the order (i, j), (i, j+8), (i+8, j), (i+8, j+8)
+    uint32_t mine_lo = ((w.x >> sh_mine) & 0xffffu) | (((w.y >> sh_mine) & 0xffffu) << 16);
+    uint32_t mine_hi = ((w.z >> sh_mine) & 0xffffu) | (((w.w >> sh_mine) & 0xffffu) << 16);
+    uint32_t send_lo = ((w.x >> sh_other) & 0xffffu) | (((w.y >> sh_other) & 0xffffu) << 16);
+    uint32_t send_hi = ((w.z >> sh_other) & 0xffffu) | (((w.w >> sh_other) & 0xffffu) << 16);
+    const uint32_t got_lo = __shfl_xor_sync(0xffffffffu, send_lo, 4), got_hi = __shfl_xor_sync(0xffffffffu, send_hi, 4);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int i = col0 + t2 + e, j = row0 + g;
-      const uint4 w = philox4x32(a.seed, attn_dropout_index(bh, n_iblk, n_jblk, i, j), a.stream);
-      bits |= (attn_dropout_half(w, i, j) >= thr ? 1u : 0u) << (0 + e);           // (i, j)     : row j,   tile 0, reg e
-      bits |= (attn_dropout_half(w, i, j + 8) >= thr ? 1u : 0u) << (2 + e);       // (i, j+8)   : row j+8, tile 0, reg 2+e
-      bits |= (attn_dropout_half(w, i + 8, j) >= thr ? 1u : 0u) << (4 + e);       // (i+8, j)   : tile 1, reg e
-      bits |= (attn_dropout_half(w, i + 8, j + 8) >= thr ? 1u : 0u) << (6 + e);   // (i+8, j+8) : tile 1, reg 2+e
+      const uint32_t lo = e == ec ? mine_lo : got_lo, hi = e == ec ? mine_hi : got_hi;
+      bits |= ((lo & 0xffffu) >= thr ? 1u : 0u) << (0 + e);   // (i, j)     : row j,   tile 0, reg e
+      bits |= ((lo >> 16) >= thr ? 1u : 0u) << (2 + e);       // (i, j+8)   : row j+8, tile 0, reg 2+e
+      bits |= ((hi & 0xffffu) >= thr ? 1u : 0u) << (4 + e);   // (i+8, j)   : tile 1, reg e
+      bits |= ((hi >> 16) >= thr ? 1u : 0u) << (6 + e);       // (i+8, j+8) : tile 1, reg 2+e
     }
   }
   return bits;

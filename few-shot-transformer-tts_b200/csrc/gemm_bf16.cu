@@ -12,12 +12,18 @@
 //   warps 2-5  epilogue: tcgen05.ld (LDTM) 32 lanes x 32 columns at a time, fused bias / ReLU / Philox dropout /
 //              residual / length mask / ReLU-gate (backward) / bf16 or fp32 store / split-K fp32 reduction
 //   tensor memory holds TWO accumulators (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   CTA PAIRS (thread-block clusters of 2 along M): the two CTAs work on vertically adjacent output tiles, which share the
+//   B operand; each CTA fetches HALF of the B tile and TMA-multicasts it into both CTAs' shared memory
+//   (.multicast::cluster), so the L2 -> SM traffic per k-block drops from 48 KB to 32 KB per CTA (a 128 x 256 tile at the
+//   tensor peak needs ~28 TB/s of operand traffic chip-wide without sharing - more than the L2 delivers).  A ring stage is
+//   released to BOTH producers by a multicast tcgen05.commit.
 // Operands may be K-major (row-major [rows][K], the forward layout) or MN-major (row-major [K][rows]): dgrad reads the
 // weight [N][K] as the MN-major B operand of dX = dY W, wgrad reads dY and X as MN-major operands of dW = dY^T X, so
 // no transposed copy of a weight or an activation is ever written.  A k5 Conv1d runs as 5 accumulated taps over a
 // zero-padded channels-last buffer (the producer shifts the A row coordinate per tap).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -92,6 +98,24 @@ __device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared-memory matrix descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor; canonical layouts
 // in cute/atom/mma_traits_sm100.hpp).  K-major: rows of 128 bytes (64 bf16 of K), 8-row atoms SBO = 1024 bytes apart.
 // MN-major: rows of 128 bytes hold 64 consecutive MN elements of one k, 8-k atoms SBO = 1024 bytes apart, the next 64
@@ -118,10 +142,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 struct Unit {
   int m0, n0, kb0, kb1;
 };
-__device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
-  const int n_tiles = p.n_mblk * p.n_nblk;
+// u: unit index of the CTA (CL = 1) or of the CTA pair (CL = 2: rows of m-block pairs; `rank` picks the m-block of the pair)
+template <int CL>
+__device__ __forceinline__ Unit decode_unit(const Params& p, int u, int rank) {
+  const int n_mrows = (p.n_mblk + CL - 1) / CL;
+  const int n_tiles = n_mrows * p.n_nblk;
   const int split = u / n_tiles, tile = u - split * n_tiles;   // split slowest: concurrent CTAs share operand slices in L2
-  const int mb = tile / p.n_nblk, nb = tile - mb * p.n_nblk;
+  const int mr = tile / p.n_nblk, nb = tile - mr * p.n_nblk;
+  const int mb = mr * CL + rank;
   const int total = p.taps * p.kb_per_tap, per = (total + p.split_k - 1) / p.split_k;
   Unit r;
   r.m0 = mb * BM;
@@ -131,21 +159,21 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u) {
   return r;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                const __grid_constant__ Params p) {
+template <int BN, int CL>
+__device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Shared* sh = reinterpret_cast<Shared*>(smem + C::kStages * C::kStage);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_units = p.n_mblk * p.n_nblk * p.split_k;
+  const int n_units = ((p.n_mblk + CL - 1) / CL) * p.n_nblk * p.split_k;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int u0 = (int)blockIdx.x / CL, ustep = (int)gridDim.x / CL;   // the CTAs of a pair walk the same units
 
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&sh->full[s], 1);
-      mbar_init(&sh->empty[s], 1);
+      mbar_init(&sh->empty[s], CL);   // a stage is refilled by multicast: BOTH CTAs' MMAs must have read it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sh->tfull[s], 1);
@@ -161,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into this CTA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = sh->tmem_base;
 
@@ -169,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
-        const Unit un = decode_unit(p, u);
+      for (int u = u0; u < n_units && ok; u += ustep) {
+        const Unit un = decode_unit<CL>(p, u, rank);
         const int n0 = un.n0 * BN;
         for (int kb = un.kb0; kb < un.kb1 && ok; ++kb, ++it) {
           const int s = it % C::kStages;
@@ -186,11 +215,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_2d(a_dst + j * 8192, &tmA, un.m0 + 64 * j, ka, bar);
           }
-          if (!p.b_mn) {
-            tma_2d(b_dst, &tmB, kbc, n0, bar);
-          } else {
+          if (CL == 1) {
+            if (!p.b_mn) {
+              tma_2d(b_dst, &tmB, kbc, n0, bar);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_2d(b_dst + j * 8192, &tmB, n0 + 64 * j, kbc, bar);
+              for (int j = 0; j < BN / 64; ++j) tma_2d(b_dst + j * 8192, &tmB, n0 + 64 * j, kbc, bar);
+            }
+          } else {   // my half of the B tile, multicast into both CTAs of the pair (same offsets, each CTA's own barrier)
+            if (!p.b_mn) {
+              tma_2d_mc(b_dst + rank * (C::kBBytes / 2), &tmB, kbc, n0 + rank * (BN / 2), bar, (uint16_t)0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = rank * (BN / 128) + j;
+                tma_2d_mc(b_dst + jj * 8192, &tmB, n0 + 64 * jj, kbc, bar, (uint16_t)0x3);
+              }
+            }
           }
         }
       }
@@ -206,8 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       uint32_t it = 0, lu = 0;
       bool ok = true;
-      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, ++lu) {
-        const Unit un = decode_unit(p, u);
+      for (int u = u0; u < n_units && ok; u += ustep, ++lu) {
+        const Unit un = decode_unit<CL>(p, u, rank);
         const uint32_t as = lu & 1u;
         ok = mbar_wait(&sh->tempty[as], ((lu >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -221,7 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(acc, make_desc(a_base + k * a_step, a_lbo, 1024u), make_desc(b_base + k * b_step, b_lbo, 1024u), idesc,
                       (kb > un.kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it
+          if (CL == 1) umma_commit(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it
+          else umma_commit_mc(&sh->empty[s], (uint16_t)0x3);   // ... in both CTAs of the pair
         }
         umma_commit(&sh->tfull[as]);    // accumulator complete
       }
@@ -235,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
     const int orpb = p.out_rows_per_batch > 0 ? p.out_rows_per_batch : rpb;
     uint32_t lu = 0;
     bool ok = true;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++lu) {
-      const Unit un = decode_unit(p, u);
+    for (int u = u0; u < n_units; u += ustep, ++lu) {
+      const Unit un = decode_unit<CL>(p, u, rank);
       const int n0 = un.n0 * BN;
       const uint32_t as = lu & 1u;
       if (ok) ok = mbar_wait(&sh->tfull[as], (lu >> 1) & 1u);
@@ -364,8 +406,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while the peer may still multicast into it or arrive on its barriers
   if (warp == 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)C::kTmemCols) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ Params p) {
+  gemm_bf16_body<BN, 1>(tmA, tmB, p);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ Params p) {
+  gemm_bf16_body<BN, 2>(tmA, tmB, p);
 }
 
 // ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ------------------
@@ -428,6 +484,20 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.fetch_or(bit, std::memory_order_release);
+  }
+  static const bool pairs_on = !(getenv("TTS_GEMM_PAIRS") != nullptr && atoi(getenv("TTS_GEMM_PAIRS")) == 0);
+  if (pairs_on && p.n_mblk >= 2) {   // CTA pairs with a TMA-multicast B tile
+    static std::atomic<unsigned long long> configured2{0ull};
+    if (!(configured2.load(std::memory_order_acquire) & bit)) {
+      TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured2.fetch_or(bit, std::memory_order_release);
+    }
+    const int units = ((p.n_mblk + 1) / 2) * p.n_nblk * p.split_k;
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (units < pairs ? units : pairs);
+    gemm_bf16_pair_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mb, p);
+    TTS_CHECK_LAUNCH();
+    return 0;
   }
   const int units = p.n_mblk * p.n_nblk * p.split_k;
   const int grid = units < sm_count() ? units : sm_count();

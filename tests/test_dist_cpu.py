@@ -28,8 +28,18 @@ def _worker(rank, world, port, out):
     params[3].grad = None                             # a parameter that received no gradient on this rank
     mine = [None if p.grad is None else p.grad.clone() for p in params]
     gb.allreduce_mean()
+    # overlapped mode: two parameter groups, all-reduce launched from autograd hooks while backward is still running
+    g2 = torch.Generator().manual_seed(7 + rank)
+    wa, wb = torch.nn.Parameter(torch.randn(40, 3, generator=g2)), torch.nn.Parameter(torch.randn(3, 5, generator=g2))
+    x = torch.randn(8, 40, generator=g2)
+    hb = GradBuckets([[wb], [wa]], bucket_bytes=256)
+    hb.attach_hooks()
+    ((x @ wa) @ wb).square().sum().backward()
+    local = [wa.grad.clone(), wb.grad.clone()]
+    hb.finish()
     out[rank] = dict(params=[p.detach().clone() for p in params], before=mine,
-                     after=[None if p.grad is None else p.grad.clone() for p in params])
+                     after=[None if p.grad is None else p.grad.clone() for p in params],
+                     hook_local=local, hook_after=[wa.grad.clone(), wb.grad.clone()])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,3 +56,6 @@ def test_bucketed_gradient_allreduce_world2():
             want = (r0["before"][i] + r1["before"][i]) / 2
             assert torch.allclose(r0["after"][i], want, atol=1e-7) and torch.equal(r0["after"][i], r1["after"][i])
         assert r0["after"][1] is None and r0["after"][3] is None
+        for i in range(2):   # hook-driven (overlapped) reduction: mean of the two ranks' gradients, identical on both
+            want = (r0["hook_local"][i] + r1["hook_local"][i]) / 2
+            assert torch.allclose(r0["hook_after"][i], want, atol=1e-5) and torch.equal(r0["hook_after"][i], r1["hook_after"][i])
