@@ -473,6 +473,11 @@ static int sm_count() {
   return n[dev];
 }
 
+static bool use_pairs(int n_mblk) {
+  static const bool pairs_on = !(getenv("TTS_GEMM_PAIRS") != nullptr && atoi(getenv("TTS_GEMM_PAIRS")) == 0);
+  return pairs_on && n_mblk >= 2;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t s) {
   using C = Cfg<BN>;
@@ -485,8 +490,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
     TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured.fetch_or(bit, std::memory_order_release);
   }
-  static const bool pairs_on = !(getenv("TTS_GEMM_PAIRS") != nullptr && atoi(getenv("TTS_GEMM_PAIRS")) == 0);
-  if (pairs_on && p.n_mblk >= 2) {   // CTA pairs with a TMA-multicast B tile
+  if (use_pairs(p.n_mblk)) {   // CTA pairs with a TMA-multicast B tile
     static std::atomic<unsigned long long> configured2{0ull};
     if (!(configured2.load(std::memory_order_acquire) & bit)) {
       TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -554,7 +558,8 @@ extern "C" int tts_gemm_bf16(const TtsGemmBf16* g, void* stream) {
   if (!p.a_mn) rc = bf::make_map(&ma, g->A, g->K, a_rows, g->lda, bf::BM);
   else rc = bf::make_map(&ma, g->A, g->M, g->K, g->lda, 64);
   if (rc) return rc;
-  if (!p.b_mn) rc = bf::make_map(&mb, g->B, (long long)taps * g->K, g->N, g->ldb, bn);
+  // K-major B: one box per CTA = the whole tile, or (CTA pairs) the half of the tile that this CTA multicasts
+  if (!p.b_mn) rc = bf::make_map(&mb, g->B, (long long)taps * g->K, g->N, g->ldb, bf::use_pairs(p.n_mblk) ? bn / 2 : bn);
   else rc = bf::make_map(&mb, g->B, g->N, g->K, g->ldb, 64);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
