@@ -4,12 +4,12 @@
 //
 //   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ),  A and B bf16, fp32 accumulation in tensor memory.
 //
-// Blackwell-native structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Blackwell-native structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0     TMA producer: cp.async.bulk.tensor.2d tiles (128-byte swizzle) into a 4/6-stage shared-memory ring,
 //              completion on mbarriers (SASS: UTMALDG)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16; SASS UTCHMMA)
 //              from shared-memory descriptors, tcgen05.commit releases ring stages and publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld (LDTM) 32 lanes x 32 columns at a time, fused bias / ReLU / Philox dropout /
+//   warps 2-9  epilogue: tcgen05.ld (LDTM) 32 lanes x 32 columns at a time, fused bias / ReLU / Philox dropout /
 //              residual / length mask / ReLU-gate (backward) / bf16 or fp32 store / split-K fp32 reduction
 //   tensor memory holds TWO accumulators (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   CTA PAIRS (thread-block clusters of 2 along M): the two CTAs work on vertically adjacent output tiles, which share the
@@ -36,7 +36,8 @@ namespace tts {
 namespace bf {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;   // two warps per tensor-memory lane quadrant; each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr long long kTimeout = 2LL << 30;
 
@@ -139,6 +140,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// 256-bit global store (sm_100: STG.256), address 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
 struct Unit {
   int m0, n0, kb0, kb1;
 };
@@ -177,7 +193,7 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sh->tfull[s], 1);
-      mbar_init(&sh->tempty[s], 4);
+      mbar_init(&sh->tempty[s], kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -270,25 +286,51 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps: TMEM lane quadrant = warp % 4, thread = output row =================
+    // ================= epilogue warps: TMEM lane quadrant = warp % 4, thread = output row; warps 2-5 take the first half
+    // of the tile's columns, warps 6-9 the second.  Global accesses are 32 bytes per lane (LDG/STG.256: one full sector
+    // per lane and instruction; with 16-byte accesses the fp32-output GEMMs of K = 768 were bound by the store requests of
+    // the epilogue, profiles/r2_gemm_bf16_sweep.txt) and the residual / gate operands of chunk c+1 are requested before
+    // chunk c is processed (their latency was exposed once per chunk) =================
     const int quad = warp & 3;
+    const int c_lo = ((warp - 2) >> 2) * (BN / 2), c_hi = c_lo + BN / 2;
     const int rpb = p.rows_per_batch > 0 ? p.rows_per_batch : p.M;
     const int valid = p.valid_rows > 0 ? p.valid_rows : rpb;
     const int orpb = p.out_rows_per_batch > 0 ? p.out_rows_per_batch : rpb;
+    const bool res_vec = p.residual != nullptr && (p.ldr & 7) == 0;
+    const bool gate_vec = p.gate != nullptr && (p.ldg & 15) == 0;
     uint32_t lu = 0;
     bool ok = true;
     for (int u = u0; u < n_units; u += ustep, ++lu) {
       const Unit un = decode_unit<CL>(p, u, rank);
       const int n0 = un.n0 * BN;
       const uint32_t as = lu & 1u;
-      if (ok) ok = mbar_wait(&sh->tfull[as], (lu >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = un.m0 + quad * 32 + lane;
       const int b = m / rpb, r = m - b * rpb;
-      const bool row_ok = ok && m < p.M && r < valid && un.kb1 > un.kb0;
-      const bool dead = row_ok && p.row_len != nullptr && r >= p.row_len[b];
+      const bool row_in = m < p.M && r < valid && un.kb1 > un.kb0;
       const size_t orow = (size_t)b * orpb + r + p.out_row_offset;
-      for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += 32) {
+      float rn[32];       // residual of the next chunk
+      uint32_t gn[16];    // gate (32 bf16) of the next chunk
+      bool pre_n = false;
+      auto prefetch = [&](int c0) {   // 32-column chunk c0 of this row, if it is complete: vector loads, else the scalar path
+        pre_n = row_in && n0 + c0 + 32 <= p.N && (res_vec || gate_vec);
+        if (!pre_n) return;
+        if (res_vec) {
+          const float* rp = p.residual + orow * p.ldr + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ld_global_v8(rp + 8 * q, *reinterpret_cast<float(*)[8]>(&rn[8 * q]));
+        }
+        if (gate_vec) {
+          const __nv_bfloat16* gp = p.gate + orow * p.ldg + n0 + c0;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) ld_global_v8(reinterpret_cast<const float*>(gp + 16 * q), *reinterpret_cast<float(*)[8]>(&gn[8 * q]));
+        }
+      };
+      if (n0 + c_lo < p.N) prefetch(c_lo);   // in flight while the MMAs of this tile finish
+      if (ok) ok = mbar_wait(&sh->tfull[as], (lu >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool row_ok = ok && row_in;
+      const bool dead = row_ok && p.row_len != nullptr && r >= p.row_len[b];
+      for (int c0 = c_lo; c0 < c_hi && n0 + c0 < p.N; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + as * BN + (uint32_t)c0;
         asm volatile(
@@ -299,6 +341,15 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
               "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
+        float rc[32];
+        uint32_t gc[16];
+        const bool pre_c = pre_n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rc[j] = rn[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gc[j] = gn[j];
+        if (c0 + 32 < c_hi && n0 + c0 + 32 < p.N) prefetch(c0 + 32);
+        else pre_n = false;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (!row_ok) continue;
         const int n = n0 + c0;
@@ -317,18 +368,13 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
         }
         if (p.gate != nullptr) {   // backward of ReLU (+ dropout): the saved forward output is > 0 exactly where both kept it
           const __nv_bfloat16* gp = p.gate + orow * p.ldg + n;
-          if (full && (p.ldg & 7) == 0) {
+          if (pre_c && gate_vec) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gp) + q);
-              const uint32_t w[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // bf16 > 0: sign clear and magnitude non-zero
-                const uint32_t lo = w[e] & 0xffffu, hi = w[e] >> 16;
-                x[q * 8 + 2 * e] = (lo != 0u && lo < 0x8000u) ? x[q * 8 + 2 * e] * p.gate_scale : 0.f;
-                x[q * 8 + 2 * e + 1] = (hi != 0u && hi < 0x8000u) ? x[q * 8 + 2 * e + 1] * p.gate_scale : 0.f;
-              }
+            for (int e = 0; e < 16; ++e) {
+              // bf16 > 0: sign clear and magnitude non-zero
+              const uint32_t lo = gc[e] & 0xffffu, hi = gc[e] >> 16;
+              x[2 * e] = (lo != 0u && lo < 0x8000u) ? x[2 * e] * p.gate_scale : 0.f;
+              x[2 * e + 1] = (hi != 0u && hi < 0x8000u) ? x[2 * e + 1] * p.gate_scale : 0.f;
             }
           } else {
 #pragma unroll
@@ -349,12 +395,9 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
         }
         if (p.residual != nullptr) {
           const float* rp = p.residual + orow * p.ldr + n;
-          if (full && (p.ldr & 3) == 0) {
+          if (pre_c && res_vec) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rp) + q);
-              x[4 * q] += rv.x; x[4 * q + 1] += rv.y; x[4 * q + 2] += rv.z; x[4 * q + 3] += rv.w;
-            }
+            for (int j = 0; j < 32; ++j) x[j] += rc[j];
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -372,15 +415,13 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
             if (full || n + j < p.N) atomicAdd(cp + j, x[j]);
         } else if (p.out_bf16) {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n;
-          if (full && (p.ldc & 7) == 0) {
+          if (full && (p.ldc & 15) == 0) {   // 32-byte stores: one full sector per lane and instruction
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(x[8 * q], x[8 * q + 1]), t1 = __floats2bfloat162_rn(x[8 * q + 2], x[8 * q + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(x[8 * q + 4], x[8 * q + 5]), t3 = __floats2bfloat162_rn(x[8 * q + 6], x[8 * q + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
-              reinterpret_cast<uint4*>(cp)[q] = o;
+            for (int q = 0; q < 2; ++q) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(x[16 * q + 2 * e], x[16 * q + 2 * e + 1]);
+              st_global_v8(cp + 16 * q, o);
             }
           } else {
 #pragma unroll
@@ -389,9 +430,14 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
           }
         } else {
           float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + n;
-          if (full && (p.ldc & 3) == 0) {
+          if (full && (p.ldc & 7) == 0) {   // 32-byte stores: one full sector per lane and instruction
 #pragma unroll
-            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(cp)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(x[8 * q + e]);
+              st_global_v8(cp + 8 * q, o);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
