@@ -519,7 +519,13 @@ def run_train_step(args, dev, rank, world):
     B, S, T = args.tf_batch, args.text_len, args.frames
     host = O.synth_batch(cfg, batch=B, text_len=S, n_frames=T, seed=100 + rank)
     keys = ("inputs", "input_lengths", "mel_targets", "target_lengths", "input_spk_ids", "input_language_vecs")
-    pinned = {k: host[k].pin_memory() for k in keys}
+    # the feeder's side of the boundary (dataloader.py:419-439): pageable host arrays, the language as an id; the stager
+    # (tts_b200/staging.py) moves them through pinned arenas on a copy stream and expands the one-hot on the device
+    from tts_b200.staging import BatchStager
+    host_batch = {k: host[k] for k in keys if k != "input_language_vecs"}
+    host_batch["input_language_ids"] = host["input_language_vecs"].argmax(dim=1)
+    stager = BatchStager(dev, depth=2, n_languages=host["input_language_vecs"].shape[1])
+    staged = [stager.stage(host_batch)]
     sel = l2_selected_names(m)
     opt = FusedAdam(m.parameters(), lr=hp.max_lr, eps=hp.adam_eps, reg_weight=hp.reg_weight,
                     l2_params=[p for n, p in m.named_parameters() if n in sel])
@@ -540,7 +546,8 @@ def run_train_step(args, dev, rank, world):
     ar_ms = []
 
     def step(timed_ar=False):
-        batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}   # dict_send_to (utils/__init__.py:3)
+        batch = staged[0].wait()                 # dict_send_to (utils/__init__.py:3), staged one step ahead
+        staged[0] = stager.stage(host_batch)     # the next batch's copy overlaps this step
         out = fwd(**batch)
         losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
         opt.zero_grad(set_to_none=False)
@@ -555,6 +562,7 @@ def run_train_step(args, dev, rank, world):
         opt.step()
         sched.step()
         loss_host.copy_(losses["loss"].detach(), non_blocking=True)
+        batch.release()
         return losses
 
     def barrier():
@@ -587,7 +595,7 @@ def run_train_step(args, dev, rank, world):
                                                      ("DistributedDataParallel" if ddp is not None else
                                                       "bucketed NCCL all-reduce overlapped with backward, 64 MB buckets"))},
             "frames_per_s": B * T * world / (ms / 1e3), "loss": float(loss_host),
-            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()), "d2h_bytes_per_step": 4,
+            "h2d_bytes_per_step": stager.h2d_bytes // (max(args.warmup, 3) + args.steps + 1), "d2h_bytes_per_step": 4,
             "gpu_launches_per_step": launches,
             "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,

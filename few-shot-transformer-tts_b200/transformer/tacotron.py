@@ -181,11 +181,17 @@ class Decoder(nn.Module):
             mels, stop = AG.DecoderFn.apply(eng, param_names(self, "decoder."), self.training, leave_one, encoder_outputs,
                                             input_lengths, targets, target_lengths, *self.parameters())
             return mels, stop, {"self": [], "encdec": []}
-        eng = engine_for(self, "decoder.", self.hparams)
+        # inside an utterance (T > 1) the cached session's engine serves the call without re-validating the module's
+        # parameter set: one frame of synthesize.py's loop costs a kernel launch, not a walk over 100 tensors
+        inc = self._inc
+        mid = leave_one and inc is not None and targets.shape[1] > 1
+        eng = inc["engine"] if mid else engine_for(self, "decoder.", self.hparams)
         if leave_one:
             out = self._incremental(eng, encoder_outputs, input_lengths, targets, target_lengths)
             if out is not None:
                 return out
+            if mid:
+                eng = engine_for(self, "decoder.", self.hparams)
         if self.training and (self.hparams.decoder_dropout_rate > 0 or self.hparams.transformer_dropout_rate > 0):
             eng.warn_dropout("Decoder")
         return eng.decode_teacher_forced(encoder_outputs, input_lengths, targets, target_lengths, leave_one=leave_one)

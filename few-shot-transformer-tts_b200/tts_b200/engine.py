@@ -77,6 +77,7 @@ class DecodeSession:
         self.input_lengths = None
         self.t = 0
         self._st = None
+        self._dw = None
         self.dropout = (0.0, 0.0, 0)   # (prenet rate, transformer rate, seed): decoder.train() at synthesis time
 
     def state(self):
@@ -101,7 +102,10 @@ class DecodeSession:
         self.input_lengths = ops._i32(input_lengths)
         assert self.memory.shape == (self.batch, self.mem_len, self.engine.cfg.decoder_hidden), self.memory.shape
         self._st = self.state()
-        N.check(N.load().tts_decode_begin(C.byref(self.engine.decoder_weights()), C.byref(self._st),
+        # the weight struct is validated against the live parameters (pointer + version of every decoder tensor) once per
+        # utterance, not once per step: parameters do not change while an utterance is being decoded
+        self._dw = self.engine.decoder_weights()
+        N.check(N.load().tts_decode_begin(C.byref(self._dw), C.byref(self._st),
                                           N.stream_ptr(self.engine.device)), "decode_begin")
         self.t = 0
 
@@ -109,7 +113,8 @@ class DecodeSession:
         if self.t + n_steps > self.t_max:   # the kernels also clamp against the DEVICE step counter and report -2
             raise RuntimeError("tts_b200: decode session overflow (t=%d + %d steps > t_max=%d)"
                                % (self.t, n_steps, self.t_max))
-        N.check(N.load().tts_decode_steps(C.byref(self.engine.decoder_weights()), C.byref(self._st), n_steps, None, 0,
+        dw = self._dw if getattr(self, "_dw", None) is not None else self.engine.decoder_weights()
+        N.check(N.load().tts_decode_steps(C.byref(dw), C.byref(self._st), n_steps, None, 0,
                                           1 if update_state else 0, impl, N.stream_ptr(self.engine.device)),
                 "decode_steps")
         self.t += n_steps
@@ -449,7 +454,18 @@ class TtsEngine:
         return DecodeSession(self, batch, mem_len, t_max, record_align)
 
     def generate(self, batch, max_frames=None, record_align="encdec", chunk=32, impl=0, session=None,
-                 memory=None, dropout=None):
+                 memory=None, dropout=None, compact=None):
+        """The whole of synthesize.eval_batch (synthesize.py:17-72) as one call: encoder, K/V-cached decode loop with the
+        stop bookkeeping on the device (one 4-byte D2H poll per `chunk` steps), Postnet.
+
+        compact: early-exit compaction of finished samples.  A finished sample's frames are
+        zero from its stop on (modules.py:144) but its K/V streams would still be read on every step; when enough
+        samples have finished to save a whole 16-row group of the decode kernel, the live rows (K/V caches, lengths,
+        last frame) are gathered into a smaller session between two launches and decoding goes on there; frames and
+        stop logits are scattered back at the end.  Per-row results do not depend on the batch composition (the
+        K/V streams of a batch of <= 16 rows are split across SMs, so sums may differ in the last bits).  Default
+        (None): on when no attention rows are recorded and dropout is off - alignment rows of a finished sample
+        beyond its stop would stay zero, and the dropout masks are indexed by batch row."""
         cfg = self.cfg
         max_frames = cfg.max_generation_frames if max_frames is None else max_frames
         if memory is None:
@@ -458,6 +474,15 @@ class TtsEngine:
         B, S, _ = memory.shape
         sess = session if session is not None else self.new_session(B, S, max_frames, record_align)
         sess.begin(memory, batch["input_lengths"].to(self.device), dropout=dropout)
+        if compact is None:
+            compact = sess.align_self is None and sess.align_cross is None and dropout is None and impl in (0, 4)
+        if compact and (sess.align_self is not None or sess.align_cross is not None):
+            raise ValueError("tts_b200: generate(compact=True) needs record_align='none'")
+        top = sess                      # the caller-visible session: receives all frames / lengths at the end
+        rows = None                     # original batch row of every row of `sess` (None: identity)
+        parts = []                      # (session, rows, t_from, t_to) of every compacted stretch
+        t_from = 0
+        compactions = []
         done = 0
         all_finished = False
         while done < max_frames:
@@ -472,12 +497,59 @@ class TtsEngine:
             if left == 0:
                 all_finished = True
                 break
-        lengths = sess.lengths.clone()
+            if compact and done < max_frames and (left + 15) // 16 < (sess.batch + 15) // 16:
+                parts.append((sess, rows, t_from, done))
+                sess, rows = self._compact_session(sess, rows, left, done)
+                t_from = done
+                compactions.append((done, sess.batch))
+        if sess is not top:             # scatter the compacted stretches back into the caller-visible session
+            parts.append((sess, rows, t_from, done))
+            # rows that had finished before a stretch were not decoded in it: their frames there are zero (modules.py:144)
+            top.frames[:, parts[1][2]:done].zero_()
+            top.stop_logits[:, parts[1][2]:done].zero_()
+            for ps, pr, a, b in parts[1:]:
+                top.frames[pr, a:b] = ps.frames[:, a:b]
+                top.stop_logits[pr, a:b] = ps.stop_logits[:, a:b]
+                top.lengths[pr] = ps.lengths
+                top.finished[pr] = ps.finished
+            top.t = done
+        lengths = top.lengths.clone()
         # eval_batch stops right after the step in which the last sample fired (synthesize.py:35)
         t_gen = int(lengths.max().item()) if all_finished else done
         t_gen = min(t_gen, max_frames)
-        mels = sess.frames[:, :t_gen].contiguous()
+        mels = top.frames[:, :t_gen].contiguous()
         mel_aft = self.postnet(mels, lengths, add_input=True)
         out = {"mel_pre": mels, "mel_aft": mel_aft, "generated_lengths": lengths, "memory": memory,
-               "stop_logits": sess.stop_logits[:, :t_gen], "alignments": sess.alignments(t_gen), "session": sess}
+               "stop_logits": top.stop_logits[:, :t_gen], "alignments": top.alignments(t_gen), "session": top,
+               "compactions": compactions}
         return out
+
+    def _compact_session(self, sess, rows, n_live, t):
+        """Gather the unfinished rows of `sess` (decoded up to step t) into a session of n_live rows."""
+        dev = self.device
+        live = torch.nonzero(sess.finished == 0).view(-1)
+        assert live.numel() == n_live, (live.numel(), n_live)
+        cache = self.__dict__.setdefault("_compact_sessions", {})
+        key = (n_live, sess.mem_len, sess.t_max)
+        small = cache.get(key)
+        if small is None or small is sess:
+            small = DecodeSession(self, n_live, sess.mem_len, sess.t_max, "none")
+            cache[key] = small
+        for name in ("self_k", "self_v"):      # [L, B, H, t_max, dh]: only the t rows written so far
+            getattr(small, name)[:, :, :, :t].copy_(getattr(sess, name)[:, :, :, :t].index_select(1, live))
+        for name in ("cross_k", "cross_v"):
+            getattr(small, name).copy_(getattr(sess, name).index_select(1, live))
+        small.lengths.copy_(sess.lengths.index_select(0, live))
+        small.finished.zero_()
+        # the first step of a launch reads frame t-1 from the frames buffer (include/tts_b200.h); earlier frames stay in
+        # the sessions that produced them
+        small.frames[:, t - 1].copy_(sess.frames[:, t - 1].index_select(0, live))
+        small.memory = sess.memory.index_select(0, live)
+        small.input_lengths = sess.input_lengths.index_select(0, live)
+        small.dropout = sess.dropout
+        small.counters.copy_(torch.tensor([t, n_live], dtype=torch.int32), non_blocking=False)
+        small.t = t
+        small._st = small.state()
+        small._dw = sess._dw
+        new_rows = live if rows is None else rows.index_select(0, live)
+        return small, new_rows

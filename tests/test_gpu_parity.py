@@ -419,6 +419,39 @@ def test_headline_config_staggered_stops_vs_oracle(full_params, ops):
     assert got["generated_lengths"].cpu().tolist() == ln.tolist()
     assert got["mel_pre"].shape == want["mel_pre"].shape
     assert _err(got["mel_pre"], want["mel_pre"]) < MEL_TOL and _err(got["mel_aft"], want["mel_aft"]) < MEL_TOL
+    # early-exit compaction (generate's default without alignments): the live rows moved into smaller sessions
+    assert len(got["compactions"]) >= 1 and got["compactions"][-1][1] <= 16, got["compactions"]
+    flat = eng.generate(batch, max_frames=T, record_align="none", chunk=50, compact=False)
+    assert flat["compactions"] == [] and flat["generated_lengths"].cpu().tolist() == ln.tolist()
+    assert _err(flat["mel_pre"], got["mel_pre"]) < 1e-4 and _err(flat["stop_logits"], got["stop_logits"]) < 1e-3
+    print("compaction points (step, live rows):", got["compactions"])
+
+
+def test_generate_compaction_reused_session(full_params, ops):
+    """Compaction with a caller-owned session that is reused across utterances: frames of rows that finished before a
+    compacted stretch are zero even when the buffers held an earlier utterance; B=40 (three row groups -> two -> one)."""
+    from tts_b200.engine import TtsEngine
+    cfg, params = full_params
+    p = dict(params)
+    p["decoder.stop_net.bias"] = torch.tensor([-5.0])
+    eng = TtsEngine.from_state_dict(p, cfg, DEV)
+    T = 120
+    sess = eng.new_session(40, 64, T, "none")
+    first = O.synth_batch(cfg, batch=40, text_len=64, n_frames=4, seed=5)
+    eng.generate(first, max_frames=T, record_align="none", chunk=20, session=sess, compact=False)   # dirty the buffers
+    batch = O.synth_batch(cfg, batch=40, text_len=64, n_frames=4, seed=6)
+    a = eng.generate(batch, max_frames=T, record_align="none", chunk=20, session=sess, compact=True)
+    a = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.items()}
+    b = eng.generate(batch, max_frames=T, record_align="none", chunk=20, compact=False)
+    assert a["generated_lengths"].cpu().tolist() == b["generated_lengths"].cpu().tolist()
+    assert len(set(b["generated_lengths"].cpu().tolist())) > 2, "expected staggered stops"
+    assert len(a["compactions"]) >= 1, a["compactions"]
+    assert a["mel_pre"].shape == b["mel_pre"].shape
+    assert _err(a["mel_pre"], b["mel_pre"]) < 1e-4 and _err(a["mel_aft"], b["mel_aft"]) < 1e-4
+    lens = b["generated_lengths"].cpu()
+    for i in range(40):
+        if int(lens[i]) < a["mel_pre"].shape[1]:
+            assert float(a["mel_pre"][i, int(lens[i]):].abs().max()) == 0.0
 
 
 def test_long_reference_golden_640_frames(full_params, golden_dir, ops):

@@ -9,10 +9,29 @@ case $mode in
   sanitize)   # compute-sanitizer on the decode kernel: split K/V streams (B=3), two groups (B=32), partial last group (B=40)
     for B in 3 32 40; do
       for tool in memcheck racecheck synccheck; do
-        PB=$B PT=6 PN=2 PTMAX=16 timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tests/tools_ncu_target.py 2>&1 | tail -15 > gpurun_out/r2_sanitizer_${tool}_B$B.log
+        PB=$B PT=6 PN=2 PTMAX=16 timeout 900 compute-sanitizer --tool $tool --print-limit 40 python tests/tools_ncu_target.py 2>&1 | tail -60 > gpurun_out/r2_sanitizer_${tool}_B$B.log
         tail -3 gpurun_out/r2_sanitizer_${tool}_B$B.log
       done
     done ;;
+  evidence)   # round-2 evidence set: full GPU suite, default bench, launch lists, ncu --set full of the dominant kernels
+    python -m pytest tests -m gpu -q -s > gpurun_out/r2_gputest_full.log 2>&1; grep -E "passed|failed|horizon|staggered|golden:|cfg5|tiny train|full train|loss curves|compaction|FAILED|Error" gpurun_out/r2_gputest_full.log | tail -40
+    python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cut -c1-300 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err
+    python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/r2_train_bench.json 2> gpurun_out/r2_train_bench.err; cut -c1-200 gpurun_out/r2_train_bench.json
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_bench_launches_decode.csv python bench.py --steps 1 --warmup 3 --no-train --no-module-api --no-cpu-baseline > /dev/null 2>&1
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 > /dev/null 2>&1
+    PIMPL=4 PT=475 PN=50 PTMAX=640 ncu --set full --clock-control none --import-source on -k regex:pipelined_decode_kernel -s 1 -c 1 -f -o gpurun_out/r2_pipe python tests/tools_ncu_target.py > /dev/null 2>&1
+    ncu -i gpurun_out/r2_pipe.ncu-rep --page raw --csv > gpurun_out/r2_pipe_ncu_raw.csv
+    PB=16 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 3 -f -o gpurun_out/r2_attn python tests/tools_attn_target.py > /dev/null 2>&1
+    ncu -i gpurun_out/r2_attn.ncu-rep --page raw --csv > gpurun_out/r2_attn_ncu_raw.csv
+    for o in bf16 f32; do
+      ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 3 -c 1 -f -o gpurun_out/r2_gemm_bf16_$o python tests/tools_gemm_bf16_one.py 64000 768 768 $o > /dev/null 2>&1
+      ncu -i gpurun_out/r2_gemm_bf16_$o.ncu-rep --page raw --csv > gpurun_out/r2_gemm_bf16_${o}_ncu_raw.csv
+    done
+    timeout 300 python tests/tools_gemm_bf16.py 10 > gpurun_out/r2_gemm_bf16_sweep.txt 2>&1
+    python tests/tools_pipe_profile.py 500 > gpurun_out/r2_pipe_phase_profile.txt 2>&1
+    ls -la gpurun_out | grep r2_ | tail -30 ;;
+  sweep)      # BASELINE configs[4]: long-form decode, T=2000, batch sweep
+    python tests/tools_sweep.py 2000 1 2 4 8 16 32 64 128 > gpurun_out/r2_cfg5_sweep.jsonl 2> gpurun_out/r2_cfg5_sweep.err; cat gpurun_out/r2_cfg5_sweep.jsonl | cut -c1-260; tail -3 gpurun_out/r2_cfg5_sweep.err ;;
   bench)
     python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cut -c1-2500 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err ;;
   train)      # BASELINE metric 2: the teacher-forced training step at configs[2], plus its launch list
