@@ -539,7 +539,8 @@ def run_train_step(args, dev, rank, world):
             # gradients appear per sub-module, in backward order: each group's all-reduce starts behind the rest of backward
             buckets = GradBuckets([list(m.postnet.parameters()), list(m.decoder.parameters()), list(m.encoder.parameters())])
             buckets.broadcast_parameters(0)
-            buckets.attach_hooks()
+            if args.dp == "buckets":      # "buckets-late": everything is reduced after backward (no overlap), for comparison
+                buckets.attach_hooks()
     fwd = ddp if ddp is not None else m
     lib = _native.load()
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
@@ -550,7 +551,7 @@ def run_train_step(args, dev, rank, world):
         staged[0] = stager.stage(host_batch)     # the next batch's copy overlaps this step
         out = fwd(**batch)
         losses = tacotron.compute_loss(m, batch["mel_targets"], batch["target_lengths"], out, hp)
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()                       # train.py:173 (torch default: gradients set to None, assigned by backward)
         losses["loss"].backward()
         if buckets is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -582,6 +583,11 @@ def run_train_step(args, dev, rank, world):
     barrier()
     ms = reduce_max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
     launches = int(lib.tts_launch_count()) // max(args.steps, 1)
+    # host side of one step: Python + launch time with an empty GPU queue (not part of the timed region)
+    t_h0 = time.perf_counter()
+    step()
+    host_issue_ms = 1e3 * (time.perf_counter() - t_h0)
+    barrier()
     flops = train_flops(S, T, B)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
@@ -596,7 +602,7 @@ def run_train_step(args, dev, rank, world):
                                                       "bucketed NCCL all-reduce overlapped with backward, 64 MB buckets"))},
             "frames_per_s": B * T * world / (ms / 1e3), "loss": float(loss_host),
             "h2d_bytes_per_step": stager.h2d_bytes // (max(args.warmup, 3) + args.steps + 1), "d2h_bytes_per_step": 4,
-            "gpu_launches_per_step": launches,
+            "gpu_launches_per_step": launches, "host_issue_ms_per_step": host_issue_ms,
             "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
                          "flops_per_step_per_gpu": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
@@ -689,7 +695,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the train_step measurement of the default run")
     ap.add_argument("--no-module-api", action="store_true", help="skip the per-frame module-API loop measurement")
     ap.add_argument("--module-api-frames", type=int, default=300)
-    ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"], help="gradient exchange of the train step at N > 1")
+    ap.add_argument("--dp", default="buckets", choices=["buckets", "buckets-late", "ddp"], help="gradient exchange of the train step at N > 1")
     ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")
     args = ap.parse_args()
     if args.workload == "forward":

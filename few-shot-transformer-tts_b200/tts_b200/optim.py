@@ -40,7 +40,7 @@ class FusedAdam(torch.optim.Optimizer):
             key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
             hit = self._tables.get(gi)
             if hit is None or hit[0] != key:   # grads are re-allocated by zero_grad(set_to_none=True): rebuild the pointer table
-                tab = TO.MultiTable(ps[0].device)
+                tab = hit[1] if hit is not None else TO.MultiTable(ps[0].device)   # reused: pinned staging, async upload
                 tab.build_opt([(p, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"], id(p) in self._l2_ids) for p in ps])
                 hit = (key, tab)
                 self._tables[gi] = hit

@@ -57,6 +57,12 @@ for k, v in agg.most_common(25):
 print("total %.3f ms over %d launches" % (tot / 1e6, sum(cnt.values())))
 PY
     ;;
+  scale)      # N-GPU box ($2 = N): gradient equality, then the data-parallel train step with the bucketed all-reduce
+    N=${2:-8}
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/tools_multi_gpu.py 2>&1 | grep -E "PASS|FAIL|Error|error" | tail -4
+    NCCL_DEBUG=INFO python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 5 --warmup 3 --workload train --dp buckets > gpurun_out/r2_train_n${N}_buckets.json 2> gpurun_out/r2_train_n${N}_buckets.err
+    grep -E "NVLS|via P2P|Channel .* via" gpurun_out/r2_train_n${N}_buckets.json gpurun_out/r2_train_n${N}_buckets.err | cut -c1-160 | sort | uniq -c | sort -rn | head -6 > gpurun_out/r2_train_n${N}_nccl.txt; cat gpurun_out/r2_train_n${N}_nccl.txt
+    grep "^{" gpurun_out/r2_train_n${N}_buckets.json | tail -1 | cut -c1-1200 ;;
   multi)      # N-GPU box: gradient equality (GradBuckets + DDP) and the train step at N GPUs ($2 = N)
     N=${2:-2}
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/tools_multi_gpu.py 2>&1 | grep -E "PASS|FAIL|Error|error" | tail -8
