@@ -10,6 +10,8 @@
 //   dK / dV : one CTA per 64 keys, loops over query blocks with the TRANSPOSED products (S^T = K Q^T, dP^T = V dO^T), so
 //             P^T and dS^T are already in A-fragment layout for dV += P^T dO and dK += dS^T Q: no shared-memory
 //             round trip, no atomics, deterministic
+//   fused   : (default when the caller provides the fp32 dQ buffer) the dK / dV kernel also produces dQ: ONE recomputation
+//             of S / dP / dropout bits per tile pair instead of two; dQ is accumulated with vector atomics
 // Reference semantics: transformer/attention.py:72-122 (scale on q :113-114, additive -1e20 bias :84-85 == exclusion
 // from the softmax, dropout on the weights :89), masks of transformer/modules.py:50-52,109-112.
 #include <cuda_bf16.h>
@@ -40,6 +42,7 @@ struct Args {
   float* delta;                     // [B][H][Tq]
   __nv_bfloat16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
+  float* dq_acc;                    // [B*Tq][H*DH] fp32: dQ accumulated with atomics by the fused backward kernel (or NULL)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -522,6 +525,213 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_kernel(const Args a) {
   }
 }
 
+
+// =====================================================================================================================
+// backward, single pass: dK, dV and dQ from ONE recomputation of S and dP per (query block, key block) pair.
+// The two-kernel path above recomputes S / dP / the dropout bits twice (7 tile products per pair); this kernel does 5:
+// the dK/dV kernel's transposed products, then dS^T goes through shared memory (bf16) and every warp multiplies a
+// [16 queries x 64 keys] slice of dS with the resident K tile; the partial dQ of this key block is added to an fp32
+// buffer with vector atomics (red.global.add.v2.f32), which a small kernel converts to bf16 afterwards.  The sum order
+// of dQ over key blocks is not fixed (like the reference's own atomics in backward); dK / dV stay deterministic.
+// delta = rowsum(dO o O) comes from attn_bwd_prep_kernel.
+// =====================================================================================================================
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) {
+  constexpr int LDS = DH + 8, BQ2 = 32, LDP = BQ2 + 8;   // dS^T rows: 32 queries + 8 (80 bytes: ldmatrix / 4-byte stores conflict-free)
+  extern __shared__ __align__(16) __nv_bfloat16 sm[];
+  __nv_bfloat16 *sK = sm, *sV = sK + BKV * LDS, *sQ = sV + BKV * LDS, *sDO = sQ + 2 * BQ2 * LDS;
+  float* sL = reinterpret_cast<float*>(sDO + 2 * BQ2 * LDS);   // 2 x ([32] lse, [32] delta)
+  __nv_bfloat16* sDS = reinterpret_cast<__nv_bfloat16*>(sL + 4 * BQ2);   // [64 keys][LDP]
+  // heavy (early) key blocks of a causal problem first
+  const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
+  const unsigned long long bh = (unsigned long long)b * a.H + h;
+  const int klen = a.key_len ? min(a.key_len[b], a.Tk) : a.Tk;
+  const int n_iblk = (a.Tq + 15) >> 4, n_jblk = (a.Tk + 15) >> 4;
+  const __nv_bfloat16* qg = a.q + (long long)b * a.Tq * a.ldq + h * DH;
+  const __nv_bfloat16* dog = a.d_o + (long long)b * a.Tq * a.lddo + h * DH;
+  const __nv_bfloat16* kg = a.k + (long long)b * a.Tk * a.ldk + h * DH;
+  const __nv_bfloat16* vg = a.v + (long long)b * a.Tk * a.ldv + h * DH;
+  const int jr = j0 + warp * 16 + g;   // this thread's key rows: jr, jr + 8
+  const long long ldacc = (long long)a.H * DH;
+  float* accg = a.dq_acc + (long long)b * a.Tq * ldacc + h * DH;
+
+  load_tile<DH, BKV>(sK, kg, a.ldk, j0, a.Tk);
+  load_tile<DH, BKV>(sV, vg, a.ldv, j0, a.Tk);
+  cp_wait_all();
+  __syncthreads();
+  uint32_t kf[DH / 16][4], vf[DH / 16][4];
+  load_a_frags<DH>(kf, sK, warp * 16);
+  load_a_frags<DH>(vf, sV, warp * 16);
+  float dk[DH / 8][4], dv[DH / 8][4];
+#pragma unroll
+  for (int n = 0; n < DH / 8; ++n) {
+    dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
+    dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
+  }
+  const bool any_key = j0 < klen;
+  const int q_begin = a.causal ? (j0 / BQ2) * BQ2 : 0;   // queries before the first key of the block never see it
+
+  auto load_q = [&](int qb, int buf) {   // Q / dO tiles and the per-query lse / delta of block qb -> buffer buf
+    load_tile<DH, BQ2>(sQ + buf * BQ2 * LDS, qg, a.ldq, qb, a.Tq);
+    load_tile<DH, BQ2>(sDO + buf * BQ2 * LDS, dog, a.lddo, qb, a.Tq);
+    if (threadIdx.x < 2 * BQ2) {
+      const int which = threadIdx.x >> 5, i = qb + (threadIdx.x & 31);
+      const float* src = which ? a.delta : a.lse;
+      const bool ok = i < a.Tq;
+      const uint32_t d = smem_u32(sL + buf * 2 * BQ2 + threadIdx.x);
+      const int bytes = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + bh * a.Tq + (ok ? i : 0)), "r"(bytes) : "memory");
+    }
+    cp_commit();
+  };
+  if (any_key && q_begin < a.Tq) load_q(q_begin, 0);
+
+  // dQ stage: warp w owns query rows (w & 1) * 16 .. + 15 of the block and head columns (w >> 1) * DH/2 .. + DH/2 - 1
+  const int mt = warp & 1, nh = warp >> 1;
+  constexpr int NP = DH / 32;   // pairs of n-tiles per warp in the dQ stage (DH / 2 columns)
+  const int mi = lane >> 3, r8 = lane & 7;
+  const uint32_t ds_base = smem_u32(sDS + ((mi >> 1) * 8 + r8) * LDP + mt * 16 + (mi & 1) * 8);
+  const uint32_t kb_base = smem_u32(sK + (r8 + (mi & 1) * 8) * LDS + (mi >> 1) * 8 + nh * (DH / 2));
+
+  for (int qb = q_begin, it = 0; qb < a.Tq && any_key; qb += BQ2, ++it) {
+    cp_wait_all();
+    __syncthreads();   // block qb has landed; everyone is past the dQ stage of the previous block (sDS may be rewritten)
+    const __nv_bfloat16 *cQ = sQ + (it & 1) * BQ2 * LDS, *cDO = sDO + (it & 1) * BQ2 * LDS;
+    const float* cL = sL + (it & 1) * 2 * BQ2;
+    if (qb + BQ2 < a.Tq) load_q(qb + BQ2, (it + 1) & 1);
+    float st[4][4], dpt[4][4];   // S^T and dP^T: rows = keys, columns = the 32 queries of the block
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+      dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f;
+    }
+    mma_a_tt<DH, 4>(st, kf, cQ, 0);
+    mma_a_tt<DH, 4>(dpt, vf, cDO, 0);
+    float pt[4][4];
+    float lq[4][2], dq_[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float2 l2 = *reinterpret_cast<const float2*>(cL + n * 8 + t2), d2 = *reinterpret_cast<const float2*>(cL + BQ2 + n * 8 + t2);
+      lq[n][0] = l2.x; lq[n][1] = l2.y; dq_[n][0] = d2.x; dq_[n][1] = d2.y;
+    }
+    const bool open_tile = qb + BQ2 <= a.Tq && j0 + warp * 16 + 16 <= klen && (!a.causal || j0 + warp * 16 + 15 <= qb);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bits = 0xffu;
+      if (a.drop_thresh != 0u) bits = keep_bits<true>(a, bh, n_iblk, n_jblk, j0 + warp * 16, qb + np * 16);
+#pragma unroll
+      for (int e8 = 0; e8 < 8; ++e8) {
+        const int n = 2 * np + (e8 >> 2), e = e8 & 3;
+        float p = ex2(st[n][e] * a.scale_log2 - lq[n][e & 1]);
+        if (!open_tile) {
+          const int j = jr + (e >> 1) * 8, i = qb + n * 8 + t2 + (e & 1);
+          p = (i < a.Tq && j < a.Tk && key_ok(a, i, j, klen)) ? p : 0.f;
+        }
+        const bool keep = (bits >> e8) & 1u;
+        pt[n][e] = keep ? p * a.drop_scale : 0.f;
+        const float dpe = keep ? dpt[n][e] * a.drop_scale : 0.f;
+        st[n][e] = p * (dpe - dq_[n][e & 1]) * a.scale;   // dS^T, scaled (dK = scale dS^T Q, dQ = scale dS K)
+      }
+    }
+    // dS^T of this warp's 16 keys -> shared memory (bf16), read back transposed by the dQ stage
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      *reinterpret_cast<uint32_t*>(sDS + (warp * 16 + g) * LDP + n * 8 + t2) = pack_bf16(st[n][0], st[n][1]);
+      *reinterpret_cast<uint32_t*>(sDS + (warp * 16 + g + 8) * LDP + n * 8 + t2) = pack_bf16(st[n][2], st[n][3]);
+    }
+    mma_p_t<DH, 4>(dv, pt, cDO, 0);
+    mma_p_t<DH, 4>(dk, st, cQ, 0);
+    __syncthreads();   // all four warps' dS^T rows are in shared memory
+    {
+      float dqa[2 * NP][4];
+#pragma unroll
+      for (int n = 0; n < 2 * NP; ++n) dqa[n][0] = dqa[n][1] = dqa[n][2] = dqa[n][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < BKV / 16; ++ks) {   // contraction over the 64 keys of the block
+        uint32_t af[4];
+        ldsm_x4_t(af, ds_base + (uint32_t)(ks * 16 * LDP) * 2u);
+#pragma unroll
+        for (int np = 0; np < NP; ++np) {
+          uint32_t bfr[4];
+          ldsm_x4_t(bfr, kb_base + (uint32_t)(ks * 16 * LDS + np * 16) * 2u);
+          mma_bf16(dqa[2 * np], af, bfr[0], bfr[1]);
+          mma_bf16(dqa[2 * np + 1], af, bfr[2], bfr[3]);
+        }
+      }
+      const int i0 = qb + mt * 16 + g;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int i = i0 + rr * 8;
+        if (i < a.Tq) {
+          float* dst = accg + (long long)i * ldacc + nh * (DH / 2) + t2;
+#pragma unroll
+          for (int n = 0; n < 2 * NP; ++n) red_add_v2(dst + n * 8, dqa[n][2 * rr], dqa[n][2 * rr + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int j = jr + rr * 8;
+    if (j >= a.Tk) continue;
+    __nv_bfloat16* kp = a.dk + ((long long)b * a.Tk + j) * a.lddk + h * DH;
+    __nv_bfloat16* vp = a.dv + ((long long)b * a.Tk + j) * a.lddv + h * DH;
+#pragma unroll
+    for (int n = 0; n < DH / 8; ++n) {
+      *reinterpret_cast<uint32_t*>(kp + n * 8 + t2) = pack_bf16(dk[n][2 * rr], dk[n][2 * rr + 1]);
+      *reinterpret_cast<uint32_t*>(vp + n * 8 + t2) = pack_bf16(dv[n][2 * rr], dv[n][2 * rr + 1]);
+    }
+  }
+}
+
+// delta[b][h][i] = sum_d dO[i][h][d] * O[i][h][d] (fp32) and dq_acc = 0: one thread per (query row, head)
+template <int DH>
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const Args a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)a.B * a.Tq * a.H;
+  if (idx >= n) return;
+  const int h = (int)(idx % a.H);
+  const long long row = idx / a.H;           // b * Tq + i
+  const int b = (int)(row / a.Tq), i = (int)(row - (long long)b * a.Tq);
+  const uint4* dp = reinterpret_cast<const uint4*>(a.d_o + row * a.lddo + h * DH);
+  const uint4* op = reinterpret_cast<const uint4*>(a.o + row * a.ldo + h * DH);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < DH / 8; ++c) {
+    const uint4 x = __ldg(dp + c), y = __ldg(op + c);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc = fmaf(__uint_as_float(xs[e] << 16), __uint_as_float(ys[e] << 16), acc);
+      acc = fmaf(__uint_as_float(xs[e] & 0xffff0000u), __uint_as_float(ys[e] & 0xffff0000u), acc);
+    }
+  }
+  a.delta[((long long)b * a.H + h) * a.Tq + i] = acc;
+  float4* z = reinterpret_cast<float4*>(a.dq_acc + row * ((long long)a.H * DH) + h * DH);
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// dq (bf16, row stride lddq) = dq_acc (fp32 [B*Tq][H*DH])
+__global__ void __launch_bounds__(256) attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                                                  long long lddq, long long rows, int width) {
+  const int per_row = width / 8;
+  const long long n = rows * per_row;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / per_row;
+    const int c = (int)(idx - row * per_row) * 8;
+    const float4 x = *reinterpret_cast<const float4*>(acc + row * width + c), y = *reinterpret_cast<const float4*>(acc + row * width + c + 4);
+    uint4 o;
+    o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w); o.z = pack_bf16(y.x, y.y); o.w = pack_bf16(y.z, y.w);
+    *reinterpret_cast<uint4*>(dq + row * lddq + c) = o;
+  }
+}
+
 template <int DH>
 static int launch_fwd(const Args& a, cudaStream_t s) {
   const size_t smem = (size_t)(BQ + 4 * BKV) * (DH + 8) * 2;
@@ -531,7 +741,24 @@ static int launch_fwd(const Args& a, cudaStream_t s) {
   return 0;
 }
 template <int DH>
+static int launch_bwd_fused(const Args& a, cudaStream_t s) {
+  const size_t smem = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 128 * sizeof(float) + (size_t)BKV * (32 + 8) * 2;
+  TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n = (long long)a.B * a.Tq * a.H;
+  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  attn_bwd_fused_kernel<DH><<<dim3(ceil_div(a.Tk, BKV), a.H, a.B), kThreads, smem, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  const long long rows = (long long)a.B * a.Tq;
+  const long long work = rows * (a.H * DH / 8);
+  attn_bwd_dq_convert_kernel<<<(unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16), 256, 0, s>>>(
+      a.dq_acc, a.dq, a.lddq, rows, a.H * DH);
+  TTS_CHECK_LAUNCH();
+  return 0;
+}
+template <int DH>
 static int launch_bwd(const Args& a, cudaStream_t s) {
+  if (a.dq_acc != nullptr) return launch_bwd_fused<DH>(a, s);
   const size_t smem_q = (size_t)(2 * BQ + 4 * BKV) * (DH + 8) * 2;
   const size_t smem_kv = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 128 * sizeof(float);
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
@@ -597,6 +824,7 @@ extern "C" int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream) {
   a.dq = reinterpret_cast<__nv_bfloat16*>(t->dq); a.dk = reinterpret_cast<__nv_bfloat16*>(t->dk);
   a.dv = reinterpret_cast<__nv_bfloat16*>(t->dv);
   a.lddq = t->lddq; a.lddk = t->lddk; a.lddv = t->lddv;
+  a.dq_acc = t->dq_acc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (t->head_dim) {
     case 32: return attn::launch_bwd<32>(a, s);

@@ -48,7 +48,7 @@ class AttnTrain(C.Structure):
                 ("drop_p", C.c_float), ("seed", C.c_uint64), ("rng_stream", C.c_uint32),
                 ("d_out", C.c_void_p), ("lddo", C.c_int64), ("delta", C.c_void_p),
                 ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64), ("lddk", C.c_int64),
-                ("lddv", C.c_int64)]
+                ("lddv", C.c_int64), ("dq_acc", C.c_void_p)]
 
 
 class DecLayerWeights(C.Structure):

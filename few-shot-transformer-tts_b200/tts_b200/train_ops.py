@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the training-path entry points of the C ABI (include/tts_b200.h, "teacher-forced
 TRAINING path").  Like ops.py: CUDA tensors in, kernels on torch's current stream, no arithmetic in torch."""
 import ctypes as C
+import os
 
 import torch
 
@@ -9,6 +10,7 @@ from .ops import ACT_NONE, ACT_RELU, LN_EPS, _i32, gemm_bf16  # noqa: F401
 
 BF16 = torch.bfloat16
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1   # torch.nn.BatchNorm1d defaults (tacotron.py:79)
+_ATTN_DETERMINISTIC = os.environ.get("TTS_ATTN_DETERMINISTIC", "0") not in ("", "0")
 
 
 def _s(t):
@@ -211,10 +213,16 @@ def attn_fwd(q, k, v, B, H, Tq, Tk, dh, causal, key_len, drop_p=0.0, seed=0, str
     return ctx, lse
 
 
-def attn_bwd(q, k, v, ctx, lse, d_ctx, dq, dk, dv, B, H, Tq, Tk, dh, causal, key_len, drop_p=0.0, seed=0, stream=0):
-    """Writes dq / dk / dv (bf16 2-D views with their own row strides)."""
+def attn_bwd(q, k, v, ctx, lse, d_ctx, dq, dk, dv, B, H, Tq, Tk, dh, causal, key_len, drop_p=0.0, seed=0, stream=0,
+             deterministic=None):
+    """Writes dq / dk / dv (bf16 2-D views with their own row strides).  Default: the single-pass kernel (dQ summed with fp32
+    atomics into a scratch buffer); deterministic=True (or TTS_ATTN_DETERMINISTIC=1): the two-kernel path."""
     a = _attn_struct(q, k, v, ctx, lse, B, H, Tq, Tk, dh, causal, key_len, drop_p, seed, stream)
     delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+    if deterministic is None:
+        deterministic = _ATTN_DETERMINISTIC
+    if not deterministic:
+        a.dq_acc = _scratch(q.device, B * Tq * H * dh).data_ptr()
     a.d_out, a.lddo, a.delta = d_ctx.data_ptr(), d_ctx.stride(0), delta.data_ptr()
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)

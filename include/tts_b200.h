@@ -165,6 +165,8 @@ typedef struct TtsAttnTrain {
   const uint16_t* d_out; int64_t lddo;
   float* delta;
   uint16_t *dq, *dk, *dv; int64_t lddq, lddk, lddv;
+  float* dq_acc;   /* optional scratch, fp32 [B*tq][n_heads*head_dim]: when given, backward runs the single-pass kernel (dK, dV and
+                      dQ from one recomputation of S / dP; dQ summed with fp32 atomics); NULL = the deterministic two-kernel path */
 } TtsAttnTrain;
 int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream);
 int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream);
