@@ -1,0 +1,429 @@
+// Attention backward of the teacher-forced TRAINING path on the 5th-generation tensor cores (tcgen05 + tensor memory):
+// dK, dV and dQ of transformer/attention.py:72-122 for head_dim 96, one CTA per (sample, head, 128-key block), looping over
+// 64-query blocks.  Included by attn_train.cu (shares Args, the delta / dq_acc prologue and the dQ conversion kernel).
+//
+// Per query block the tensor cores run five products with fp32 accumulators in TENSOR MEMORY (512 columns, all used):
+//   S^T  [128 keys x 64 q] = K Q^T          (K-major A = K tile, K-major B = Q tile; 6 k-steps of 16 over head_dim 96)
+//   dP^T [128 x 64]        = V dO^T
+//   dV   [128 x 96]       += P^T dO         (A = P^T from shared memory, MN-major B = dO tile; accumulates over the loop)
+//   dK   [128 x 96]       += dS^T Q
+//   dQ^T [128(d) x 64 q]   = K^T dS^T       (MN-major A = K tile, MN-major B = dS^T; rows 96..127 are padding)
+// and eight "softmax" warps turn S^T / dP^T into P^T / dS^T: one thread per key row (tcgen05.ld 32 lanes x 32 columns, two
+// warps per lane quadrant), p = exp2(s scale - lse[q]), masks from indices / lengths, the dropout keep bit of the element
+// from the forward kernel's bit cache (one 32-bit word per query and 32 keys = one word per warp and query: no Philox in
+// backward), bf16 results written to shared memory in the 128-byte-swizzled layout both MMAs read (the SAME dS^T buffer
+// is the K-major A operand of dK and the MN-major B operand of dQ^T).  Four more warps add dQ^T to the fp32 dQ buffer with
+// coalesced red.global.add (lane = head column), a TMA warp streams Q / dO tiles (cp.async.bulk.tensor.2d, 128-byte
+// swizzle) and the per-query statistics two stages ahead, one elected lane issues every tcgen05.mma.  S^T / dP^T are
+// double-buffered in tensor memory so the products of block i+1 run while the softmax warps work on block i.
+// head_dim 96 = 1.5 swizzle atoms: tiles are loaded 128 columns wide (the extra 32 columns are the next head's, or zero
+// past the tensor) and the k-loops / N extents simply stop at 96.
+#pragma once
+#include <cuda.h>
+
+namespace tts {
+int make_tma_map_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_outer);   // gemm_bf16.cu
+
+namespace attn {
+namespace tc {
+
+constexpr int DH = 96;
+constexpr int BKT = 128, BQT = 64;
+constexpr int kThreads = 14 * 32;   // TMA, MMA, 8 softmax, 4 dQ warps
+constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oP = 131072, oDS = 147456, oStat = 163840,
+                   kStatBytes = 1536, oBar = oStat + 2 * kStatBytes;
+constexpr size_t kSmem = oBar + 256 + 1024;
+constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 352, cDQ = 448;   // tensor-memory columns
+constexpr long long kTimeout = 1LL << 28;
+
+__device__ int g_err;   // sticky: a barrier wait timed out
+
+struct Bars {
+  uint64_t kv_full, q_full[2], q_empty[2], s_full[2], s_empty[2], p_full, p_empty, dq_full, dq_empty, acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error raises g_err (every later wait of the launch then falls through) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  long long t0 = 0, spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((++spins & 255) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_err) != 0) return;
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeout) {
+        atomicExch(&g_err, 1);
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, 128-byte swizzle (see gemm_bf16.cu make_desc)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+struct Params {
+  int B, H, Tq, Tk, causal, use_mask, n_kw;
+  float scale_log2, scale, drop_scale;
+  const int32_t* key_len;
+  const float *lse, *delta;
+  const uint32_t* keep_mask;
+  __nv_bfloat16 *dk, *dv;
+  long long lddk, lddv;
+  float* dq_acc;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                  const __grid_constant__ CUtensorMap tmK,
+                                                                  const __grid_constant__ CUtensorMap tmV,
+                                                                  const __grid_constant__ CUtensorMap tmDO,
+                                                                  const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  Bars* bars = reinterpret_cast<Bars*>(smem + oBar);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j0 = blockIdx.x * BKT, h = blockIdx.y, b = blockIdx.z;
+  const long long bh = (long long)b * p.H + h;
+  const int klen = p.key_len ? min(p.key_len[b], p.Tk) : p.Tk;
+  const int q_begin = p.causal ? (j0 / BQT) * BQT : 0;   // queries before the first key of the block never see it
+  const int n_it = (j0 < klen && q_begin < p.Tq) ? (p.Tq - q_begin + BQT - 1) / BQT : 0;
+
+  if (tid == 0) {
+    mbar_init(&bars->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->q_full[s], 33);   // the TMA lane's expect_tx arrival + one cp.async arrival per producer lane
+      mbar_init(&bars->q_empty[s], 1);
+      mbar_init(&bars->s_full[s], 1);
+      mbar_init(&bars->s_empty[s], 8);
+    }
+    mbar_init(&bars->p_full, 8);
+    mbar_init(&bars->p_empty, 1);
+    mbar_init(&bars->dq_full, 1);
+    mbar_init(&bars->dq_empty, 4);
+    mbar_init(&bars->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= producer: K / V once, then Q / dO tiles and the per-query statistics, two stages =================
+    if (n_it > 0 && lane == 0) {
+      mbar_expect_tx(&bars->kv_full, 65536u);
+      tma_2d(sbase + oK, &tmK, h * DH, b * p.Tk + j0, &bars->kv_full);
+      tma_2d(sbase + oK + 16384, &tmK, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
+      tma_2d(sbase + oV, &tmV, h * DH, b * p.Tk + j0, &bars->kv_full);
+      tma_2d(sbase + oV + 16384, &tmV, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1, qb = q_begin + it * BQT;
+      mbar_wait(&bars->q_empty[s], ((it >> 1) & 1u) ^ 1u);
+      if (lane == 0) {
+        uint64_t* bar = &bars->q_full[s];
+        mbar_expect_tx(bar, 32768u);
+        const uint32_t dst = sbase + oQ + s * kStageBytes;
+        tma_2d(dst, &tmQ, h * DH, b * p.Tq + qb, bar);
+        tma_2d(dst + 8192, &tmQ, h * DH + 64, b * p.Tq + qb, bar);
+        tma_2d(dst + 16384, &tmDO, h * DH, b * p.Tq + qb, bar);
+        tma_2d(dst + 24576, &tmDO, h * DH + 64, b * p.Tq + qb, bar);
+      }
+      // [64] lse | [64] delta | [4 key words][64] keep bits
+      const uint32_t st = sbase + oStat + s * kStatBytes;
+#pragma unroll
+      for (int w = 0; w < 12; ++w) {
+        const int idx = lane + 32 * w, which = idx >> 6, c = idx & 63, i = qb + c;
+        bool ok = i < p.Tq;
+        const void* src;
+        if (which == 0) src = p.lse + bh * p.Tq + (ok ? i : 0);
+        else if (which == 1) src = p.delta + bh * p.Tq + (ok ? i : 0);
+        else {
+          const int kw = (j0 >> 5) + which - 2;
+          ok = ok && p.use_mask && kw < p.n_kw;
+          src = ok ? (const void*)(p.keep_mask + (bh * p.n_kw + kw) * p.Tq + i) : (const void*)p.lse;
+        }
+        const int bytes = ok ? 4 : 0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st + idx * 4), "l"(src), "r"(bytes) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->q_full[s])) : "memory");
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idS = idesc(128, BQT, 0, 0), idKV = idesc(128, DH, 0, 1), idQ = idesc(128, BQT, 1, 1);
+      auto issue_s = [&](int it) {   // S^T and dP^T of block `it` into tensor-memory buffer it & 1
+        const uint32_t s = it & 1, qs = sbase + oQ + s * kStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint32_t ao = (ks >> 2) * 16384 + (ks & 3) * 32, bo = (ks >> 2) * 8192 + (ks & 3) * 32;
+          umma_bf16(tmem + cS + s * BQT, make_desc(sbase + oK + ao, 16, 1024), make_desc(qs + bo, 16, 1024), idS, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint32_t ao = (ks >> 2) * 16384 + (ks & 3) * 32, bo = (ks >> 2) * 8192 + (ks & 3) * 32;
+          umma_bf16(tmem + cDP + s * BQT, make_desc(sbase + oV + ao, 16, 1024), make_desc(qs + 16384 + bo, 16, 1024), idS, ks > 0);
+        }
+        umma_commit(&bars->s_full[s]);
+      };
+      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(&bars->q_full[0], 0);
+      fence_after();
+      issue_s(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) {
+          const int s1 = (it + 1) & 1;
+          mbar_wait(&bars->q_full[s1], ((it + 1) >> 1) & 1u);
+          mbar_wait(&bars->s_empty[s1], (((it + 1) >> 1) & 1u) ^ 1u);
+          fence_after();
+          issue_s(it + 1);
+        }
+        mbar_wait(&bars->p_full, it & 1u);
+        mbar_wait(&bars->dq_empty, (it & 1u) ^ 1u);
+        fence_after();
+        const uint32_t qs = sbase + oQ + (it & 1) * kStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < BQT / 16; ++ks)   // dV += P^T dO
+          umma_bf16(tmem + cDV, make_desc(sbase + oP + ks * 32, 16, 1024), make_desc(qs + 16384 + ks * 2048, 8192, 1024), idKV,
+                    (it > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < BQT / 16; ++ks)   // dK += dS^T Q
+          umma_bf16(tmem + cDK, make_desc(sbase + oDS + ks * 32, 16, 1024), make_desc(qs + ks * 2048, 8192, 1024), idKV,
+                    (it > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < BKT / 16; ++ks)   // dQ^T = K^T dS^T
+          umma_bf16(tmem + cDQ, make_desc(sbase + oK + ks * 2048, 16384, 1024), make_desc(sbase + oDS + ks * 2048, 8192, 1024), idQ,
+                    ks > 0 ? 1u : 0u);
+        umma_commit(&bars->p_empty);
+        umma_commit(&bars->q_empty[it & 1]);
+        umma_commit(&bars->dq_full);
+      }
+      umma_commit(&bars->acc_full);
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ================= softmax warps: thread = key row; warps 2-5 take queries 0-31 of the block, 6-9 queries 32-63 =================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane, j = j0 + r;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1, qb = q_begin + it * BQT;
+      mbar_wait(&bars->q_full[s], (it >> 1) & 1u);   // the statistics of this block are in shared memory
+      mbar_wait(&bars->s_full[s], (it >> 1) & 1u);
+      fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(lane_addr + cS + s * BQT + half * 32, sv);
+      tmem_ld32(lane_addr + cDP + s * BQT + half * 32, dv);
+      tmem_wait_ld();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[s]);
+      const float* stl = reinterpret_cast<const float*>(smem + oStat + s * kStatBytes) + half * 32;
+      const float* std_ = stl + 64;
+      const uint32_t* stm = reinterpret_cast<const uint32_t*>(stl + 128 + quad * 64);
+      // interior tiles: every query exists and sees every key of the tile
+      const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
+      uint32_t pw[16], dw[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(stl + 4 * c4), d4 = *reinterpret_cast<const float4*>(std_ + 4 * c4);
+        uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (p.use_mask) m4 = *reinterpret_cast<const uint4*>(stm + 4 * c4);
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+        const uint32_t mk[4] = {m4.x, m4.y, m4.z, m4.w};
+        float pt[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * c4 + e;
+          float pe = ex2(__uint_as_float(sv[c]) * p.scale_log2 - ls[e]);
+          if (!open) {
+            const int i = qb + half * 32 + c;
+            pe = (i < p.Tq && j < klen && (!p.causal || j <= i)) ? pe : 0.f;
+          }
+          const bool keep = (mk[e] >> lane) & 1u;
+          pt[e] = keep ? pe * p.drop_scale : 0.f;
+          const float dpe = keep ? __uint_as_float(dv[c]) * p.drop_scale : 0.f;
+          ds[e] = pe * (dpe - dl[e]) * p.scale;
+        }
+        pw[2 * c4] = pack_bf16(pt[0], pt[1]); pw[2 * c4 + 1] = pack_bf16(pt[2], pt[3]);
+        dw[2 * c4] = pack_bf16(ds[0], ds[1]); dw[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
+      }
+      mbar_wait(&bars->p_empty, (it & 1u) ^ 1u);   // the products of the previous block have read P^T / dS^T
+      const uint32_t rowP = sbase + oP + r * 128, rowD = sbase + oDS + r * 128;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {   // 16-byte chunk half * 4 + c8 of the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
+        const uint32_t off = (uint32_t)(((half * 4 + c8) ^ (r & 7)) << 4);
+        st_shared_v4(rowP + off, pw[4 * c8], pw[4 * c8 + 1], pw[4 * c8 + 2], pw[4 * c8 + 3]);
+        st_shared_v4(rowD + off, dw[4 * c8], dw[4 * c8 + 1], dw[4 * c8 + 2], dw[4 * c8 + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);
+    }
+    // dV (warps 2-5) / dK (warps 6-9) of this thread's key row -> bf16
+    if (n_it > 0) {
+      mbar_wait(&bars->acc_full, 0);
+      fence_after();
+    }
+    __nv_bfloat16* dst = half == 0 ? p.dv + ((long long)b * p.Tk + j) * p.lddv + h * DH : p.dk + ((long long)b * p.Tk + j) * p.lddk + h * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t v[32];
+      if (n_it > 0) {
+        tmem_ld32(lane_addr + (half == 0 ? cDV : cDK) + c0, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (j < p.Tk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+          o.y = pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+          o.z = pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+          o.w = pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(dst + c0 + 8 * q) = o;
+        }
+      }
+    }
+  } else {
+    // ================= dQ warps: lane = head column d (TMEM lane), 64 query columns; coalesced fp32 reductions =================
+    const int quad = warp & 3, d = quad * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + cDQ;
+    const long long ldacc = (long long)p.H * DH;
+    float* accg = p.dq_acc + (long long)b * p.Tq * ldacc + h * DH + d;
+    for (int it = 0; it < n_it; ++it) {
+      const int qb = q_begin + it * BQT;
+      mbar_wait(&bars->dq_full, it & 1u);
+      fence_after();
+      uint32_t v0[32], v1[32];
+      if (quad < 3) {
+        tmem_ld32(lane_addr, v0);
+        tmem_ld32(lane_addr + 32, v1);
+        tmem_wait_ld();
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dq_empty);
+      if (quad < 3) {
+        float* dst = accg + (long long)qb * ldacc;
+        const int nq = min(BQT, p.Tq - qb);
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < nq) red_add_f32(dst + (long long)c * ldacc, __uint_as_float(v0[c]));
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (32 + c < nq) red_add_f32(dst + (long long)(32 + c) * ldacc, __uint_as_float(v1[c]));
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace tc
+
+// single-pass backward on tcgen05 (head_dim 96): delta / dq_acc prologue, the kernel above, fp32 -> bf16 dQ conversion
+static int launch_bwd_tc(const Args& a, cudaStream_t s) {
+  constexpr int DH = tc::DH;
+  CUtensorMap mq, mk, mv, mdo;
+  const long long width = (long long)a.H * DH;
+  int rc;
+  if ((rc = make_tma_map_bf16(&mq, a.q, width, (long long)a.B * a.Tq, a.ldq, tc::BQT))) return rc;
+  if ((rc = make_tma_map_bf16(&mdo, a.d_o, width, (long long)a.B * a.Tq, a.lddo, tc::BQT))) return rc;
+  if ((rc = make_tma_map_bf16(&mk, a.k, width, (long long)a.B * a.Tk, a.ldk, tc::BKT))) return rc;
+  if ((rc = make_tma_map_bf16(&mv, a.v, width, (long long)a.B * a.Tk, a.ldv, tc::BKT))) return rc;
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk; p.causal = a.causal;
+  p.use_mask = a.drop_thresh != 0u ? 1 : 0; p.n_kw = a.n_kw;
+  p.scale_log2 = a.scale_log2; p.scale = a.scale; p.drop_scale = a.drop_scale;
+  p.key_len = a.key_len; p.lse = a.lse; p.delta = a.delta; p.keep_mask = a.keep_mask;
+  p.dk = a.dk; p.dv = a.dv; p.lddk = a.lddk; p.lddv = a.lddv; p.dq_acc = a.dq_acc;
+  static bool attr = false;
+  if (!attr) {
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmem));
+    attr = true;
+  }
+  const long long n = (long long)a.B * a.Tq * a.H;
+  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  TTS_CHECK_LAUNCH();
+  tc::attn_bwd_tc_kernel<<<dim3(ceil_div(a.Tk, tc::BKT), a.H, a.B), tc::kThreads, tc::kSmem, s>>>(mq, mk, mv, mdo, p);
+  TTS_CHECK_LAUNCH();
+  const long long rows = (long long)a.B * a.Tq;
+  const long long work = rows * (a.H * DH / 8);
+  attn_bwd_dq_convert_kernel<<<(unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16), 256, 0, s>>>(
+      a.dq_acc, a.dq, a.lddq, rows, a.H * DH);
+  TTS_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace attn
+}  // namespace tts

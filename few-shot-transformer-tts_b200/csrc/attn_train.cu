@@ -16,6 +16,8 @@
 // from the softmax, dropout on the weights :89), masks of transformer/modules.py:50-52,109-112.
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -43,6 +45,10 @@ struct Args {
   __nv_bfloat16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   float* dq_acc;                    // [B*Tq][H*DH] fp32: dQ accumulated with atomics by the fused backward kernel (or NULL)
+  // optional cache of the dropout keep bits: word [bh][kw][i] holds keys 32 kw .. 32 kw + 31 of query i (n_kw = 2 ceil(Tk / 64)
+  // words per query).  The forward kernel writes it (the same Philox bits), the single-pass backward reads it instead of
+  // running Philox again: 1 bit per attention weight (64 MB per decoder layer at B=64, T=1000; the reference keeps 2 GB)
+  uint32_t* keep_mask; int n_kw;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -278,12 +284,28 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const Args a) {
         l[e >> 1] += s[n][e];
       }
     if (a.drop_thresh != 0u) {
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};   // [key word of the tile (2)][row g / g + 8]
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         const uint32_t bits = keep_bits<false>(a, bh, n_iblk, n_jblk, q0 + warp * 16, kb + np * 16);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           if (!((bits >> e) & 1u)) s[2 * np + (e >> 2)][e & 3] = 0.f;
+        // keys {t2, t2+1, t2+8, t2+9} of this 16-key block: bits 0,1,4,5 (row g) and 2,3,6,7 (row g + 8)
+        const uint32_t sh = (uint32_t)((np & 1) * 16 + t2);
+        mw[(np >> 1) * 2 + 0] |= ((bits & 3u) | (((bits >> 4) & 3u) << 8)) << sh;
+        mw[(np >> 1) * 2 + 1] |= (((bits >> 2) & 3u) | (((bits >> 6) & 3u) << 8)) << sh;
+      }
+      if (a.keep_mask != nullptr) {   // the four lanes of a quad hold disjoint key bits of the same two rows
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          mw[w] |= __shfl_xor_sync(0xffffffffu, mw[w], 1);
+          mw[w] |= __shfl_xor_sync(0xffffffffu, mw[w], 2);
+        }
+        const int t = lane & 3;   // lane t of the quad stores word t
+        const uint32_t word = t == 0 ? mw[0] : (t == 1 ? mw[1] : (t == 2 ? mw[2] : mw[3]));
+        const int row = i0 + (t & 1) * 8;
+        if (row < a.Tq) a.keep_mask[((bh * a.n_kw) + (kb >> 5) + (t >> 1)) * a.Tq + row] = word;
       }
     }
     mma_p_t<DH, 8>(o, s, cV, 0);
@@ -545,7 +567,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) 
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
   __nv_bfloat16 *sK = sm, *sV = sK + BKV * LDS, *sQ = sV + BKV * LDS, *sDO = sQ + 2 * BQ2 * LDS;
   float* sL = reinterpret_cast<float*>(sDO + 2 * BQ2 * LDS);   // 2 x ([32] lse, [32] delta)
-  __nv_bfloat16* sDS = reinterpret_cast<__nv_bfloat16*>(sL + 4 * BQ2);   // [64 keys][LDP]
+  uint32_t* sM = reinterpret_cast<uint32_t*>(sL + 4 * BQ2);    // 2 x [2 key words][32 queries] cached keep bits
+  __nv_bfloat16* sDS = reinterpret_cast<__nv_bfloat16*>(sM + 4 * BQ2);   // [64 keys][LDP]
   // heavy (early) key blocks of a causal problem first
   const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t2 = (lane & 3) * 2;
@@ -573,6 +596,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) 
     dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
     dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
   }
+  const bool use_mask = a.keep_mask != nullptr && a.drop_thresh != 0u;
   const bool any_key = j0 < klen;
   const int q_begin = a.causal ? (j0 / BQ2) * BQ2 : 0;   // queries before the first key of the block never see it
 
@@ -586,6 +610,13 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) 
       const uint32_t d = smem_u32(sL + buf * 2 * BQ2 + threadIdx.x);
       const int bytes = ok ? 4 : 0;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src + bh * a.Tq + (ok ? i : 0)), "r"(bytes) : "memory");
+    } else if (use_mask) {
+      const int idx = threadIdx.x - 2 * BQ2, kw = idx >> 5, i = qb + (idx & 31);
+      const bool ok = i < a.Tq;
+      const uint32_t d = smem_u32(sM + buf * 2 * BQ2 + idx);
+      const int bytes = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d),
+                   "l"(a.keep_mask + (bh * a.n_kw + (j0 >> 5) + kw) * a.Tq + (ok ? i : 0)), "r"(bytes) : "memory");
     }
     cp_commit();
   };
@@ -620,10 +651,16 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) 
       lq[n][0] = l2.x; lq[n][1] = l2.y; dq_[n][0] = d2.x; dq_[n][1] = d2.y;
     }
     const bool open_tile = qb + BQ2 <= a.Tq && j0 + warp * 16 + 16 <= klen && (!a.causal || j0 + warp * 16 + 15 <= qb);
+    const uint32_t* cM = sM + (it & 1) * 2 * BQ2 + (warp >> 1) * BQ2;   // the key word of this warp's 16 keys, per query
+    const uint32_t kbit = (uint32_t)((warp & 1) * 16 + g);              // bit of key row jr (jr + 8: kbit + 8)
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t bits = 0xffu;
-      if (a.drop_thresh != 0u) bits = keep_bits<true>(a, bh, n_iblk, n_jblk, j0 + warp * 16, qb + np * 16);
+      if (use_mask) {   // bit e8 <-> n-tile 2 np + (e8 >> 2), register e8 & 3: query n * 8 + t2 + (e & 1), key row jr + 8 (e >> 1)
+        const uint2 w0 = *reinterpret_cast<const uint2*>(cM + (2 * np) * 8 + t2), w1 = *reinterpret_cast<const uint2*>(cM + (2 * np + 1) * 8 + t2);
+        bits = ((w0.x >> kbit) & 1u) | (((w0.y >> kbit) & 1u) << 1) | (((w0.x >> (kbit + 8)) & 1u) << 2) | (((w0.y >> (kbit + 8)) & 1u) << 3) |
+               (((w1.x >> kbit) & 1u) << 4) | (((w1.y >> kbit) & 1u) << 5) | (((w1.x >> (kbit + 8)) & 1u) << 6) | (((w1.y >> (kbit + 8)) & 1u) << 7);
+      } else if (a.drop_thresh != 0u) bits = keep_bits<true>(a, bh, n_iblk, n_jblk, j0 + warp * 16, qb + np * 16);
 #pragma unroll
       for (int e8 = 0; e8 < 8; ++e8) {
         const int n = 2 * np + (e8 >> 2), e = e8 & 3;
@@ -742,7 +779,7 @@ static int launch_fwd(const Args& a, cudaStream_t s) {
 }
 template <int DH>
 static int launch_bwd_fused(const Args& a, cudaStream_t s) {
-  const size_t smem = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 128 * sizeof(float) + (size_t)BKV * (32 + 8) * 2;
+  const size_t smem = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 256 * sizeof(float) + (size_t)BKV * (32 + 8) * 2;
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long n = (long long)a.B * a.Tq * a.H;
   attn_bwd_prep_kernel<DH><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
@@ -792,6 +829,7 @@ static int fill(Args& a, const TtsAttnTrain* t) {
     a.drop_thresh = drop_threshold16(t->drop_p);
     a.drop_scale = 1.f / (1.f - t->drop_p);
     a.seed = t->seed; a.stream = t->rng_stream;
+    a.keep_mask = t->keep_mask; a.n_kw = 2 * ((t->tk + 63) / 64);
   }
   return 0;
 }
@@ -799,7 +837,11 @@ static int fill(Args& a, const TtsAttnTrain* t) {
 }  // namespace attn
 }  // namespace tts
 
+#include "attn_bwd_tc.cuh"
+
 using namespace tts;
+
+extern "C" int32_t tts_attn_keep_words(int32_t tk) { return 2 * ((tk + 63) / 64); }
 
 extern "C" int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream) {
   attn::Args a;
@@ -826,9 +868,20 @@ extern "C" int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream) {
   a.lddq = t->lddq; a.lddk = t->lddk; a.lddv = t->lddv;
   a.dq_acc = t->dq_acc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // head_dim 96 (the decoder): the tcgen05 kernel; it takes the dropout bits from the forward kernel's cache only
+  static const bool tc_on = !(getenv("TTS_ATTN_TC") != nullptr && atoi(getenv("TTS_ATTN_TC")) == 0);
+  if (tc_on && t->head_dim == 96 && a.dq_acc != nullptr && (a.drop_thresh == 0u || a.keep_mask != nullptr)) return attn::launch_bwd_tc(a, s);
   switch (t->head_dim) {
     case 32: return attn::launch_bwd<32>(a, s);
     case 64: return attn::launch_bwd<64>(a, s);
     default: return attn::launch_bwd<96>(a, s);
   }
+}
+
+/* 1 after a barrier wait of the tcgen05 attention kernel timed out (protocol error); reading resets it */
+extern "C" int tts_attn_tc_status(void) {
+  int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, attn::tc::g_err, sizeof(int)) != cudaSuccess) return -1;
+  if (v != 0) cudaMemcpyToSymbol(attn::tc::g_err, &zero, sizeof(int));
+  return v;
 }

@@ -557,6 +557,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
 }
 
 }  // namespace bf
+
+// 2-D bf16 tensor map, 128-byte swizzle, box = [box_outer rows][64 elements] (also used by the tcgen05 attention kernels)
+int make_tma_map_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long ld, int box_outer) {
+  return bf::make_map(map, ptr, inner, outer, ld, box_outer);
+}
 }  // namespace tts
 
 using namespace tts;

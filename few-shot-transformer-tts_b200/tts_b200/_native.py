@@ -48,7 +48,7 @@ class AttnTrain(C.Structure):
                 ("drop_p", C.c_float), ("seed", C.c_uint64), ("rng_stream", C.c_uint32),
                 ("d_out", C.c_void_p), ("lddo", C.c_int64), ("delta", C.c_void_p),
                 ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddq", C.c_int64), ("lddk", C.c_int64),
-                ("lddv", C.c_int64), ("dq_acc", C.c_void_p)]
+                ("lddv", C.c_int64), ("dq_acc", C.c_void_p), ("keep_mask", C.c_void_p)]
 
 
 class DecLayerWeights(C.Structure):
@@ -88,6 +88,8 @@ _EXPORTS = {
     "tts_gemm_bf16_status": (C.c_int, []),
     "tts_attn_train_fwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
     "tts_attn_train_bwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
+    "tts_attn_keep_words": (C.c_int32, [C.c_int32]),
+    "tts_attn_tc_status": (C.c_int, []),
     "tts_ln_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_ln_bwd_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_ln_bwd_scratch_floats": (C.c_size_t, [C.c_int32]),

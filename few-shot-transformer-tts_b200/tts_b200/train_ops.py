@@ -11,6 +11,7 @@ from .ops import ACT_NONE, ACT_RELU, LN_EPS, _i32, gemm_bf16  # noqa: F401
 BF16 = torch.bfloat16
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1   # torch.nn.BatchNorm1d defaults (tacotron.py:79)
 _ATTN_DETERMINISTIC = os.environ.get("TTS_ATTN_DETERMINISTIC", "0") not in ("", "0")
+_ATTN_KEEP_MASK = os.environ.get("TTS_ATTN_KEEP_MASK", "1") not in ("", "0")   # 0: backward regenerates the Philox bits
 
 
 def _s(t):
@@ -204,11 +205,16 @@ def _attn_struct(q, k, v, out, lse, B, H, Tq, Tk, dh, causal, key_len, drop_p, s
     return a
 
 
-def attn_fwd(q, k, v, B, H, Tq, Tk, dh, causal, key_len, drop_p=0.0, seed=0, stream=0):
-    """q [B*Tq, >=H*dh], k / v [B*Tk, ...] bf16 2-D views (row stride = ld) -> (ctx bf16 [B*Tq, H*dh], lse [B,H,Tq])."""
+def attn_fwd(q, k, v, B, H, Tq, Tk, dh, causal, key_len, drop_p=0.0, seed=0, stream=0, keep_mask=True):
+    """q [B*Tq, >=H*dh], k / v [B*Tk, ...] bf16 2-D views (row stride = ld) -> (ctx bf16 [B*Tq, H*dh], lse [B,H,Tq]).
+    keep_mask (with drop_p > 0): the forward kernel also stores its dropout keep bits, 1 bit per attention weight, and
+    the single-pass backward reads them instead of running Philox again; the words travel as `lse.keep_mask`."""
     ctx = torch.empty((B * Tq, H * dh), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     a = _attn_struct(q, k, v, ctx, lse, B, H, Tq, Tk, dh, causal, key_len, drop_p, seed, stream)
+    if keep_mask and drop_p > 0.0 and _ATTN_KEEP_MASK:
+        lse.keep_mask = torch.empty((B * H, N.load().tts_attn_keep_words(Tk), Tq), device=q.device, dtype=torch.int32)
+        a.keep_mask = lse.keep_mask.data_ptr()
     N.check(N.load().tts_attn_train_fwd(C.byref(a), _s(q)), "attn_train_fwd")
     return ctx, lse
 
@@ -223,6 +229,9 @@ def attn_bwd(q, k, v, ctx, lse, d_ctx, dq, dk, dv, B, H, Tq, Tk, dh, causal, key
         deterministic = _ATTN_DETERMINISTIC
     if not deterministic:
         a.dq_acc = _scratch(q.device, B * Tq * H * dh).data_ptr()
+        km = getattr(lse, "keep_mask", None)
+        if km is not None and drop_p > 0.0:
+            a.keep_mask = km.data_ptr()
     a.d_out, a.lddo, a.delta = d_ctx.data_ptr(), d_ctx.stride(0), delta.data_ptr()
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)

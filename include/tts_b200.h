@@ -167,7 +167,12 @@ typedef struct TtsAttnTrain {
   uint16_t *dq, *dk, *dv; int64_t lddq, lddk, lddv;
   float* dq_acc;   /* optional scratch, fp32 [B*tq][n_heads*head_dim]: when given, backward runs the single-pass kernel (dK, dV and
                       dQ from one recomputation of S / dP; dQ summed with fp32 atomics); NULL = the deterministic two-kernel path */
+  uint32_t* keep_mask;   /* optional cache of the dropout keep bits, [batch*n_heads][tts_attn_keep_words(tk)][tq] words (1 bit per
+                      attention weight): written by the forward call (drop_p > 0), read by the single-pass backward instead of
+                      regenerating the Philox bits; NULL = regenerate (same bits either way) */
 } TtsAttnTrain;
+int32_t tts_attn_keep_words(int32_t tk);
+int tts_attn_tc_status(void);   /* 1 after a barrier wait of the tcgen05 backward kernel timed out; reading resets it */
 int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream);
 int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream);
 

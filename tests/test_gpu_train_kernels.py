@@ -194,7 +194,10 @@ def _attn_ref(q, k, v, B, H, Tq, Tk, dh, causal, key_len, keep, p):
 
 @pytest.mark.parametrize("dh,H,B,Tq,Tk,mode,p", [(96, 2, 2, 150, 150, "causal", 0.0), (64, 2, 3, 70, 70, "keylen", 0.0),
                                                  (96, 3, 2, 130, 50, "keylen", 0.0), (32, 2, 2, 33, 33, "causal", 0.0),
-                                                 (96, 2, 2, 100, 100, "causal", 0.1), (64, 2, 2, 90, 41, "keylen", 0.25)])
+                                                 (96, 2, 2, 100, 100, "causal", 0.1), (64, 2, 2, 90, 41, "keylen", 0.25),
+                                                 # several 128-key blocks / 64-query blocks of the tcgen05 backward, ragged edges
+                                                 (96, 2, 2, 333, 333, "causal", 0.1), (96, 2, 2, 300, 258, "keylen", 0.1),
+                                                 (96, 1, 1, 1000, 1000, "causal", 0.1), (96, 2, 1, 257, 129, "keylen", 0.0)])
 def test_attention_train_fwd_bwd(ops, dh, H, B, Tq, Tk, mode, p):
     from tts_b200 import train_ops as TO
     g = torch.Generator().manual_seed(dh + Tq + Tk)
@@ -219,9 +222,16 @@ def test_attention_train_fwd_bwd(ops, dh, H, B, Tq, Tk, mode, p):
     assert _err(ctx, want) < 3e-2, "forward"
     dq, dk, dv = (torch.empty_like(t) for t in (qd, kd, vd))
     TO.attn_bwd(qd, kd, vd, ctx, lse, d_ctx.to(DEV), dq, dk, dv, B, H, Tq, Tk, dh, causal, kl, p, seed, stream)
+    from tts_b200 import _native
+    assert _native.load().tts_attn_tc_status() == 0, "a barrier wait of the tcgen05 backward kernel timed out"
     for name, got, ref in (("dq", dq, q.grad), ("dk", dk, k.grad), ("dv", dv, v.grad)):
         scale = float(ref.abs().max())
         assert _err(got, ref) < 3e-2 * max(scale, 1.0), (name, _err(got, ref), scale)
+    if dh == 96:   # the tcgen05 kernel against the mma.sync two-kernel path on the same inputs
+        dq2, dk2, dv2 = (torch.empty_like(t) for t in (qd, kd, vd))
+        TO.attn_bwd(qd, kd, vd, ctx, lse, d_ctx.to(DEV), dq2, dk2, dv2, B, H, Tq, Tk, dh, causal, kl, p, seed, stream, deterministic=True)
+        for name, got, ref in (("dq", dq, dq2), ("dk", dk, dk2), ("dv", dv, dv2)):
+            assert _err(got, ref.float().cpu()) < 2e-2 * max(float(ref.float().abs().max()), 1.0), ("tc vs mma.sync", name)
 
 
 def test_layernorm_train_fwd_bwd(ops):
