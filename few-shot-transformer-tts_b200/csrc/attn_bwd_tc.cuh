@@ -128,6 +128,41 @@ struct Params {
   float* dq_acc;
 };
 
+// One thread's 32 (key row, query) elements of a block: P^T (kept weights, NOT yet scaled by 1 / (1 - p)) and dS^T (not yet
+// scaled by head_dim^-0.5) as packed bf16 pairs.  Both scale factors are applied once, to the accumulated dV / dK / dQ.
+//   p = exp2(s scale - lse);  dS = p (keep ? dP / (1 - p_drop) : 0  -  delta)
+template <bool OPEN>
+__device__ __forceinline__ void soft_block(const Params& p, const uint32_t (&sv)[32], const uint32_t (&dv)[32], const float* stl,
+                                           int quad, int lane, int i0, int j, int klen, uint32_t (&pw)[16], uint32_t (&dw)[16]) {
+  const float* std_ = stl + 64;
+  const uint32_t* stm = reinterpret_cast<const uint32_t*>(stl + 128 + quad * 64);
+  const uint32_t lane_bit = 1u << lane;
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 l4 = *reinterpret_cast<const float4*>(stl + 4 * c4), d4 = *reinterpret_cast<const float4*>(std_ + 4 * c4);
+    uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p.use_mask) m4 = *reinterpret_cast<const uint4*>(stm + 4 * c4);
+    const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+    const uint32_t mk[4] = {m4.x, m4.y, m4.z, m4.w};
+    float pt[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * c4 + e;
+      float pe = ex2(fmaf(__uint_as_float(sv[c]), p.scale_log2, -ls[e]));
+      if (!OPEN) {
+        const int i = i0 + c;
+        pe = (i < p.Tq && j < klen && (!p.causal || j <= i)) ? pe : 0.f;
+      }
+      const bool keep = (mk[e] & lane_bit) != 0u;
+      pt[e] = keep ? pe : 0.f;
+      const float dpk = keep ? __uint_as_float(dv[c]) : 0.f;
+      ds[e] = pe * fmaf(dpk, p.drop_scale, -dl[e]);
+    }
+    pw[2 * c4] = pack_bf16(pt[0], pt[1]); pw[2 * c4 + 1] = pack_bf16(pt[2], pt[3]);
+    dw[2 * c4] = pack_bf16(ds[0], ds[1]); dw[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                   const __grid_constant__ CUtensorMap tmK,
                                                                   const __grid_constant__ CUtensorMap tmV,
@@ -283,35 +318,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[s]);
       const float* stl = reinterpret_cast<const float*>(smem + oStat + s * kStatBytes) + half * 32;
-      const float* std_ = stl + 64;
-      const uint32_t* stm = reinterpret_cast<const uint32_t*>(stl + 128 + quad * 64);
       // interior tiles: every query exists and sees every key of the tile
       const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
       uint32_t pw[16], dw[16];
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(stl + 4 * c4), d4 = *reinterpret_cast<const float4*>(std_ + 4 * c4);
-        uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (p.use_mask) m4 = *reinterpret_cast<const uint4*>(stm + 4 * c4);
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-        const uint32_t mk[4] = {m4.x, m4.y, m4.z, m4.w};
-        float pt[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * c4 + e;
-          float pe = ex2(__uint_as_float(sv[c]) * p.scale_log2 - ls[e]);
-          if (!open) {
-            const int i = qb + half * 32 + c;
-            pe = (i < p.Tq && j < klen && (!p.causal || j <= i)) ? pe : 0.f;
-          }
-          const bool keep = (mk[e] >> lane) & 1u;
-          pt[e] = keep ? pe * p.drop_scale : 0.f;
-          const float dpe = keep ? __uint_as_float(dv[c]) * p.drop_scale : 0.f;
-          ds[e] = pe * (dpe - dl[e]) * p.scale;
-        }
-        pw[2 * c4] = pack_bf16(pt[0], pt[1]); pw[2 * c4 + 1] = pack_bf16(pt[2], pt[3]);
-        dw[2 * c4] = pack_bf16(ds[0], ds[1]); dw[2 * c4 + 1] = pack_bf16(ds[2], ds[3]);
-      }
+      if (open) soft_block<true>(p, sv, dv, stl, quad, lane, 0, 0, 0, pw, dw);
+      else soft_block<false>(p, sv, dv, stl, quad, lane, qb + half * 32, j, klen, pw, dw);
       mbar_wait(&bars->p_empty, (it & 1u) ^ 1u);   // the products of the previous block have read P^T / dS^T
       const uint32_t rowP = sbase + oP + r * 128, rowD = sbase + oDS + r * 128;
 #pragma unroll
@@ -341,13 +352,14 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         for (int e = 0; e < 32; ++e) v[e] = 0u;
       }
       if (j < p.Tk) {
+        const float f = half == 0 ? p.drop_scale : p.scale;   // dV = P_drop^T dO / (1 - p);  dK = head_dim^-0.5 dS^T Q
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-          o.y = pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-          o.z = pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-          o.w = pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+          o.x = pack_bf16(__uint_as_float(v[8 * q + 0]) * f, __uint_as_float(v[8 * q + 1]) * f);
+          o.y = pack_bf16(__uint_as_float(v[8 * q + 2]) * f, __uint_as_float(v[8 * q + 3]) * f);
+          o.z = pack_bf16(__uint_as_float(v[8 * q + 4]) * f, __uint_as_float(v[8 * q + 5]) * f);
+          o.w = pack_bf16(__uint_as_float(v[8 * q + 6]) * f, __uint_as_float(v[8 * q + 7]) * f);
           *reinterpret_cast<uint4*>(dst + c0 + 8 * q) = o;
         }
       }
@@ -371,15 +383,22 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dq_empty);
-      if (quad < 3) {
+      if (quad < 3) {   // unscaled: head_dim^-0.5 is applied by the fp32 -> bf16 conversion kernel
         float* dst = accg + (long long)qb * ldacc;
         const int nq = min(BQT, p.Tq - qb);
+        if (nq == BQT) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < nq) red_add_f32(dst + (long long)c * ldacc, __uint_as_float(v0[c]));
+          for (int c = 0; c < 32; ++c, dst += ldacc) red_add_f32(dst, __uint_as_float(v0[c]));
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (32 + c < nq) red_add_f32(dst + (long long)(32 + c) * ldacc, __uint_as_float(v1[c]));
+          for (int c = 0; c < 32; ++c, dst += ldacc) red_add_f32(dst, __uint_as_float(v1[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < nq) red_add_f32(dst + (long long)c * ldacc, __uint_as_float(v0[c]));
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (32 + c < nq) red_add_f32(dst + (long long)(32 + c) * ldacc, __uint_as_float(v1[c]));
+        }
       }
     }
   }
@@ -420,7 +439,7 @@ static int launch_bwd_tc(const Args& a, cudaStream_t s) {
   const long long rows = (long long)a.B * a.Tq;
   const long long work = rows * (a.H * DH / 8);
   attn_bwd_dq_convert_kernel<<<(unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16), 256, 0, s>>>(
-      a.dq_acc, a.dq, a.lddq, rows, a.H * DH);
+      a.dq_acc, a.dq, a.lddq, rows, a.H * DH, a.scale);
   TTS_CHECK_LAUNCH();
   return 0;
 }

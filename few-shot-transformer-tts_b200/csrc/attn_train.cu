@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const Args a) {
 
 // dq (bf16, row stride lddq) = dq_acc (fp32 [B*Tq][H*DH])
 __global__ void __launch_bounds__(256) attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
-                                                                  long long lddq, long long rows, int width) {
+                                                                  long long lddq, long long rows, int width, float f) {
   const int per_row = width / 8;
   const long long n = rows * per_row;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_convert_kernel(const float* _
     const int c = (int)(idx - row * per_row) * 8;
     const float4 x = *reinterpret_cast<const float4*>(acc + row * width + c), y = *reinterpret_cast<const float4*>(acc + row * width + c + 4);
     uint4 o;
-    o.x = pack_bf16(x.x, x.y); o.y = pack_bf16(x.z, x.w); o.z = pack_bf16(y.x, y.y); o.w = pack_bf16(y.z, y.w);
+    o.x = pack_bf16(x.x * f, x.y * f); o.y = pack_bf16(x.z * f, x.w * f); o.z = pack_bf16(y.x * f, y.y * f); o.w = pack_bf16(y.z * f, y.w * f);
     *reinterpret_cast<uint4*>(dq + row * lddq + c) = o;
   }
 }
@@ -789,7 +789,7 @@ static int launch_bwd_fused(const Args& a, cudaStream_t s) {
   const long long rows = (long long)a.B * a.Tq;
   const long long work = rows * (a.H * DH / 8);
   attn_bwd_dq_convert_kernel<<<(unsigned)((work + 255) / 256 < 148 * 16 ? (work + 255) / 256 : 148 * 16), 256, 0, s>>>(
-      a.dq_acc, a.dq, a.lddq, rows, a.H * DH);
+      a.dq_acc, a.dq, a.lddq, rows, a.H * DH, 1.f);
   TTS_CHECK_LAUNCH();
   return 0;
 }
