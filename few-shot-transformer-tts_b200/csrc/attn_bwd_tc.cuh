@@ -30,8 +30,9 @@ namespace tc {
 constexpr int DH = 96;
 constexpr int BKT = 128, BQT = 64;
 constexpr int kThreads = 14 * 32;   // TMA, MMA, 8 softmax, 4 dQ warps
-constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oP = 131072, oDS = 147456, oStat = 163840,
-                   kStatBytes = 1536, oBar = oStat + 2 * kStatBytes;
+constexpr int kQStages = 3;   // Q / dO / statistics ring: the tile of block i+2 is requested while block i is worked on
+constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oP = oQ + kQStages * kStageBytes, oDS = oP + 16384,
+                   oStat = oDS + 16384, kStatBytes = 1536, oBar = oStat + kQStages * kStatBytes;
 constexpr size_t kSmem = oBar + 256 + 1024;
 constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 352, cDQ = 448;   // tensor-memory columns
 constexpr long long kTimeout = 1LL << 28;
@@ -39,7 +40,7 @@ constexpr long long kTimeout = 1LL << 28;
 __device__ int g_err;   // sticky: a barrier wait timed out
 
 struct Bars {
-  uint64_t kv_full, q_full[2], q_empty[2], s_full[2], s_empty[2], p_full, p_empty, dq_full, dq_empty, acc_full;
+  uint64_t kv_full, q_full[kQStages], q_empty[kQStages], s_full[2], s_empty[2], p_full, p_empty, dq_full, dq_empty, acc_full;
   uint32_t tmem_base;
 };
 
@@ -181,9 +182,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 
   if (tid == 0) {
     mbar_init(&bars->kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kQStages; ++s) {
       mbar_init(&bars->q_full[s], 33);   // the TMA lane's expect_tx arrival + one cp.async arrival per producer lane
       mbar_init(&bars->q_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
       mbar_init(&bars->s_empty[s], 8);
     }
@@ -217,8 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       tma_2d(sbase + oV + 16384, &tmV, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
     }
     for (int it = 0; it < n_it; ++it) {
-      const int s = it & 1, qb = q_begin + it * BQT;
-      mbar_wait(&bars->q_empty[s], ((it >> 1) & 1u) ^ 1u);
+      const int s = it % kQStages, qb = q_begin + it * BQT;
+      mbar_wait(&bars->q_empty[s], ((it / kQStages) & 1u) ^ 1u);
       if (lane == 0) {
         uint64_t* bar = &bars->q_full[s];
         mbar_expect_tx(bar, 32768u);
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t idS = idesc(128, BQT, 0, 0), idKV = idesc(128, DH, 0, 1), idQ = idesc(128, BQT, 1, 1);
       auto issue_s = [&](int it) {   // S^T and dP^T of block `it` into tensor-memory buffer it & 1
-        const uint32_t s = it & 1, qs = sbase + oQ + s * kStageBytes;
+        const uint32_t s = it & 1, qs = sbase + oQ + (it % kQStages) * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
           const uint32_t ao = (ks >> 2) * 16384 + (ks & 3) * 32, bo = (ks >> 2) * 8192 + (ks & 3) * 32;
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       for (int it = 0; it < n_it; ++it) {
         if (it + 1 < n_it) {
           const int s1 = (it + 1) & 1;
-          mbar_wait(&bars->q_full[s1], ((it + 1) >> 1) & 1u);
+          mbar_wait(&bars->q_full[(it + 1) % kQStages], ((it + 1) / kQStages) & 1u);
           mbar_wait(&bars->s_empty[s1], (((it + 1) >> 1) & 1u) ^ 1u);
           fence_after();
           issue_s(it + 1);
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         mbar_wait(&bars->p_full, it & 1u);
         mbar_wait(&bars->dq_empty, (it & 1u) ^ 1u);
         fence_after();
-        const uint32_t qs = sbase + oQ + (it & 1) * kStageBytes;
+        const uint32_t qs = sbase + oQ + (it % kQStages) * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < BQT / 16; ++ks)   // dV += P^T dO
           umma_bf16(tmem + cDV, make_desc(sbase + oP + ks * 32, 16, 1024), make_desc(qs + 16384 + ks * 2048, 8192, 1024), idKV,
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
           umma_bf16(tmem + cDQ, make_desc(sbase + oK + ks * 2048, 16384, 1024), make_desc(sbase + oDS + ks * 2048, 8192, 1024), idQ,
                     ks > 0 ? 1u : 0u);
         umma_commit(&bars->p_empty);
-        umma_commit(&bars->q_empty[it & 1]);
+        umma_commit(&bars->q_empty[it % kQStages]);
         umma_commit(&bars->dq_full);
       }
       umma_commit(&bars->acc_full);
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1, qb = q_begin + it * BQT;
-      mbar_wait(&bars->q_full[s], (it >> 1) & 1u);   // the statistics of this block are in shared memory
+      const int qst = it % kQStages;
+      mbar_wait(&bars->q_full[qst], (it / kQStages) & 1u);   // the statistics of this block are in shared memory
       mbar_wait(&bars->s_full[s], (it >> 1) & 1u);
       fence_after();
       uint32_t sv[32], dv[32];
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[s]);
-      const float* stl = reinterpret_cast<const float*>(smem + oStat + s * kStatBytes) + half * 32;
+      const float* stl = reinterpret_cast<const float*>(smem + oStat + qst * kStatBytes) + half * 32;
       // interior tiles: every query exists and sees every key of the tile
       const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
       uint32_t pw[16], dw[16];
