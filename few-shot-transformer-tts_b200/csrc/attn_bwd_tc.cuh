@@ -114,6 +114,9 @@ __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::aft
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
@@ -133,18 +136,19 @@ struct Params {
 // scaled by head_dim^-0.5) as packed bf16 pairs.  Both scale factors are applied once, to the accumulated dV / dK / dQ.
 //   p = exp2(s scale - lse);  dS = p (keep ? dP / (1 - p_drop) : 0  -  delta)
 template <bool OPEN>
-__device__ __forceinline__ void soft_block(const Params& p, const uint32_t (&sv)[32], const uint32_t (&dv)[32], const float* stl,
+__device__ __forceinline__ void soft_block(const Params& p, const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t stl,
                                            int quad, int lane, int i0, int j, int klen, uint32_t (&pw)[16], uint32_t (&dw)[16]) {
-  const float* std_ = stl + 64;
-  const uint32_t* stm = reinterpret_cast<const uint32_t*>(stl + 128 + quad * 64);
+  // stl: shared-memory address of this warp's 32 lse values; + 256: delta; + 512 + 256 quad: the keep words of its 32 keys
+  const uint32_t stm = stl + 512 + quad * 256;
   const uint32_t lane_bit = 1u << lane;
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
-    const float4 l4 = *reinterpret_cast<const float4*>(stl + 4 * c4), d4 = *reinterpret_cast<const float4*>(std_ + 4 * c4);
-    uint4 m4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    if (p.use_mask) m4 = *reinterpret_cast<const uint4*>(stm + 4 * c4);
-    const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-    const uint32_t mk[4] = {m4.x, m4.y, m4.z, m4.w};
+    uint32_t ls_[4], dl_[4], mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    ld_shared_v4(stl + 16 * c4, ls_);
+    ld_shared_v4(stl + 256 + 16 * c4, dl_);
+    if (p.use_mask) ld_shared_v4(stm + 16 * c4, mk);
+    const float ls[4] = {__uint_as_float(ls_[0]), __uint_as_float(ls_[1]), __uint_as_float(ls_[2]), __uint_as_float(ls_[3])};
+    const float dl[4] = {__uint_as_float(dl_[0]), __uint_as_float(dl_[1]), __uint_as_float(dl_[2]), __uint_as_float(dl_[3])};
     float pt[4], ds[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -201,6 +205,26 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
   }
+  auto load_q = [&](int it) {   // Q / dO tiles of query block `it` -> ring stage it % kQStages (one lane)
+    const int s = it % kQStages, qb = q_begin + it * BQT;
+    uint64_t* bar = &bars->q_full[s];
+    mbar_expect_tx(bar, 32768u);
+    const uint32_t dst = sbase + oQ + s * kStageBytes;
+    tma_2d(dst, &tmQ, h * DH, b * p.Tq + qb, bar);
+    tma_2d(dst + 8192, &tmQ, h * DH + 64, b * p.Tq + qb, bar);
+    tma_2d(dst + 16384, &tmDO, h * DH, b * p.Tq + qb, bar);
+    tma_2d(dst + 24576, &tmDO, h * DH + 64, b * p.Tq + qb, bar);
+  };
+  if (tid == 0 && n_it > 0) {
+    // the first tiles are requested before the CTA-wide sync: tensor-memory allocation and the loads' latency overlap
+    mbar_expect_tx(&bars->kv_full, 65536u);
+    tma_2d(sbase + oK, &tmK, h * DH, b * p.Tk + j0, &bars->kv_full);
+    tma_2d(sbase + oV, &tmV, h * DH, b * p.Tk + j0, &bars->kv_full);
+    load_q(0);
+    tma_2d(sbase + oK + 16384, &tmK, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
+    tma_2d(sbase + oV + 16384, &tmV, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
+    for (int it = 1; it < kQStages && it < n_it; ++it) load_q(it);
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -212,24 +236,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ================= producer: K / V once, then Q / dO tiles and the per-query statistics, two stages =================
-    if (n_it > 0 && lane == 0) {
-      mbar_expect_tx(&bars->kv_full, 65536u);
-      tma_2d(sbase + oK, &tmK, h * DH, b * p.Tk + j0, &bars->kv_full);
-      tma_2d(sbase + oK + 16384, &tmK, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
-      tma_2d(sbase + oV, &tmV, h * DH, b * p.Tk + j0, &bars->kv_full);
-      tma_2d(sbase + oV + 16384, &tmV, h * DH + 64, b * p.Tk + j0, &bars->kv_full);
-    }
     for (int it = 0; it < n_it; ++it) {
       const int s = it % kQStages, qb = q_begin + it * BQT;
-      mbar_wait(&bars->q_empty[s], ((it / kQStages) & 1u) ^ 1u);
-      if (lane == 0) {
-        uint64_t* bar = &bars->q_full[s];
-        mbar_expect_tx(bar, 32768u);
-        const uint32_t dst = sbase + oQ + s * kStageBytes;
-        tma_2d(dst, &tmQ, h * DH, b * p.Tq + qb, bar);
-        tma_2d(dst + 8192, &tmQ, h * DH + 64, b * p.Tq + qb, bar);
-        tma_2d(dst + 16384, &tmDO, h * DH, b * p.Tq + qb, bar);
-        tma_2d(dst + 24576, &tmDO, h * DH + 64, b * p.Tq + qb, bar);
+      if (it >= kQStages) {   // the first kQStages tiles were requested in the prologue
+        mbar_wait(&bars->q_empty[s], ((it / kQStages) & 1u) ^ 1u);
+        if (lane == 0) load_q(it);
       }
       // [64] lse | [64] delta | [4 key words][64] keep bits
       const uint32_t st = sbase + oStat + s * kStatBytes;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[s]);
-      const float* stl = reinterpret_cast<const float*>(smem + oStat + qst * kStatBytes) + half * 32;
+      const uint32_t stl = sbase + oStat + qst * kStatBytes + half * 128;
       // interior tiles: every query exists and sees every key of the tile
       const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
       uint32_t pw[16], dw[16];
@@ -390,7 +401,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       if (quad < 3) {   // unscaled: head_dim^-0.5 is applied by the fp32 -> bf16 conversion kernel
         float* dst = accg + (long long)qb * ldacc;
         const int nq = min(BQT, p.Tq - qb);
-        if (nq == BQT) {
+        if (nq == BQT && ldacc == 8 * DH) {   // the decoder's 8 heads: constant row stride, immediate offsets
+#pragma unroll
+          for (int c = 0; c < 32; ++c) red_add_f32(dst + c * 8 * DH, __uint_as_float(v0[c]));
+#pragma unroll
+          for (int c = 0; c < 32; ++c) red_add_f32(dst + (32 + c) * 8 * DH, __uint_as_float(v1[c]));
+        } else if (nq == BQT) {
 #pragma unroll
           for (int c = 0; c < 32; ++c, dst += ldacc) red_add_f32(dst, __uint_as_float(v0[c]));
 #pragma unroll
