@@ -29,7 +29,10 @@ namespace tc {
 
 constexpr int DH = 96;
 constexpr int BKT = 128, BQT = 64;
-constexpr int kThreads = 14 * 32;   // TMA, MMA, 8 softmax, 4 dQ warps
+constexpr int kSoftWarps = 16;                      // 4 per tensor-memory lane quadrant: 16 query columns per thread
+constexpr int CPT = BQT * 4 / kSoftWarps;
+constexpr int kWarps = 2 + kSoftWarps + 4 + 1;        // TMA, MMA issuer A, softmax, 4 dQ warps, MMA issuer B
+constexpr int kThreads = kWarps * 32;
 constexpr int kQStages = 3;   // Q / dO / statistics ring: the tile of block i+2 is requested while block i is worked on
 constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oP = oQ + kQStages * kStageBytes, oDS = oP + 16384,
                    oStat = oDS + 16384, kStatBytes = 1536, oBar = oStat + kQStages * kStatBytes;
@@ -38,6 +41,13 @@ constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 352, cDQ = 448;   // tens
 constexpr long long kTimeout = 1LL << 28;
 
 __device__ int g_err;   // sticky: a barrier wait timed out
+__device__ long long g_trace[3][32][8];   // diagnostics (TTS_ATTN_TC_TRACE=1): SM-clock stamps of CTA (0,0,0): [softmax warp, MMA, dQ warp][block][event]
+// compiled in only with -DTTS_ATTN_TC_TRACE_BUILD (the stamps lengthen the single-thread MMA issue path by ~7 %)
+#ifdef TTS_ATTN_TC_TRACE_BUILD
+#define TC_STAMP(role, k) do { if (tracing && it < 32) g_trace[role][it][k] = clock64(); } while (0)
+#else
+#define TC_STAMP(role, k) do { } while (0)
+#endif
 
 struct Bars {
   uint64_t kv_full, q_full[kQStages], q_empty[kQStages], s_full[2], s_empty[2], p_full, p_empty, dq_full, dq_empty, acc_full;
@@ -108,6 +118,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -130,19 +147,20 @@ struct Params {
   __nv_bfloat16 *dk, *dv;
   long long lddk, lddv;
   float* dq_acc;
+  int trace;
 };
 
-// One thread's 32 (key row, query) elements of a block: P^T (kept weights, NOT yet scaled by 1 / (1 - p)) and dS^T (not yet
+// One thread's CPT (key row, query) elements of a block: P^T (kept weights, NOT yet scaled by 1 / (1 - p)) and dS^T (not yet
 // scaled by head_dim^-0.5) as packed bf16 pairs.  Both scale factors are applied once, to the accumulated dV / dK / dQ.
 //   p = exp2(s scale - lse);  dS = p (keep ? dP / (1 - p_drop) : 0  -  delta)
 template <bool OPEN>
-__device__ __forceinline__ void soft_block(const Params& p, const uint32_t (&sv)[32], const uint32_t (&dv)[32], uint32_t stl,
-                                           int quad, int lane, int i0, int j, int klen, uint32_t (&pw)[16], uint32_t (&dw)[16]) {
-  // stl: shared-memory address of this warp's 32 lse values; + 256: delta; + 512 + 256 quad: the keep words of its 32 keys
+__device__ __forceinline__ void soft_block(const Params& p, const uint32_t (&sv)[CPT], const uint32_t (&dv)[CPT], uint32_t stl,
+                                           int quad, int lane, int i0, int j, int klen, uint32_t (&pw)[CPT / 2], uint32_t (&dw)[CPT / 2]) {
+  // stl: shared-memory address of this warp's CPT lse values; + 256: delta; + 512 + 256 quad: the keep words of its 32 keys
   const uint32_t stm = stl + 512 + quad * 256;
   const uint32_t lane_bit = 1u << lane;
 #pragma unroll
-  for (int c4 = 0; c4 < 8; ++c4) {
+  for (int c4 = 0; c4 < CPT / 4; ++c4) {
     uint32_t ls_[4], dl_[4], mk[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     ld_shared_v4(stl + 16 * c4, ls_);
     ld_shared_v4(stl + 256 + 16 * c4, dl_);
@@ -192,9 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->s_empty[s], 8);
+      mbar_init(&bars->s_empty[s], kSoftWarps);
     }
-    mbar_init(&bars->p_full, 8);
+    mbar_init(&bars->p_full, kSoftWarps);
     mbar_init(&bars->p_empty, 1);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 4);
@@ -233,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
   __syncthreads();
   fence_after();
   const uint32_t tmem = bars->tmem_base;
+  [[maybe_unused]] const bool tracing = p.trace == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 2 + kSoftWarps || warp == 2 + kSoftWarps + 1);
 
   if (warp == 0) {
     // ================= producer: K / V once, then Q / dO tiles and the per-query statistics, two stages =================
@@ -240,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       const int s = it % kQStages, qb = q_begin + it * BQT;
       if (it >= kQStages) {   // the first kQStages tiles were requested in the prologue
         mbar_wait(&bars->q_empty[s], ((it / kQStages) & 1u) ^ 1u);
+        TC_STAMP(2, 3);
         if (lane == 0) load_q(it);
       }
       // [64] lse | [64] delta | [4 key words][64] keep bits
@@ -260,53 +280,59 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(st + idx * 4), "l"(src), "r"(bytes) : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->q_full[s])) : "memory");
+      TC_STAMP(2, 4);
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer A: S^T = K Q^T and dP^T = V dO^T of every block, as soon as its tile and a tensor-memory buffer exist =================
     if (lane == 0 && n_it > 0) {
-      constexpr uint32_t idS = idesc(128, BQT, 0, 0), idKV = idesc(128, DH, 0, 1), idQ = idesc(128, BQT, 1, 1);
-      auto issue_s = [&](int it) {   // S^T and dP^T of block `it` into tensor-memory buffer it & 1
-        const uint32_t s = it & 1, qs = sbase + oQ + (it % kQStages) * kStageBytes;
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint32_t ao = (ks >> 2) * 16384 + (ks & 3) * 32, bo = (ks >> 2) * 8192 + (ks & 3) * 32;
-          umma_bf16(tmem + cS + s * BQT, make_desc(sbase + oK + ao, 16, 1024), make_desc(qs + bo, 16, 1024), idS, ks > 0);
-        }
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint32_t ao = (ks >> 2) * 16384 + (ks & 3) * 32, bo = (ks >> 2) * 8192 + (ks & 3) * 32;
-          umma_bf16(tmem + cDP + s * BQT, make_desc(sbase + oV + ao, 16, 1024), make_desc(qs + 16384 + bo, 16, 1024), idS, ks > 0);
-        }
-        umma_commit(&bars->s_full[s]);
-      };
+      constexpr uint32_t idS = idesc(128, BQT, 0, 0);
+      // base descriptors, built once: an operand slice is base + (byte offset >> 4) (the 14-bit address field cannot overflow:
+      // shared-memory addresses are below 256 KB), so the code between two tcgen05.mma is one 64-bit add per operand
+      const uint64_t dKk = make_desc(sbase + oK, 16, 1024), dVk = make_desc(sbase + oV, 16, 1024);      // K-major A: K / V tile
+      const uint64_t dQk0 = make_desc(sbase + oQ, 16, 1024);                                           // K-major B: Q tile of stage 0 (dO: + 16384)
       mbar_wait(&bars->kv_full, 0);
-      mbar_wait(&bars->q_full[0], 0);
-      fence_after();
-      issue_s(0);
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) {
-          const int s1 = (it + 1) & 1;
-          mbar_wait(&bars->q_full[(it + 1) % kQStages], ((it + 1) / kQStages) & 1u);
-          mbar_wait(&bars->s_empty[s1], (((it + 1) >> 1) & 1u) ^ 1u);
-          fence_after();
-          issue_s(it + 1);
-        }
+        const uint32_t s = it & 1;
+        mbar_wait(&bars->q_full[it % kQStages], (it / kQStages) & 1u);
+        mbar_wait(&bars->s_empty[s], ((it >> 1) & 1u) ^ 1u);
+        fence_after();
+        const uint64_t qk = dQk0 + (uint64_t)(((it % kQStages) * kStageBytes) >> 4), dok = qk + (16384 >> 4);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tmem + cS + s * BQT, dKk + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), qk + (((ks >> 2) * 8192 + (ks & 3) * 32) >> 4), idS, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tmem + cDP + s * BQT, dVk + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), dok + (((ks >> 2) * 8192 + (ks & 3) * 32) >> 4), idS, ks > 0);
+        umma_commit(&bars->s_full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarps - 1) {
+    // ================= MMA issuer B: the three gradient products of a block, as soon as the softmax warps have written P^T / dS^T.
+    // Its own thread, so that a late Q tile (issuer A waiting) never delays these products and the stage / buffer releases
+    // that hang on their completion =================
+    if (lane == 0 && n_it > 0) {
+      constexpr uint32_t idKV = idesc(128, DH, 0, 1), idQ = idesc(128, BQT, 1, 1);
+      const uint64_t dKm = make_desc(sbase + oK, 16384, 1024);                                         // MN-major A: K tile (dQ^T)
+      const uint64_t dPk = make_desc(sbase + oP, 16, 1024), dDSk = make_desc(sbase + oDS, 16, 1024);    // K-major A: P^T / dS^T
+      const uint64_t dDSm = make_desc(sbase + oDS, 8192, 1024);                                        // MN-major B: dS^T (dQ^T)
+      const uint64_t dQm0 = make_desc(sbase + oQ, 8192, 1024);                                         // MN-major B: Q tile of stage 0 (dO: + 16384)
+      mbar_wait(&bars->kv_full, 0);
+      for (int it = 0; it < n_it; ++it) {
         mbar_wait(&bars->p_full, it & 1u);
         mbar_wait(&bars->dq_empty, (it & 1u) ^ 1u);
         fence_after();
-        const uint32_t qs = sbase + oQ + (it % kQStages) * kStageBytes;
+        const uint64_t qm = dQm0 + (uint64_t)(((it % kQStages) * kStageBytes) >> 4), dom = qm + (16384 >> 4);
+        const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
         for (int ks = 0; ks < BQT / 16; ++ks)   // dV += P^T dO
-          umma_bf16(tmem + cDV, make_desc(sbase + oP + ks * 32, 16, 1024), make_desc(qs + 16384 + ks * 2048, 8192, 1024), idKV,
-                    (it > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16(tmem + cDV, dPk + ((ks * 32) >> 4), dom + ((ks * 2048) >> 4), idKV, ks > 0 ? 1u : acc);
 #pragma unroll
         for (int ks = 0; ks < BQT / 16; ++ks)   // dK += dS^T Q
-          umma_bf16(tmem + cDK, make_desc(sbase + oDS + ks * 32, 16, 1024), make_desc(qs + ks * 2048, 8192, 1024), idKV,
-                    (it > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16(tmem + cDK, dDSk + ((ks * 32) >> 4), qm + ((ks * 2048) >> 4), idKV, ks > 0 ? 1u : acc);
 #pragma unroll
         for (int ks = 0; ks < BKT / 16; ++ks)   // dQ^T = K^T dS^T
-          umma_bf16(tmem + cDQ, make_desc(sbase + oK + ks * 2048, 16384, 1024), make_desc(sbase + oDS + ks * 2048, 8192, 1024), idQ,
-                    ks > 0 ? 1u : 0u);
+          umma_bf16(tmem + cDQ, dKm + ((ks * 2048) >> 4), dDSm + ((ks * 2048) >> 4), idQ, ks > 0 ? 1u : 0u);
         umma_commit(&bars->p_empty);
         umma_commit(&bars->q_empty[it % kQStages]);
         umma_commit(&bars->dq_full);
@@ -314,62 +340,73 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       umma_commit(&bars->acc_full);
     }
     __syncwarp();
-  } else if (warp < 10) {
-    // ================= softmax warps: thread = key row; warps 2-5 take queries 0-31 of the block, 6-9 queries 32-63 =================
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+  } else if (warp < 2 + kSoftWarps) {
+    // ================= softmax warps: thread = key row (TMEM lane quadrant = warp % 4), CPT query columns per thread =================
+    const int quad = warp & 3, cg = (warp - 2) >> 2;
     const int r = quad * 32 + lane, j = j0 + r;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1, qb = q_begin + it * BQT;
       const int qst = it % kQStages;
+      TC_STAMP(0, 0);
       mbar_wait(&bars->q_full[qst], (it / kQStages) & 1u);   // the statistics of this block are in shared memory
+      TC_STAMP(0, 1);
       mbar_wait(&bars->s_full[s], (it >> 1) & 1u);
       fence_after();
-      uint32_t sv[32], dv[32];
-      tmem_ld32(lane_addr + cS + s * BQT + half * 32, sv);
-      tmem_ld32(lane_addr + cDP + s * BQT + half * 32, dv);
+      TC_STAMP(0, 2);
+      uint32_t sv[CPT], dv[CPT];
+      tmem_ld16(lane_addr + cS + s * BQT + cg * CPT, sv);
+      tmem_ld16(lane_addr + cDP + s * BQT + cg * CPT, dv);
       tmem_wait_ld();
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[s]);
-      const uint32_t stl = sbase + oStat + qst * kStatBytes + half * 128;
+      TC_STAMP(0, 3);
+      const uint32_t stl = sbase + oStat + qst * kStatBytes + cg * CPT * 4;
       // interior tiles: every query exists and sees every key of the tile
       const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
-      uint32_t pw[16], dw[16];
+      uint32_t pw[CPT / 2], dw[CPT / 2];
       if (open) soft_block<true>(p, sv, dv, stl, quad, lane, 0, 0, 0, pw, dw);
-      else soft_block<false>(p, sv, dv, stl, quad, lane, qb + half * 32, j, klen, pw, dw);
+      else soft_block<false>(p, sv, dv, stl, quad, lane, qb + cg * CPT, j, klen, pw, dw);
+      TC_STAMP(0, 4);
       mbar_wait(&bars->p_empty, (it & 1u) ^ 1u);   // the products of the previous block have read P^T / dS^T
+      TC_STAMP(0, 5);
       const uint32_t rowP = sbase + oP + r * 128, rowD = sbase + oDS + r * 128;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {   // 16-byte chunk half * 4 + c8 of the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
-        const uint32_t off = (uint32_t)(((half * 4 + c8) ^ (r & 7)) << 4);
+      for (int c8 = 0; c8 < CPT / 8; ++c8) {   // 16-byte chunks of the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
+        const uint32_t off = (uint32_t)(((cg * (CPT / 8) + c8) ^ (r & 7)) << 4);
         st_shared_v4(rowP + off, pw[4 * c8], pw[4 * c8 + 1], pw[4 * c8 + 2], pw[4 * c8 + 3]);
         st_shared_v4(rowD + off, dw[4 * c8], dw[4 * c8 + 1], dw[4 * c8 + 2], dw[4 * c8 + 3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
+      TC_STAMP(0, 6);
     }
-    // dV (warps 2-5) / dK (warps 6-9) of this thread's key row -> bf16
+    // dV (first half of the warps) / dK (second half) of this thread's key row -> bf16; each warp takes kEpiCols columns
     if (n_it > 0) {
       mbar_wait(&bars->acc_full, 0);
       fence_after();
     }
-    __nv_bfloat16* dst = half == 0 ? p.dv + ((long long)b * p.Tk + j) * p.lddv + h * DH : p.dk + ((long long)b * p.Tk + j) * p.lddk + h * DH;
+    constexpr int kEpiCols = 2 * DH / (kSoftWarps / 4);   // 48
+    const int col0 = cg * kEpiCols;                        // column of the 192-wide [dV | dK] accumulator pair
+    const bool is_dv = col0 < DH;
+    const int c_in = is_dv ? col0 : col0 - DH;
+    __nv_bfloat16* dst = is_dv ? p.dv + ((long long)b * p.Tk + j) * p.lddv + h * DH + c_in : p.dk + ((long long)b * p.Tk + j) * p.lddk + h * DH + c_in;
+    const float f = is_dv ? p.drop_scale : p.scale;   // dV = P_drop^T dO / (1 - p);  dK = head_dim^-0.5 dS^T Q
 #pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 32) {
-      uint32_t v[32];
+    for (int c0 = 0; c0 < kEpiCols; c0 += 16) {
+      uint32_t v[16];
       if (n_it > 0) {
-        tmem_ld32(lane_addr + (half == 0 ? cDV : cDK) + c0, v);
+        tmem_ld16(lane_addr + cDV + col0 + c0, v);   // dK follows dV in tensor memory
         tmem_wait_ld();
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0u;
+        for (int e = 0; e < 16; ++e) v[e] = 0u;
       }
       if (j < p.Tk) {
-        const float f = half == 0 ? p.drop_scale : p.scale;   // dV = P_drop^T dO / (1 - p);  dK = head_dim^-0.5 dS^T Q
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           uint4 o;
           o.x = pack_bf16(__uint_as_float(v[8 * q + 0]) * f, __uint_as_float(v[8 * q + 1]) * f);
           o.y = pack_bf16(__uint_as_float(v[8 * q + 2]) * f, __uint_as_float(v[8 * q + 3]) * f);
@@ -387,8 +424,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     float* accg = p.dq_acc + (long long)b * p.Tq * ldacc + h * DH + d;
     for (int it = 0; it < n_it; ++it) {
       const int qb = q_begin + it * BQT;
+      TC_STAMP(2, 0);
       mbar_wait(&bars->dq_full, it & 1u);
       fence_after();
+      TC_STAMP(2, 1);
       uint32_t v0[32], v1[32];
       if (quad < 3) {
         tmem_ld32(lane_addr, v0);
@@ -398,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dq_empty);
+      TC_STAMP(2, 2);
       if (quad < 3) {   // unscaled: head_dim^-0.5 is applied by the fp32 -> bf16 conversion kernel
         float* dst = accg + (long long)qb * ldacc;
         const int nq = min(BQT, p.Tq - qb);
@@ -446,6 +486,8 @@ static int launch_bwd_tc(const Args& a, cudaStream_t s) {
   p.scale_log2 = a.scale_log2; p.scale = a.scale; p.drop_scale = a.drop_scale;
   p.key_len = a.key_len; p.lse = a.lse; p.delta = a.delta; p.keep_mask = a.keep_mask;
   p.dk = a.dk; p.dv = a.dv; p.lddk = a.lddk; p.lddv = a.lddv; p.dq_acc = a.dq_acc;
+  static const bool trace_on = getenv("TTS_ATTN_TC_TRACE") != nullptr && atoi(getenv("TTS_ATTN_TC_TRACE")) != 0;
+  p.trace = trace_on ? atoi(getenv("TTS_ATTN_TC_TRACE")) : 0;
   static bool attr = false;
   if (!attr) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmem));

@@ -885,3 +885,8 @@ extern "C" int tts_attn_tc_status(void) {
   if (v != 0) cudaMemcpyToSymbol(attn::tc::g_err, &zero, sizeof(int));
   return v;
 }
+
+/* diagnostics: copies the 3 x 32 x 8 SM-clock stamps recorded with TTS_ATTN_TC_TRACE=1 (tests/tools_attn_trace.py) */
+extern "C" int tts_attn_tc_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, attn::tc::g_trace, sizeof(long long) * 3 * 32 * 8) == cudaSuccess ? 0 : 1;
+}

@@ -90,6 +90,7 @@ _EXPORTS = {
     "tts_attn_train_bwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
     "tts_attn_keep_words": (C.c_int32, [C.c_int32]),
     "tts_attn_tc_status": (C.c_int, []),
+    "tts_attn_tc_trace": (C.c_int, [C.c_void_p]),
     "tts_ln_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_ln_bwd_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_ln_bwd_scratch_floats": (C.c_size_t, [C.c_int32]),

@@ -172,6 +172,7 @@ typedef struct TtsAttnTrain {
                       regenerating the Philox bits; NULL = regenerate (same bits either way) */
 } TtsAttnTrain;
 int32_t tts_attn_keep_words(int32_t tk);
+int tts_attn_tc_trace(long long* out);   /* diagnostics: 3 x 32 x 8 SM-clock stamps of one CTA (TTS_ATTN_TC_TRACE=1) */
 int tts_attn_tc_status(void);   /* 1 after a barrier wait of the tcgen05 backward kernel timed out; reading resets it */
 int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream);
 int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream);
