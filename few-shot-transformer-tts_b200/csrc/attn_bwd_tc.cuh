@@ -34,8 +34,8 @@ constexpr int CPT = BQT * 4 / kSoftWarps;
 constexpr int kWarps = 2 + kSoftWarps + 4 + 1;        // TMA, MMA issuer A, softmax, 4 dQ warps, MMA issuer B
 constexpr int kThreads = kWarps * 32;
 constexpr int kQStages = 3;   // Q / dO / statistics ring: the tile of block i+2 is requested while block i is worked on
-constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oP = oQ + kQStages * kStageBytes, oDS = oP + 16384,
-                   oStat = oDS + 16384, kStatBytes = 1536, oBar = oStat + kQStages * kStatBytes;
+constexpr uint32_t oK = 0, oV = 32768, oQ = 65536, kStageBytes = 32768, oDS = oQ + kQStages * kStageBytes,   // dS^T, two buffers of 16 KB
+                   oStat = oDS + 2 * 16384, kStatBytes = 1536, oBar = oStat + kQStages * kStatBytes;
 constexpr size_t kSmem = oBar + 256 + 1024;
 constexpr uint32_t cS = 0, cDP = 128, cDV = 256, cDK = 352, cDQ = 448;   // tensor-memory columns
 constexpr long long kTimeout = 1LL << 28;
@@ -50,7 +50,7 @@ __device__ long long g_trace[3][32][8];   // diagnostics (TTS_ATTN_TC_TRACE=1): 
 #endif
 
 struct Bars {
-  uint64_t kv_full, q_full[kQStages], q_empty[kQStages], s_full[2], s_empty[2], p_full, p_empty, dq_full, dq_empty, acc_full;
+  uint64_t kv_full, q_full[kQStages], q_empty[kQStages], s_full[2], p_full[2], p_empty[2], dq_full, dq_empty, acc_full;
   uint32_t tmem_base;
 };
 
@@ -100,6 +100,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A operand from tensor memory (128 lanes x 8 columns of bf16 pairs), B from shared memory
+__device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -210,10 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->s_empty[s], kSoftWarps);
+      mbar_init(&bars->p_full[s], kSoftWarps);
+      mbar_init(&bars->p_empty[s], 1);
     }
-    mbar_init(&bars->p_full, kSoftWarps);
-    mbar_init(&bars->p_empty, 1);
     mbar_init(&bars->dq_full, 1);
     mbar_init(&bars->dq_empty, 4);
     mbar_init(&bars->acc_full, 1);
@@ -294,7 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       for (int it = 0; it < n_it; ++it) {
         const uint32_t s = it & 1;
         mbar_wait(&bars->q_full[it % kQStages], (it / kQStages) & 1u);
-        mbar_wait(&bars->s_empty[s], ((it >> 1) & 1u) ^ 1u);
+        // buffer s of tensor memory held S^T / dP^T / P^T of block it - 2: free once that block's gradient products are done
+        mbar_wait(&bars->p_empty[s], ((it >> 1) & 1u) ^ 1u);
         fence_after();
         const uint64_t qk = dQk0 + (uint64_t)(((it % kQStages) * kStageBytes) >> 4), dok = qk + (16384 >> 4);
 #pragma unroll
@@ -314,26 +325,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
     if (lane == 0 && n_it > 0) {
       constexpr uint32_t idKV = idesc(128, DH, 0, 1), idQ = idesc(128, BQT, 1, 1);
       const uint64_t dKm = make_desc(sbase + oK, 16384, 1024);                                         // MN-major A: K tile (dQ^T)
-      const uint64_t dPk = make_desc(sbase + oP, 16, 1024), dDSk = make_desc(sbase + oDS, 16, 1024);    // K-major A: P^T / dS^T
-      const uint64_t dDSm = make_desc(sbase + oDS, 8192, 1024);                                        // MN-major B: dS^T (dQ^T)
+      const uint64_t dDSk0 = make_desc(sbase + oDS, 16, 1024);                                         // K-major A: dS^T, buffer 0
+      const uint64_t dDSm0 = make_desc(sbase + oDS, 8192, 1024);                                       // MN-major B: dS^T (dQ^T), buffer 0
       const uint64_t dQm0 = make_desc(sbase + oQ, 8192, 1024);                                         // MN-major B: Q tile of stage 0 (dO: + 16384)
       mbar_wait(&bars->kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
-        mbar_wait(&bars->p_full, it & 1u);
+        const uint32_t s = it & 1;
+        mbar_wait(&bars->p_full[s], (it >> 1) & 1u);
         mbar_wait(&bars->dq_empty, (it & 1u) ^ 1u);
         fence_after();
+        const uint64_t dDSk = dDSk0 + (uint64_t)((s * 16384) >> 4), dDSm = dDSm0 + (uint64_t)((s * 16384) >> 4);
         const uint64_t qm = dQm0 + (uint64_t)(((it % kQStages) * kStageBytes) >> 4), dom = qm + (16384 >> 4);
         const uint32_t acc = it > 0 ? 1u : 0u;
 #pragma unroll
         for (int ks = 0; ks < BQT / 16; ++ks)   // dV += P^T dO
-          umma_bf16(tmem + cDV, dPk + ((ks * 32) >> 4), dom + ((ks * 2048) >> 4), idKV, ks > 0 ? 1u : acc);
+          umma_bf16_ta(tmem + cDV, tmem + cS + s * BQT + ks * 16, dom + ((ks * 2048) >> 4), idKV, ks > 0 ? 1u : acc);
 #pragma unroll
         for (int ks = 0; ks < BQT / 16; ++ks)   // dK += dS^T Q
           umma_bf16(tmem + cDK, dDSk + ((ks * 32) >> 4), qm + ((ks * 2048) >> 4), idKV, ks > 0 ? 1u : acc);
 #pragma unroll
         for (int ks = 0; ks < BKT / 16; ++ks)   // dQ^T = K^T dS^T
           umma_bf16(tmem + cDQ, dKm + ((ks * 2048) >> 4), dDSm + ((ks * 2048) >> 4), idQ, ks > 0 ? 1u : 0u);
-        umma_commit(&bars->p_empty);
+        umma_commit(&bars->p_empty[s]);
         umma_commit(&bars->q_empty[it % kQStages]);
         umma_commit(&bars->dq_full);
       }
@@ -358,9 +371,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       tmem_ld16(lane_addr + cS + s * BQT + cg * CPT, sv);
       tmem_ld16(lane_addr + cDP + s * BQT + cg * CPT, dv);
       tmem_wait_ld();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[s]);
       TC_STAMP(0, 3);
       const uint32_t stl = sbase + oStat + qst * kStatBytes + cg * CPT * 4;
       // interior tiles: every query exists and sees every key of the tile
@@ -369,18 +379,21 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       if (open) soft_block<true>(p, sv, dv, stl, quad, lane, 0, 0, 0, pw, dw);
       else soft_block<false>(p, sv, dv, stl, quad, lane, qb + cg * CPT, j, klen, pw, dw);
       TC_STAMP(0, 4);
-      mbar_wait(&bars->p_empty, (it & 1u) ^ 1u);   // the products of the previous block have read P^T / dS^T
-      TC_STAMP(0, 5);
-      const uint32_t rowP = sbase + oP + r * 128, rowD = sbase + oDS + r * 128;
+      // P^T goes back into tensor memory, over this thread's own (already loaded) S^T columns: columns 16 cg .. 16 cg + 7 of the
+      // buffer hold queries 16 cg .. 16 cg + 15 as bf16 pairs = the A operand of k-step cg of dV += P^T dO.  dS^T goes to
+      // shared-memory buffer s.  Neither needs a wait: S^T of this block was only issued once block it - 2 had released both.
+      tmem_st8(lane_addr + cS + s * BQT + cg * CPT, pw);
+      const uint32_t rowD = sbase + oDS + s * 16384 + r * 128;
 #pragma unroll
       for (int c8 = 0; c8 < CPT / 8; ++c8) {   // 16-byte chunks of the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
         const uint32_t off = (uint32_t)(((cg * (CPT / 8) + c8) ^ (r & 7)) << 4);
-        st_shared_v4(rowP + off, pw[4 * c8], pw[4 * c8 + 1], pw[4 * c8 + 2], pw[4 * c8 + 3]);
         st_shared_v4(rowD + off, dw[4 * c8], dw[4 * c8 + 1], dw[4 * c8 + 2], dw[4 * c8 + 3]);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full);
+      if (lane == 0) mbar_arrive(&bars->p_full[s]);
       TC_STAMP(0, 6);
     }
     // dV (first half of the warps) / dK (second half) of this thread's key row -> bf16; each warp takes kEpiCols columns
