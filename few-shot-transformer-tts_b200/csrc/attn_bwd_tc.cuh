@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
   __syncthreads();
   fence_after();
   const uint32_t tmem = bars->tmem_base;
-  [[maybe_unused]] const bool tracing = p.trace == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 2 + kSoftWarps || warp == 2 + kSoftWarps + 1);
+  [[maybe_unused]] const bool tracing = p.trace == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 2 + kSoftWarps || warp == kWarps - 1);
 
   if (warp == 0) {
     // ================= producer: K / V once, then Q / dO tiles and the per-query statistics, two stages =================
@@ -303,7 +303,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       mbar_wait(&bars->kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
         const uint32_t s = it & 1;
+        TC_STAMP(1, 0);
         mbar_wait(&bars->q_full[it % kQStages], (it / kQStages) & 1u);
+        TC_STAMP(1, 1);
         // buffer s of tensor memory held S^T / dP^T / P^T of block it - 2: free once that block's gradient products are done
         mbar_wait(&bars->p_empty[s], ((it >> 1) & 1u) ^ 1u);
         fence_after();
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         for (int ks = 0; ks < DH / 16; ++ks)
           umma_bf16(tmem + cDP + s * BQT, dVk + (((ks >> 2) * 16384 + (ks & 3) * 32) >> 4), dok + (((ks >> 2) * 8192 + (ks & 3) * 32) >> 4), idS, ks > 0);
         umma_commit(&bars->s_full[s]);
+        TC_STAMP(1, 2);
       }
     }
     __syncwarp();
@@ -331,7 +334,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       mbar_wait(&bars->kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
         const uint32_t s = it & 1;
+        TC_STAMP(1, 3);
         mbar_wait(&bars->p_full[s], (it >> 1) & 1u);
+        TC_STAMP(1, 4);
         mbar_wait(&bars->dq_empty, (it & 1u) ^ 1u);
         fence_after();
         const uint64_t dDSk = dDSk0 + (uint64_t)((s * 16384) >> 4), dDSm = dDSm0 + (uint64_t)((s * 16384) >> 4);
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
         umma_commit(&bars->p_empty[s]);
         umma_commit(&bars->q_empty[it % kQStages]);
         umma_commit(&bars->dq_full);
+        TC_STAMP(1, 5);
       }
       umma_commit(&bars->acc_full);
     }
