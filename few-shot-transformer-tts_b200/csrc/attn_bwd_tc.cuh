@@ -513,7 +513,8 @@ static int launch_bwd_tc(const Args& a, cudaStream_t s) {
     attr = true;
   }
   const long long n = (long long)a.B * a.Tq * a.H;
-  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  TTS_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)n * DH * sizeof(float), s));
+  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(a);
   TTS_CHECK_LAUNCH();
   tc::attn_bwd_tc_kernel<<<dim3(ceil_div(a.Tk, tc::BKT), a.H, a.B), tc::kThreads, tc::kSmem, s>>>(mq, mk, mv, mdo, p);
   TTS_CHECK_LAUNCH();

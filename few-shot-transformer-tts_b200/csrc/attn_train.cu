@@ -726,12 +726,16 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_fused_kernel(const Args a) 
   }
 }
 
-// delta[b][h][i] = sum_d dO[i][h][d] * O[i][h][d] (fp32) and dq_acc = 0: one thread per (query row, head)
+// delta[b][h][i] = sum_d dO[i][h][d] * O[i][h][d] (fp32): four threads per (query row, head), each takes every fourth
+// 16-byte chunk of the head's row, so a quad reads 64 contiguous bytes per instruction (full sectors; one thread per
+// head read 16 of every 32-byte sector and ran at half the bandwidth).  dq_acc is zeroed by a memset node.
 template <int DH>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const Args a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)a.B * a.Tq * a.H;
-  if (idx >= n) return;
+  long long idx = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const bool valid = idx < n;
+  if (!valid) idx = n - 1;
+  const int t = threadIdx.x & 3;
   const int h = (int)(idx % a.H);
   const long long row = idx / a.H;           // b * Tq + i
   const int b = (int)(row / a.Tq), i = (int)(row - (long long)b * a.Tq);
@@ -739,7 +743,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const Args a) {
   const uint4* op = reinterpret_cast<const uint4*>(a.o + row * a.ldo + h * DH);
   float acc = 0.f;
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) {
+  for (int c = t; c < DH / 8; c += 4) {
     const uint4 x = __ldg(dp + c), y = __ldg(op + c);
     const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -748,10 +752,9 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const Args a) {
       acc = fmaf(__uint_as_float(xs[e] & 0xffff0000u), __uint_as_float(ys[e] & 0xffff0000u), acc);
     }
   }
-  a.delta[((long long)b * a.H + h) * a.Tq + i] = acc;
-  float4* z = reinterpret_cast<float4*>(a.dq_acc + row * ((long long)a.H * DH) + h * DH);
-#pragma unroll
-  for (int c = 0; c < DH / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (valid && t == 0) a.delta[((long long)b * a.H + h) * a.Tq + i] = acc;
 }
 
 // dq (bf16, row stride lddq) = dq_acc (fp32 [B*Tq][H*DH])
@@ -782,7 +785,8 @@ static int launch_bwd_fused(const Args& a, cudaStream_t s) {
   const size_t smem = (size_t)(2 * BKV + 4 * 32) * (DH + 8) * 2 + 256 * sizeof(float) + (size_t)BKV * (32 + 8) * 2;
   TTS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long n = (long long)a.B * a.Tq * a.H;
-  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  TTS_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)n * DH * sizeof(float), s));
+  attn_bwd_prep_kernel<DH><<<(unsigned)((n + 63) / 64), 256, 0, s>>>(a);
   TTS_CHECK_LAUNCH();
   attn_bwd_fused_kernel<DH><<<dim3(ceil_div(a.Tk, BKV), a.H, a.B), kThreads, smem, s>>>(a);
   TTS_CHECK_LAUNCH();

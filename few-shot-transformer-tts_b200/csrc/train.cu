@@ -6,6 +6,7 @@
 // (seed, stream, element) instead of being stored (philox.cuh).
 // Reference semantics: transformer/modules.py:49-69,108-145; tacotron.py:33-44,55-65,81-90,136-158; train.py:130,188.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <math_constants.h>
 #include <string.h>
 
@@ -117,68 +118,88 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
 
 // LayerNorm backward.  dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dy gamma; dx (+= dres) in fp32;
 // per-CTA partial sums of dgamma = sum dy xhat and dbeta = sum dy go to part[blockIdx][2][C] (finalised below).
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const float* __restrict__ x,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
-                                                     float* __restrict__ dx, float* __restrict__ part, int rows, int C,
-                                                     const int32_t* row_len, int rpb) {
-  __shared__ float sh[8][2];
-  (void)sh;
+// One warp per row.  The column partials live in SHARED memory (one private [2][C] slice per warp), not in registers, and
+// xhat / g are recomputed for the output pass instead of being kept: 3 CTAs (24 warps) per SM instead of the 1 CTA that
+// the 193-register version got (ncu: 12.5 % occupancy, 1.4-2.6 TB/s).  Optionally also writes dyb = dropout_backward(dx) in
+// bf16 (the dY operand of the preceding Linear's wgrad / dgrad), which saves the separate cast kernel's re-read of dx.
+template <int NV, bool EARLY>
+__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const float* __restrict__ x,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                        float* __restrict__ dx, bf16* __restrict__ dyb, long long lddyb, Drop drop,
+                                                        float* __restrict__ part, int rows, int C, const int32_t* row_len, int rpb) {
+  extern __shared__ float red[];   // [8 warps][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nv = C >> 2;
-  float4 ag[kLnMaxV], ab[kLnMaxV];
+  float4* wa = reinterpret_cast<float4*>(red + (size_t)(warp * 2) * C);
+  float4* wb = reinterpret_cast<float4*>(red + (size_t)(warp * 2 + 1) * C);
 #pragma unroll
-  for (int i = 0; i < kLnMaxV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nv) wa[c] = wb[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  const float inv_c = 1.f / (float)C;
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
     const bool dead = row_len != nullptr && (row % rpb) >= row_len[row / rpb];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
     const uint2* dr = reinterpret_cast<const uint2*>(dy + (size_t)row * lddy);
     const float4* rr = dres ? reinterpret_cast<const float4*>(dres + (size_t)row * C) : nullptr;
-    float4 xh[kLnMaxV], gg[kLnMaxV], rv[kLnMaxV];
+    float4 xv[NV], rv[NV];
+    uint2 dv[NV];
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {   // the residual-path gradient is requested with the other operands, not after the reductions
+    for (int i = 0; i < NV; ++i) {   // every operand of the row is requested up front
       const int c = lane + 32 * i;
-      rv[i] = (rr != nullptr && c < nv) ? rr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool in = c < nv;
+      xv[i] = in ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[i] = (in && !dead) ? dr[c] : make_uint2(0u, 0u);
+      if (EARLY) rv[i] = (in && rr != nullptr) ? rr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nv) {
-        const float4 xv = xr[c];
-        float4 d = dead ? make_float4(0.f, 0.f, 0.f, 0.f) : unpack4(dr[c]);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-        gg[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        s1 += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
-        s2 += gg[i].x * xh[i].x + gg[i].y * xh[i].y + gg[i].z * xh[i].z + gg[i].w * xh[i].w;
-      } else {
-        xh[i] = gg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 d = unpack4(dv[i]);
+        const float4 xh = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+        float4 a = wa[c], bsum = wb[c];
+        a.x += d.x * xh.x; a.y += d.y * xh.y; a.z += d.z * xh.z; a.w += d.w * xh.w;
+        bsum.x += d.x; bsum.y += d.y; bsum.z += d.z; bsum.w += d.w;
+        wa[c] = a; wb[c] = bsum;
+        const float4 gg = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s1 += (gg.x + gg.y) + (gg.z + gg.w);
+        s2 += gg.x * xh.x + gg.y * xh.y + gg.z * xh.z + gg.w * xh.w;
       }
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+    if (!EARLY) {   // the residual-path gradient is requested once the first pass' temporaries are dead (no spills at 80 registers)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        rv[i] = (c < nv && rr != nullptr) ? rr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
     float4* ox = reinterpret_cast<float4*>(dx + (size_t)row * C);
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < nv)
-        ox[c] = make_float4(rs * (gg[i].x - s1 - xh[i].x * s2) + rv[i].x, rs * (gg[i].y - s1 - xh[i].y * s2) + rv[i].y,
-                            rs * (gg[i].z - s1 - xh[i].z * s2) + rv[i].z, rs * (gg[i].w - s1 - xh[i].w * s2) + rv[i].w);
+      if (c < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 d = unpack4(dv[i]);
+        const float4 xh = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+        float4 o = make_float4(rs * (d.x * g.x - s1 - xh.x * s2) + rv[i].x, rs * (d.y * g.y - s1 - xh.y * s2) + rv[i].y,
+                               rs * (d.z * g.z - s1 - xh.z * s2) + rv[i].z, rs * (d.w * g.w - s1 - xh.w * s2) + rv[i].w);
+        ox[c] = o;
+        if (dyb != nullptr) {
+          drop4(drop, (unsigned long long)row * C + 4 * c, o);
+          *reinterpret_cast<uint2*>(dyb + (size_t)row * lddyb + 4 * c) = pack4(o);
+        }
+      }
     }
   }
-  // cross-warp reduction of the column partials through shared memory, one [2][C] record per CTA
-  extern __shared__ float red[];   // [8 warps][2][C]
-#pragma unroll
-  for (int i = 0; i < kLnMaxV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nv) {
-      reinterpret_cast<float4*>(red + (size_t)(warp * 2) * C)[c] = ag[i];
-      reinterpret_cast<float4*>(red + (size_t)(warp * 2 + 1) * C)[c] = ab[i];
-    }
-  }
+  // cross-warp reduction of the column partials, one [2][C] record per CTA
   __syncthreads();
   for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
     float t = 0.f;
@@ -645,20 +666,38 @@ extern "C" int tts_ln_fwd_train(const float* x, uint16_t* y, int64_t ldy, const 
 
 extern "C" int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x, const float* mean, const float* rstd,
                                 const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, float* scratch,
-                                int32_t rows, int32_t channels, const int32_t* row_len, int32_t rows_per_batch, void* stream) {
+                                int32_t rows, int32_t channels, const int32_t* row_len, int32_t rows_per_batch, uint16_t* dyb,
+                                int64_t lddyb, float drop_p, uint64_t seed, uint32_t rng_stream, void* stream) {
   TTS_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && scratch && rows > 0, "ln_bwd_train: bad arguments");
-  TTS_REQUIRE(channels % 4 == 0 && channels <= 128 * tr::kLnMaxV && lddy % 4 == 0, "ln_bwd_train: channels %d unsupported", channels);
+  TTS_REQUIRE(channels % 4 == 0 && channels <= 128 * tr::kLnMaxV && lddy % 4 == 0 && lddyb % 4 == 0, "ln_bwd_train: channels %d unsupported", channels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int blocks = ceil_div(rows, 8);
-  if (blocks > 592) blocks = 592;   // 4 CTAs of 8 warps per SM: enough rows in flight to cover the HBM latency
+  if (blocks > 444) blocks = 444;   // 3 CTAs of 8 warps per SM
   const size_t smem = (size_t)16 * channels * sizeof(float);
-  static bool attr = false;
-  if (!attr || smem > 48 * 1024) {
-    TTS_CHECK_CUDA(cudaFuncSetAttribute(tr::ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
-  tr::ln_bwd_kernel<<<blocks, 256, smem, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, mean, rstd, gamma, dres, dx, scratch, rows,
-                                              channels, row_len, rows_per_batch > 0 ? rows_per_batch : rows);
+  const int nvl = ceil_div(channels / 4, 32);   // float4 per lane
+  const tr::Drop d = tr::make_drop(dyb ? drop_p : 0.f, seed, rng_stream);
+  const int rpb = rows_per_batch > 0 ? rows_per_batch : rows;
+  static const bool early = getenv("TTS_LN_BWD_EARLY") != nullptr && atoi(getenv("TTS_LN_BWD_EARLY")) != 0;
+#define TTS_LN_BWD(NV)                                                                                                              \
+  do {                                                                                                                              \
+    static bool attr = false;                                                                                                       \
+    if (!attr) {                                                                                                                    \
+      TTS_CHECK_CUDA(cudaFuncSetAttribute(tr::ln_bwd_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));    \
+      TTS_CHECK_CUDA(cudaFuncSetAttribute(tr::ln_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   \
+      attr = true;                                                                                                                  \
+    }                                                                                                                               \
+    if (early)                                                                                                                      \
+      tr::ln_bwd_kernel<NV, true><<<blocks, 256, smem, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, mean, rstd, gamma, dres, dx, \
+                                                    reinterpret_cast<bf16*>(dyb), lddyb, d, scratch, rows, channels, row_len, rpb); \
+    else                                                                                                                            \
+      tr::ln_bwd_kernel<NV, false><<<blocks, 256, smem, s>>>(reinterpret_cast<const bf16*>(dy), lddy, x, mean, rstd, gamma, dres, dx, \
+                                                    reinterpret_cast<bf16*>(dyb), lddyb, d, scratch, rows, channels, row_len, rpb); \
+  } while (0)
+  if (nvl <= 2) TTS_LN_BWD(2);
+  else if (nvl <= 4) TTS_LN_BWD(4);
+  else if (nvl <= 6) TTS_LN_BWD(6);
+  else TTS_LN_BWD(8);
+#undef TTS_LN_BWD
   TTS_CHECK_LAUNCH();
   tr::colpart_finalize_kernel<<<ceil_div(2 * channels, 32), 256, 0, s>>>(scratch, blocks, 2 * channels, dgamma, dbeta, channels);
   TTS_CHECK_LAUNCH();

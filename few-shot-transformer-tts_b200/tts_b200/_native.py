@@ -92,7 +92,7 @@ _EXPORTS = {
     "tts_attn_tc_status": (C.c_int, []),
     "tts_attn_tc_trace": (C.c_int, [C.c_void_p]),
     "tts_ln_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
-    "tts_ln_bwd_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "tts_ln_bwd_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
     "tts_ln_bwd_scratch_floats": (C.c_size_t, [C.c_int32]),
     "tts_dropout_cast": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int32, C.c_void_p]),
     "tts_multi_cast_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),

@@ -183,21 +183,21 @@ class TrainEngine:
             else:
                 grads["encoder.language_embed.weight"] = dh_.t() @ src
         dy = TO.dropout_cast(d2[:, :E])                                                      # bf16 [R,E] from the strided view
-        dx, grads[pre + "output_layer_norm.weight"], grads[pre + "output_layer_norm.bias"] = TO.ln_bwd(
-            dy, saved["x_out"], saved["mf"], saved["rf"], w[pre + "output_layer_norm.weight"])
+        # every LayerNorm backward also emits dyb = dropout_backward(dx) in bf16 for the Linear that precedes it (fused cast)
+        dx, grads[pre + "output_layer_norm.weight"], grads[pre + "output_layer_norm.bias"], dyb = TO.ln_bwd(
+            dy, saved["x_out"], saved["mf"], saved["rf"], w[pre + "output_layer_norm.weight"],
+            cast_drop=(p, seed, 10 + 4 * (cfg.n_encoder_layer - 1) + 3))
         for l in reversed(range(cfg.n_encoder_layer)):
             sv = saved["layers"][l]
             sid = 10 + 4 * l
             # FFN
-            dyb = TO.dropout_cast(dx, p, seed, sid + 3)
             grads[f"{pre}ffn_layers.{l}.output_layer.weight"] = self._wgrad(dyb, sv["a"])
             da = self._dgrad(dyb, f"{pre}ffn_layers.{l}.output_layer.weight", gate=sv["a"], gate_scale=1.0 / (1.0 - p))
             grads[f"{pre}ffn_layers.{l}.input_layer.weight"] = self._wgrad(da, sv["h2"])
             dh2 = self._dgrad(da, f"{pre}ffn_layers.{l}.input_layer.weight")
-            dx, grads[f"{pre}ffn_layer_norms.{l}.weight"], grads[f"{pre}ffn_layer_norms.{l}.bias"] = TO.ln_bwd(
-                dh2, sv["x2"], sv["m2"], sv["r2"], w[f"{pre}ffn_layer_norms.{l}.weight"], dres=dx)
+            dx, grads[f"{pre}ffn_layer_norms.{l}.weight"], grads[f"{pre}ffn_layer_norms.{l}.bias"], dyb = TO.ln_bwd(
+                dh2, sv["x2"], sv["m2"], sv["r2"], w[f"{pre}ffn_layer_norms.{l}.weight"], dres=dx, cast_drop=(p, seed, sid + 1))
             # self-attention
-            dyb = TO.dropout_cast(dx, p, seed, sid + 1)
             grads[f"{pre}self_attentions.{l}.output_transform.weight"] = self._wgrad(dyb, sv["ctx"])
             dctx = self._dgrad(dyb, f"{pre}self_attentions.{l}.output_transform.weight")
             qkv = sv["qkv"]
@@ -206,8 +206,10 @@ class TrainEngine:
                         dqkv[:, 2 * E:], B, H, S, S, dh, False, lens, p, seed, sid)
             grads[f"{pre}self_attentions.{l}.qkv_transform.weight"] = self._wgrad(dqkv, sv["h"])
             dh1 = self._dgrad(dqkv, f"{pre}self_attentions.{l}.qkv_transform.weight")
-            dx, grads[f"{pre}attn_layer_norms.{l}.weight"], grads[f"{pre}attn_layer_norms.{l}.bias"] = TO.ln_bwd(
-                dh1, sv["x"], sv["m1"], sv["r1"], w[f"{pre}attn_layer_norms.{l}.weight"], dres=dx)
+            res = TO.ln_bwd(dh1, sv["x"], sv["m1"], sv["r1"], w[f"{pre}attn_layer_norms.{l}.weight"], dres=dx,
+                            cast_drop=(p, seed, 10 + 4 * (l - 1) + 3) if l > 0 else None)
+            dx, grads[f"{pre}attn_layer_norms.{l}.weight"], grads[f"{pre}attn_layer_norms.{l}.bias"] = res[:3]
+            dyb = res[3] if l > 0 else None
         ge, gs = TO.embed_bwd(dx, saved["ids"], lens, self.pe(S, E), w["encoder.embed.weight"].shape[0], B, S, p, seed, 1)
         grads["encoder.embed.weight"], grads[pre + "pe_scale"] = ge, gs
         return grads
@@ -288,24 +290,23 @@ class TrainEngine:
             grads["decoder.stop_net.bias"] = TO.sum_f32(ds).view(1)
         if do is None:
             do = torch.zeros((R, D), device=self.device, dtype=BF16)
-        dx, grads[pre + "output_layer_norm.weight"], grads[pre + "output_layer_norm.bias"] = TO.ln_bwd(
-            do, saved["x_out"], saved["mo"], saved["ro"], w[pre + "output_layer_norm.weight"], row_len=tg_len, rows_per_batch=T)
+        dx, grads[pre + "output_layer_norm.weight"], grads[pre + "output_layer_norm.bias"], dyb = TO.ln_bwd(
+            do, saved["x_out"], saved["mo"], saved["ro"], w[pre + "output_layer_norm.weight"], row_len=tg_len, rows_per_batch=T,
+            cast_drop=(p, seed, 100 + 8 * (cfg.n_decoder_layer - 1) + 5))
         mem_bf = saved["mem_bf"]
         dmem = None
         for l in reversed(range(cfg.n_decoder_layer)):
             sv = saved["layers"][l]
             sid = 100 + 8 * l
-            # FFN
-            dyb = TO.dropout_cast(dx, p, seed, sid + 5)
+            # FFN (dyb = dropout_backward(dx), bf16, came out of the LayerNorm backward that produced dx)
             grads[f"{pre}ffn_layers.{l}.output_layer.weight"] = self._wgrad(dyb, sv["a"])
             da = self._dgrad(dyb, f"{pre}ffn_layers.{l}.output_layer.weight", gate=sv["a"], gate_scale=1.0 / (1.0 - p))
             grads[f"{pre}ffn_layers.{l}.input_layer.weight"] = self._wgrad(da, sv["h3"])
             dh3 = self._dgrad(da, f"{pre}ffn_layers.{l}.input_layer.weight")
             del da
-            dx, grads[f"{pre}ffn_layer_norms.{l}.weight"], grads[f"{pre}ffn_layer_norms.{l}.bias"] = TO.ln_bwd(
-                dh3, sv["x3"], sv["m3"], sv["r3"], w[f"{pre}ffn_layer_norms.{l}.weight"], dres=dx)
+            dx, grads[f"{pre}ffn_layer_norms.{l}.weight"], grads[f"{pre}ffn_layer_norms.{l}.bias"], dyb = TO.ln_bwd(
+                dh3, sv["x3"], sv["m3"], sv["r3"], w[f"{pre}ffn_layer_norms.{l}.weight"], dres=dx, cast_drop=(p, seed, sid + 3))
             # cross-attention
-            dyb = TO.dropout_cast(dx, p, seed, sid + 3)
             grads[f"{pre}encdec_attentions.{l}.output_transform.weight"] = self._wgrad(dyb, sv["ctx2"])
             dctx2 = self._dgrad(dyb, f"{pre}encdec_attentions.{l}.output_transform.weight")
             kv = sv["kv"]
@@ -317,10 +318,9 @@ class TrainEngine:
             grads[f"{pre}encdec_attentions.{l}.kv_transform.weight"] = self._wgrad(dkv, mem_bf)
             if need_dmem:
                 dmem = self._dgrad(dkv, f"{pre}encdec_attentions.{l}.kv_transform.weight", out_dtype=torch.float32, residual=dmem)
-            dx, grads[f"{pre}encdec_layer_norms.{l}.weight"], grads[f"{pre}encdec_layer_norms.{l}.bias"] = TO.ln_bwd(
-                dh2, sv["x2"], sv["m2"], sv["r2"], w[f"{pre}encdec_layer_norms.{l}.weight"], dres=dx)
+            dx, grads[f"{pre}encdec_layer_norms.{l}.weight"], grads[f"{pre}encdec_layer_norms.{l}.bias"], dyb = TO.ln_bwd(
+                dh2, sv["x2"], sv["m2"], sv["r2"], w[f"{pre}encdec_layer_norms.{l}.weight"], dres=dx, cast_drop=(p, seed, sid + 1))
             # self-attention
-            dyb = TO.dropout_cast(dx, p, seed, sid + 1)
             grads[f"{pre}self_attentions.{l}.output_transform.weight"] = self._wgrad(dyb, sv["ctx"])
             dctx = self._dgrad(dyb, f"{pre}self_attentions.{l}.output_transform.weight")
             qkv = sv["qkv"]
@@ -330,8 +330,10 @@ class TrainEngine:
             grads[f"{pre}self_attentions.{l}.qkv_transform.weight"] = self._wgrad(dqkv, sv["h"])
             dh1 = self._dgrad(dqkv, f"{pre}self_attentions.{l}.qkv_transform.weight")
             del dqkv
-            dx, grads[f"{pre}attn_layer_norms.{l}.weight"], grads[f"{pre}attn_layer_norms.{l}.bias"] = TO.ln_bwd(
-                dh1, sv["x"], sv["m1"], sv["r1"], w[f"{pre}attn_layer_norms.{l}.weight"], dres=dx)
+            res = TO.ln_bwd(dh1, sv["x"], sv["m1"], sv["r1"], w[f"{pre}attn_layer_norms.{l}.weight"], dres=dx,
+                            cast_drop=(p, seed, 100 + 8 * (l - 1) + 5) if l > 0 else None)
+            dx, grads[f"{pre}attn_layer_norms.{l}.weight"], grads[f"{pre}attn_layer_norms.{l}.bias"] = res[:3]
+            dyb = res[3] if l > 0 else None
             saved["layers"][l] = None   # free the layer's activations as soon as its backward is done
         dpre, grads[pre + "pe_scale"] = TO.shift_pe_bwd(dx, tg_len, self.pe(T, D), B, T, p, seed, 2)
         q = "decoder.prenet."

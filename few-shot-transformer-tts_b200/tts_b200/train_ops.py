@@ -39,17 +39,22 @@ def ln_fwd(x, gamma, beta, row_len=None, rows_per_batch=0):
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, mean, rstd, gamma, dres=None, row_len=None, rows_per_batch=0):
-    """dy bf16 [R,C] -> (dx fp32 [R,C] (+ dres), dgamma [C], dbeta [C])."""
+def ln_bwd(dy, x, mean, rstd, gamma, dres=None, row_len=None, rows_per_batch=0, cast_drop=None):
+    """dy bf16 [R,C] -> (dx fp32 [R,C] (+ dres), dgamma [C], dbeta [C]).  cast_drop = (p, seed, stream): a fourth result
+    dyb = dropout_cast(dx, p, seed, stream) (bf16) comes out of the same kernel."""
     R, Cc = x.shape
     lib = N.load()
     dx = torch.empty_like(x)
     dg = torch.empty((Cc,), device=x.device, dtype=torch.float32)
     db = torch.empty_like(dg)
     scratch = _scratch(x.device, lib.tts_ln_bwd_scratch_floats(Cc))
+    dyb = torch.empty((R, Cc), device=x.device, dtype=BF16) if cast_drop is not None else None
+    p, seed, stream = cast_drop if cast_drop is not None else (0.0, 0, 0)
     N.check(lib.tts_ln_bwd_train(dy.data_ptr(), dy.stride(0), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                  N.ptr(dres), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), scratch.data_ptr(), R, Cc,
-                                 N.ptr(row_len), rows_per_batch, _s(x)), "ln_bwd_train")
+                                 N.ptr(row_len), rows_per_batch, N.ptr(dyb), Cc, p, seed, stream, _s(x)), "ln_bwd_train")
+    if cast_drop is not None:
+        return dx, dg, db, dyb
     return dx, dg, db
 
 

@@ -182,10 +182,12 @@ int tts_attn_train_bwd(const TtsAttnTrain* t, void* stream);
 int tts_ln_fwd_train(const float* x, uint16_t* y, int64_t ldy, const float* gamma, const float* beta, float* mean,
                      float* rstd, int32_t rows, int32_t channels, float eps, const int32_t* row_len,
                      int32_t rows_per_batch, void* stream);
-/* dx = LN'(dy) (+ dres: the gradient arriving over the residual connection), dgamma, dbeta.  scratch: tts_ln_bwd_scratch_floats. */
+/* dx = LN'(dy) (+ dres: the gradient arriving over the residual connection), dgamma, dbeta.  scratch: tts_ln_bwd_scratch_floats.
+ * dyb (optional, bf16): also dyb = keep(seed, rng_stream, element) ? dx / (1 - drop_p) : 0, the tts_dropout_cast of dx. */
 int tts_ln_bwd_train(const uint16_t* dy, int64_t lddy, const float* x, const float* mean, const float* rstd,
                      const float* gamma, const float* dres, float* dx, float* dgamma, float* dbeta, float* scratch,
-                     int32_t rows, int32_t channels, const int32_t* row_len, int32_t rows_per_batch, void* stream);
+                     int32_t rows, int32_t channels, const int32_t* row_len, int32_t rows_per_batch, uint16_t* dyb,
+                     int64_t lddyb, float drop_p, uint64_t seed, uint32_t rng_stream, void* stream);
 size_t tts_ln_bwd_scratch_floats(int32_t channels);
 /* dst (bf16) = keep(seed, stream, element) ? src / (1 - p) : 0: the backward of an epilogue dropout, or (p = 0) a cast. */
 int tts_dropout_cast(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int32_t channels,

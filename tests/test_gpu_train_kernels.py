@@ -252,6 +252,11 @@ def test_layernorm_train_fwd_bwd(ops):
         assert _err(dx, xr.grad + dres.double()) < 1e-4 * max(1.0, float(xr.grad.abs().max()))
         assert _err(dg, gr.grad) < 2e-3 * max(1.0, float(gr.grad.abs().max()) / 10)
         assert _err(db, br.grad) < 2e-3 * max(1.0, float(br.grad.abs().max()) / 10)
+        # the fused bf16 output = the separate dropout-cast kernel on dx (same Philox mask), with and without dropout
+        for pd in (0.0, 0.3):
+            dx2, _, _, dyb = TO.ln_bwd(dy.to(DEV), x.to(DEV), mean, rstd, gam.to(DEV), dres=dres.to(DEV), cast_drop=(pd, 77, 9))
+            assert torch.equal(dx2, dx)
+            assert torch.equal(dyb, TO.dropout_cast(dx, pd, 77, 9))
     # row mask (final LayerNorm + impute)
     lens = torch.tensor([2, 5], dtype=torch.int32, device=DEV)
     x = torch.randn(10, 64, generator=g).to(DEV)
