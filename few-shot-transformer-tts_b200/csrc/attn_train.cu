@@ -842,6 +842,7 @@ static int fill(Args& a, const TtsAttnTrain* t) {
 }  // namespace tts
 
 #include "attn_bwd_tc.cuh"
+#include "attn_fwd_tc.cuh"
 
 using namespace tts;
 
@@ -852,6 +853,9 @@ extern "C" int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream) {
   int rc = attn::fill(a, t);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // head_dim 96 (the decoder's self- and cross-attention): the tcgen05 kernel (TTS_ATTN_FWD_TC=0: the mma.sync kernel)
+  static const bool tc_on = getenv("TTS_ATTN_FWD_TC") != nullptr && atoi(getenv("TTS_ATTN_FWD_TC")) != 0;   // opt-in until verified on hardware
+  if (tc_on && t->head_dim == 96) return attn::launch_fwd_tc(a, s);
   switch (t->head_dim) {
     case 32: return attn::launch_fwd<32>(a, s);
     case 64: return attn::launch_fwd<64>(a, s);

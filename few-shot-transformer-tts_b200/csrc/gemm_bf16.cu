@@ -41,11 +41,15 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr long long kTimeout = 2LL << 30;
 
-template <int BN>
+// MODE 0: one CTA per tile (cta_group::1).  MODE 1: CTA pair, cta_group::1 MMAs, B tile TMA-multicast into both CTAs.
+// MODE 2: CTA pair, ONE cta_group::2 MMA (M = 256) per k-step issued by the even CTA: each CTA keeps its own 128 rows of A
+// and HALF of the B tile in shared memory (a stage is 32 KB instead of 48, six stages instead of four).
+template <int BN, int MODE = 0>
 struct Cfg {
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBBytes = BN * BK * 2;                      // whole B tile
+  static constexpr int kBStage = MODE == 2 ? kBBytes / 2 : kBBytes;   // B bytes resident per CTA and stage
+  static constexpr int kStage = kABytes + kBStage;
+  static constexpr int kStages = MODE == 2 ? (BN == 256 ? 6 : 8) : (BN == 256 ? 4 : 6);
   static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -108,6 +112,25 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// cta_group::2 forms: the TMA of either CTA of the pair completes its bytes on the EVEN CTA's barrier (`bar` is a
+// shared::cluster address obtained with mapa), the MMA spans both CTAs' shared and tensor memory, the commit arrives on the
+// same barrier offset in both CTAs.
+__device__ __forceinline__ void tma_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)0x3) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -134,6 +157,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -175,9 +204,11 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int u, int rank) {
   return r;
 }
 
-template <int BN, int CL>
+template <int BN, int MODE>
 __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const Params& p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MODE>;
+  constexpr int CL = MODE == 0 ? 1 : 2;
+  constexpr bool TWO = MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Shared* sh = reinterpret_cast<Shared*>(smem + C::kStages * C::kStage);
@@ -189,19 +220,25 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
   if (tid == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&sh->full[s], 1);
-      mbar_init(&sh->empty[s], CL);   // a stage is refilled by multicast: BOTH CTAs' MMAs must have read it
+      // MODE 1: a stage is refilled by multicast, BOTH CTAs' MMAs must have read it.  MODE 2: one cta_group::2 commit
+      mbar_init(&sh->empty[s], TWO ? 1 : CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sh->tfull[s], 1);
-      mbar_init(&sh->tempty[s], kEpiWarps);
+      mbar_init(&sh->tempty[s], TWO ? 2 * kEpiWarps : kEpiWarps);   // MODE 2: both CTAs' epilogues free the pair's accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) {   // the MMA warp owns the tensor-memory allocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)C::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // the MMA warp owns the tensor-memory allocation (MODE 2: the same warp of both CTAs, collectively)
+    if (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -221,10 +258,27 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
           const int s = it % C::kStages;
           ok = mbar_wait(&sh->empty[s], ((it / C::kStages) & 1u) ^ 1u);
           uint64_t* bar = &sh->full[s];
-          mbar_expect_tx(bar, (unsigned)C::kStage);
           const uint32_t a_dst = smem_u32(smem + s * C::kStage), b_dst = a_dst + kABytes;
           const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
           const int ka = kc * BK, kbc = tap * p.tap_b_stride + kc * BK;
+          if (TWO) {   // both CTAs' tiles complete on the even CTA's barrier, which expects the bytes of the pair
+            if (rank == 0) mbar_expect_tx(bar, 2u * (unsigned)C::kStage);
+            const uint32_t lbar = mapa_rank(smem_u32(bar), 0u);
+            if (!p.a_mn) {
+              tma_2d_2sm(a_dst, &tmA, ka, un.m0 + tap, lbar);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_2d_2sm(a_dst + j * 8192, &tmA, un.m0 + 64 * j, ka, lbar);
+            }
+            if (!p.b_mn) {   // my half of the tile's B rows, at the start of my B region
+              tma_2d_2sm(b_dst, &tmB, kbc, n0 + rank * (BN / 2), lbar);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) tma_2d_2sm(b_dst + j * 8192, &tmB, n0 + rank * (BN / 2) + 64 * j, kbc, lbar);
+            }
+            continue;
+          }
+          mbar_expect_tx(bar, (unsigned)C::kStage);
           if (!p.a_mn) {
             tma_2d(a_dst, &tmA, ka, un.m0 + tap, bar);
           } else {
@@ -254,11 +308,12 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (MODE 2: the even CTA issues for the pair) =================
+    if (lane == 0 && (!TWO || rank == 0)) {
       // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, per-operand major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((TWO ? 2 * BM : BM) >> 4) << 24);
       const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;   // bytes per K = 16
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       uint32_t it = 0, lu = 0;
@@ -275,13 +330,17 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_base = smem_u32(smem + s * C::kStage), b_base = a_base + kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(acc, make_desc(a_base + k * a_step, a_lbo, 1024u), make_desc(b_base + k * b_step, b_lbo, 1024u), idesc,
-                      (kb > un.kb0 || k > 0) ? 1u : 0u);
-          if (CL == 1) umma_commit(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it
-          else umma_commit_mc(&sh->empty[s], (uint16_t)0x3);   // ... in both CTAs of the pair
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_desc(a_base + k * a_step, a_lbo, 1024u), db = make_desc(b_base + k * b_step, b_lbo, 1024u);
+            if (TWO) umma_bf16_2sm(acc, da, db, idesc, (kb > un.kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(acc, da, db, idesc, (kb > un.kb0 || k > 0) ? 1u : 0u);
+          }
+          if (TWO) umma_commit_2sm(&sh->empty[s]);   // the stage may be refilled once these MMAs have read it, in both CTAs
+          else if (CL == 1) umma_commit(&sh->empty[s]);
+          else umma_commit_mc(&sh->empty[s], (uint16_t)0x3);
         }
-        umma_commit(&sh->tfull[as]);    // accumulator complete
+        if (TWO) umma_commit_2sm(&sh->tfull[as]);   // accumulator complete: both CTAs' epilogues read their 128 rows
+        else umma_commit(&sh->tfull[as]);
       }
     }
     __syncwarp();
@@ -410,9 +469,16 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
         }
         if (p.split_k > 1) {   // fp32 reduction of the K splits into a zero-initialised C
           float* cp = reinterpret_cast<float*>(p.C) + orow * p.ldc + n;
+          if (full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n + j < p.N) atomicAdd(cp + j, x[j]);
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + 4 * q), "f"(x[4 * q]), "f"(x[4 * q + 1]),
+                           "f"(x[4 * q + 2]), "f"(x[4 * q + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) atomicAdd(cp + j, x[j]);
+          }
         } else if (p.out_bf16) {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n;
           if (full && (p.ldc & 15) == 0) {   // 32-byte stores: one full sector per lane and instruction
@@ -447,26 +513,37 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->tempty[as]);   // this warp's quadrant of the accumulator is free again
+      if (lane == 0) {   // this warp's quadrant of the accumulator is free again (MODE 2: tell the issuing CTA)
+        if (TWO) mbar_arrive_cluster(mapa_rank(smem_u32(&sh->tempty[as]), 0u));
+        else mbar_arrive(&sh->tempty[as]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // nobody leaves while the peer may still multicast into it or arrive on its barriers
-  if (warp == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)C::kTmemCols) : "memory");
+  if (warp == 1) {
+    if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)C::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)C::kTmemCols) : "memory");
+  }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ Params p) {
-  gemm_bf16_body<BN, 1>(tmA, tmB, p);
+  gemm_bf16_body<BN, 0>(tmA, tmB, p);
 }
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ Params p) {
+  gemm_bf16_body<BN, 1>(tmA, tmB, p);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ Params p) {
   gemm_bf16_body<BN, 2>(tmA, tmB, p);
 }
 
@@ -519,33 +596,35 @@ static int sm_count() {
   return n[dev];
 }
 
-static bool use_pairs(int n_mblk) {
-  static const bool pairs_on = !(getenv("TTS_GEMM_PAIRS") != nullptr && atoi(getenv("TTS_GEMM_PAIRS")) == 0);
-  return pairs_on && n_mblk >= 2;
+// TTS_GEMM_PAIRS: 0 = one CTA per tile, 1 = CTA pairs with a multicast B tile (cta_group::1), 2 (default) = cta_group::2 pairs
+static int pair_mode(int n_mblk) {
+  static const int mode = getenv("TTS_GEMM_PAIRS") != nullptr ? atoi(getenv("TTS_GEMM_PAIRS")) : 2;
+  return n_mblk >= 2 ? (mode < 0 || mode > 2 ? 2 : mode) : 0;
 }
+static bool use_pairs(int n_mblk) { return pair_mode(n_mblk) != 0; }
 
 template <int BN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaStream_t s) {
   using C = Cfg<BN>;
   const size_t smem = (size_t)C::kStages * C::kStage + sizeof(Shared) + 1024 + 64;
+  const size_t smem2 = (size_t)Cfg<BN, 2>::kStages * Cfg<BN, 2>::kStage + sizeof(Shared) + 1024 + 64;
   static std::atomic<unsigned long long> configured{0ull};
   int dev = 0;
   cudaGetDevice(&dev);
   const unsigned long long bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     configured.fetch_or(bit, std::memory_order_release);
   }
-  if (use_pairs(p.n_mblk)) {   // CTA pairs with a TMA-multicast B tile
-    static std::atomic<unsigned long long> configured2{0ull};
-    if (!(configured2.load(std::memory_order_acquire) & bit)) {
-      TTS_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured2.fetch_or(bit, std::memory_order_release);
-    }
+  const int mode = pair_mode(p.n_mblk);
+  if (mode != 0) {   // CTA pairs: one cta_group::2 MMA per pair, or cta_group::1 MMAs with a TMA-multicast B tile
     const int units = ((p.n_mblk + 1) / 2) * p.n_nblk * p.split_k;
     const int pairs = sm_count() / 2;
     const int grid = 2 * (units < pairs ? units : pairs);
-    gemm_bf16_pair_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mb, p);
+    if (mode == 2) gemm_bf16_2sm_kernel<BN><<<grid, kThreads, smem2, s>>>(ma, mb, p);
+    else gemm_bf16_pair_kernel<BN><<<grid, kThreads, smem, s>>>(ma, mb, p);
     TTS_CHECK_LAUNCH();
     return 0;
   }

@@ -4,6 +4,7 @@ Every function takes CUDA fp32 tensors, launches on torch's current stream and r
 tensors that own the output memory.  No function here computes anything in torch.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -152,6 +153,9 @@ def attention(q, ldq, k, ldk, v, ldv, batch, n_heads, tq, tk, head_dim, causal, 
 # ---------------------------------------------------------------------------------------------------------------------
 # training path (bf16 operands, fp32 accumulation): include/tts_b200.h "teacher-forced TRAINING path"
 # ---------------------------------------------------------------------------------------------------------------------
+_GEMM_LOG = os.environ.get("TTS_GEMM_LOG")
+
+
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, m=None, n=None, k=None, out=None, out_dtype=torch.bfloat16, bias=None,
               act=ACT_NONE, alpha=1.0, residual=None, drop_p=0.0, seed=0, rng_stream=0, gate=None, gate_scale=1.0,
               taps=1, split_k=1, row_len=None, rows_per_batch=0, valid_rows=0, out_rows_per_batch=0, out_row_offset=0,
@@ -184,5 +188,10 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, m=None, n=None, k=None, out=None,
         g.gate, g.ldg, g.gate_scale = gate.data_ptr(), gate.stride(0), gate_scale
     g.row_len, g.rows_per_batch, g.valid_rows = N.ptr(row_len), rows_per_batch, valid_rows
     g.out_rows_per_batch, g.out_row_offset = out_rows_per_batch, out_row_offset
+    if _GEMM_LOG:   # diagnostics: one line per call, to be joined with an ncu launch list by order
+        with open(_GEMM_LOG, "a") as f:
+            f.write("M=%d N=%d K=%d a_mn=%d b_mn=%d taps=%d split=%d out=%s res=%d drop=%g gate=%d act=%d\n" % (
+                M, Nn, K, a_mn, b_mn, taps, split_k, "bf16" if g.out_bf16 else "f32", residual is not None, drop_p,
+                gate is not None, act))
     N.check(lib.tts_gemm_bf16(C.byref(g), N.stream_ptr(a.device)), "gemm_bf16")
     return out
