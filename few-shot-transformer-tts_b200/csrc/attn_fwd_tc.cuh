@@ -23,9 +23,10 @@ namespace tcf {
 using namespace tc;   // PTX helpers of attn_bwd_tc.cuh
 
 constexpr int BQ = 128, BK = 128, kTiles = 2;
-constexpr int kWarpsF = 2 + 4 * kTiles;   // TMA, MMA issuer, 4 softmax warps per query tile
+constexpr int kWarpsF = 8 * kTiles + 4;   // 8 softmax warps per query tile (warpgroups 0-3), then TMA, MMA issuer, two idle warps
+constexpr int kTmaWarp = 8 * kTiles, kMmaWarp = kTmaWarp + 1;
 constexpr int kThreadsF = kWarpsF * 32;
-constexpr uint32_t oQf = 0, oKf = 65536, oVf = oKf + 2 * 32768, oBarF = oVf + 2 * 32768;
+constexpr uint32_t oQf = 0, oKf = 65536, oVf = oKf + 2 * 32768, oXchF = oVf + 2 * 32768, oBarF = oXchF + kTiles * 2048;
 constexpr size_t kSmemF = oBarF + 256 + 1024;
 constexpr uint32_t cSf = 0, cOf = 256;   // tensor-memory columns: S_w at 128 w, O_w at 256 + 96 w
 
@@ -61,15 +62,41 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
       "r"(v[30]), "r"(v[31]) : "memory");
 }
+// bounded wait with a suspend-time hint: the hardware parks the thread until the phase completes (or ~10 us pass) instead
+// of the thread spinning through try_wait - the helper warps share their schedulers with softmax warps
+__device__ __forceinline__ void wait_bar(uint64_t* bar, unsigned parity) {
+  long long t0 = 0, spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(10000u) : "memory");
+    if (ok) return;
+    if ((++spins & 15) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_err) != 0) return;
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > kTimeout) {
+        atomicExch(&g_err, 1);
+        return;
+      }
+    }
+  }
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // keep bits of the 32 weights (row i, keys 16 jb0 .. 16 jb0 + 31): bit c <-> key 16 jb0 + c.  philox.cuh: call index
 // ((bh n_iblk + i / 16) n_jblk + j / 16) * 32 + (i & 7) * 4 + t covers rows {i & ~8, i | 8} x keys {2t, 2t+1, 2t+8, 2t+9} of the
 // 16 x 16 block; words (x, y) belong to the row with bit 3 clear, (z, w) to the other.  The lane with bit 3 clear computes
 // t = 0, 1, its partner (lane ^ 8) t = 2, 3.
+// two keep bits of one Philox word (two 16-bit lanes): bit 0 <-> low half >= thresh, bit 1 <-> high half >= thresh
+// (half + add carries into bit 16  <=>  half >= thresh, add = 2^16 - thresh)
+__device__ __forceinline__ uint32_t keep2(uint32_t x, uint32_t add) {
+  const uint32_t lo = ((x & 0xffffu) + add) >> 16, hi = ((x >> 16) + add) >> 16;
+  return lo + 2u * hi;
+}
 __device__ __forceinline__ uint32_t keep_bits32(const ParamsF& p, unsigned long long blk_idx, int i, int lane) {
   const bool hi = (lane & 8) != 0;
-  const uint32_t add = 0x10000u - p.drop_thresh;   // half >= thresh  <=>  half + add carries into bit 16
+  const uint32_t add = 0x10000u - p.drop_thresh;
+  const uint32_t sh_mine = hi ? 4u : 0u, sh_got = 4u - sh_mine;   // my calls are t = 2 hi, 2 hi + 1: keys 4 hi .. 4 hi + 3 (+ 8)
   uint32_t bits = 0;
 #pragma unroll
   for (int blk = 0; blk < 2; ++blk) {
@@ -80,15 +107,10 @@ __device__ __forceinline__ uint32_t keep_bits32(const ParamsF& p, unsigned long 
     const uint32_t sx0 = hi ? w0.x : w0.z, sy0 = hi ? w0.y : w0.w, sx1 = hi ? w1.x : w1.z, sy1 = hi ? w1.y : w1.w;
     const uint32_t gx0 = __shfl_xor_sync(0xffffffffu, sx0, 8), gy0 = __shfl_xor_sync(0xffffffffu, sy0, 8);
     const uint32_t gx1 = __shfl_xor_sync(0xffffffffu, sx1, 8), gy1 = __shfl_xor_sync(0xffffffffu, sy1, 8);
-    // calls t = 0..3 in order: X_t = keys (2t, 2t+1), Y_t = keys (2t+8, 2t+9)
-    const uint32_t X[4] = {hi ? gx0 : mx0, hi ? gx1 : mx1, hi ? mx0 : gx0, hi ? mx1 : gx1};
-    const uint32_t Y[4] = {hi ? gy0 : my0, hi ? gy1 : my1, hi ? my0 : gy0, hi ? my1 : gy1};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const uint32_t kx = ((((X[t] & 0xffffu) + add) >> 16) & 1u) | (((((X[t] >> 16) + add) >> 16) & 1u) << 1);
-      const uint32_t ky = ((((Y[t] & 0xffffu) + add) >> 16) & 1u) | (((((Y[t] >> 16) + add) >> 16) & 1u) << 1);
-      bits |= (kx << (16 * blk + 2 * t)) | (ky << (16 * blk + 8 + 2 * t));
-    }
+    // X words cover keys (2t, 2t+1), Y words keys (2t+8, 2t+9): two calls = 4 + 4 keys, placed by one shift per source
+    const uint32_t mine = keep2(mx0, add) | (keep2(mx1, add) << 2) | (keep2(my0, add) << 8) | (keep2(my1, add) << 10);
+    const uint32_t got = keep2(gx0, add) | (keep2(gx1, add) << 2) | (keep2(gy0, add) << 8) | (keep2(gy1, add) << 10);
+    bits |= ((mine << sh_mine) | (got << sh_got)) << (16 * blk);
   }
   return bits;
 }
@@ -123,7 +145,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       mbar_init(&bars->v_full[s], 1);
       mbar_init(&bars->v_empty[s], 1);
       mbar_init(&bars->s_full[s], 1);
-      mbar_init(&bars->p_full[s], 4);
+      mbar_init(&bars->p_full[s], 8);
       mbar_init(&bars->o_done[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,7 +153,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -139,8 +161,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
   __syncthreads();
   fence_after();
   const uint32_t tmem = bars->tmem_base;
+  // the softmax warpgroups keep a row's 128 logits in registers: take the helper warpgroup's share of the register file
 
-  if (warp == 0) {
+  if (warp >= kTmaWarp) {
+    // helper warpgroup (TMA, MMA issuer, two idle warps): ONE setmaxnreg for the whole warpgroup, then the roles
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+  }
+  if (warp == kTmaWarp) {
     // ================= producer: both Q tiles once, then K / V tiles through two-stage rings =================
     if (lane == 0 && n_max > 0) {
       mbar_expect_tx(&bars->q_full, 65536u);
@@ -152,18 +179,18 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       for (int j = 0; j < n_max; ++j) {
         const int s = j & 1;
         const uint32_t par = ((j >> 1) & 1u) ^ 1u;
-        mbar_wait(&bars->k_empty[s], par);
+        wait_bar(&bars->k_empty[s], par);
         mbar_expect_tx(&bars->k_full[s], 32768u);
         tma_2d(sbase + oKf + s * 32768, &tmK, h * DH, b * p.Tk + j * BK, &bars->k_full[s]);
         tma_2d(sbase + oKf + s * 32768 + 16384, &tmK, h * DH + 64, b * p.Tk + j * BK, &bars->k_full[s]);
-        mbar_wait(&bars->v_empty[s], par);
+        wait_bar(&bars->v_empty[s], par);
         mbar_expect_tx(&bars->v_full[s], 32768u);
         tma_2d(sbase + oVf + s * 32768, &tmV, h * DH, b * p.Tk + j * BK, &bars->v_full[s]);
         tma_2d(sbase + oVf + s * 32768 + 16384, &tmV, h * DH + 64, b * p.Tk + j * BK, &bars->v_full[s]);
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer: PV_w(j) as soon as P_w(j) is published, then at once S_w(j+1): a tile's next logits are
     // computed while the OTHER tile's softmax warps work =================
     if (lane == 0 && n_max > 0) {
@@ -180,8 +207,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
         }
         umma_commit(&bars->s_full[w]);
       };
-      mbar_wait(&bars->q_full, 0);
-      mbar_wait(&bars->k_full[0], 0);
+      wait_bar(&bars->q_full, 0);
+      wait_bar(&bars->k_full[0], 0);
       fence_after();
 #pragma unroll
       for (int w = 0; w < kTiles; ++w)
@@ -189,17 +216,17 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       umma_commit(&bars->k_empty[0]);
       for (int j = 0; j < n_max; ++j) {
         const int s = j & 1;
-        mbar_wait(&bars->v_full[s], (j >> 1) & 1u);
-        if (j + 1 < n_max) mbar_wait(&bars->k_full[s ^ 1], ((j + 1) >> 1) & 1u);
+        wait_bar(&bars->v_full[s], (j >> 1) & 1u);
+        if (j + 1 < n_max) wait_bar(&bars->k_full[s ^ 1], ((j + 1) >> 1) & 1u);
         const uint64_t vd = dV0 + (uint64_t)((s * 32768) >> 4);
 #pragma unroll
         for (int w = 0; w < kTiles; ++w) {
           if (j < n_w[w]) {
-            mbar_wait(&bars->p_full[w], j & 1u);
+            wait_bar(&bars->p_full[w], j & 1u);
             fence_after();
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks)   // O_w += P_w V_j
-              umma_bf16_ta(tmem + cOf + w * DH, tmem + cSf + w * BK + ks * 8, vd + (uint64_t)((ks * 2048) >> 4), idO,
+              umma_bf16_ta(tmem + cOf + w * DH, tmem + cSf + w * BK + (ks >> 2) * (BK / 2) + (ks & 3) * 8, vd + (uint64_t)((ks * 2048) >> 4), idO,
                            (j > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&bars->o_done[w]);
             if (j + 1 < n_w[w]) issue_s(w, j + 1);
@@ -210,97 +237,115 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else {
-    // ================= softmax warps: query tile w = (warp - 2) / 4, thread = query row (TMEM lane quadrant = warp % 4) =================
-    const int w = (warp - 2) >> 2, quad = warp & 3;
+  } else if (warp < kTmaWarp) {
+    // ================= softmax warps: query tile w = warp / 8; TWO threads per query row (TMEM lane quadrant = warp % 4): the
+    // thread of half 0 owns keys 0..63 of the tile (and head columns 0..47 of O), its partner in warp + 4 keys 64..127 (columns
+    // 48..95).  Sixteen warps = four per scheduler hide each other's dependent chains (Philox, exp2, tensor-memory round
+    // trips); the halves of a row exchange their maxima through shared memory at one named barrier per tile =================
+    // register pool of the CTA = 96 (launch bound of 640 threads) x 640 = 61440 = 512 x 104 + 128 x 64: an increase beyond the
+    // pool would wait forever
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
+    const int w = warp >> 3, half = (warp >> 2) & 1, quad = warp & 3;
     const int r = quad * 32 + lane, i = q0 + BQ * w + r;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t sS = lane_addr + cSf + w * BK, sO = lane_addr + cOf + w * DH;
+    const uint32_t sS = lane_addr + cSf + w * BK + half * (BK / 2), sP = sS;   // P goes over this thread's OWN consumed S columns
+    const uint32_t sO = lane_addr + cOf + w * DH + half * (DH / 2);
+    float* xch = reinterpret_cast<float*>(smem + oXchF) + w * 512;   // [2 buffers][2 halves][128 rows]
     const int n_it = n_w[w];
     const int n_iblk = (p.Tq + 15) >> 4, n_jblk = (p.Tk + 15) >> 4;
     const unsigned long long blk_row = (bh * (unsigned long long)n_iblk + (unsigned)(i >> 4)) * (unsigned long long)n_jblk;
     const bool drop = p.drop_thresh != 0u;
-    float m = -CUDART_INF_F, l = 0.f;
+    float m = -CUDART_INF_F, l = 0.f;   // l: this thread's half of the row sum
     for (int j = 0; j < n_it; ++j) {
-      const int kb = j * BK;
-      mbar_wait(&bars->s_full[w], j & 1u);
+      const int kb = j * BK + half * (BK / 2);   // first key of this thread's 64
+      wait_bar(&bars->s_full[w], j & 1u);
       fence_after();
       // interior tiles: every key of the tile exists and is visible to every row of the query tile
-      const bool open = kb + BK <= klen && (!p.causal || kb + BK - 1 <= q0 + BQ * w);
-      // ---- pass 1: row maximum of the scaled logits
+      const bool open = j * BK + BK <= klen && (!p.causal || j * BK + BK - 1 <= q0 + BQ * w);
+      // ---- pass 1: maximum of the half row (rolled loops over the two 32-key chunks keep the code small: the unrolled
+      //      version was ~80 KB of instructions and the warps starved on instruction fetch), exchanged with the partner
       float mx = -CUDART_INF_F;
-#pragma unroll
-      for (int c = 0; c < BK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(sS + 32 * c, v);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(sS + 32 * c, sv);
         tmem_wait_ld();
+        float m4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
         if (open) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(sv[e]));
         } else {
+          const int lim = min(klen, p.causal ? i + 1 : klen) - (kb + 32 * c);   // keys kb + 32 c + e with e < lim are visible
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int jj = kb + 32 * c + e;
-            if (jj < klen && (!p.causal || jj <= i)) mx = fmaxf(mx, __uint_as_float(v[e]));
-          }
+          for (int e = 0; e < 32; ++e) m4[e & 3] = fmaxf(m4[e & 3], e < lim ? __uint_as_float(sv[e]) : -CUDART_INF_F);
         }
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
-      mx *= p.scale_log2;   // scale > 0: max(s) scale = max(s scale); -inf stays -inf
-      const float mn = fmaxf(m, mx);
+      float* xb = xch + (j & 1) * 256;
+      xb[half * 128 + r] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + r]) * p.scale_log2;   // scale > 0: max(s) scale = max(s scale); -inf stays -inf
+      // The reference point of the exponentials only moves when the row maximum grew by more than 2^8 (or on the first
+      // tile): p <= 256 is harmless in bf16 / fp32, l and lse = m + log2(l) stay exact, and O_w is rescaled rarely.
+      const bool move = mx > m + 8.f || (m == -CUDART_INF_F && mx > -CUDART_INF_F);
+      const float mn = move ? mx : m;
       const float mu = mn == -CUDART_INF_F ? 0.f : mn;
-      const float corr = ex2(m - mu);   // exp2(-inf) = 0 on the first tile
+      const float corr = move ? ex2(m - mu) : 1.f;   // exp2(-inf) = 0 on the first tile
       m = mn;
       l *= corr;
-      // ---- rescale O_w when a row's maximum moved (warp-uniform decision: the tensor-memory accesses are collective)
-      if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
-        mbar_wait(&bars->o_done[w], (j - 1) & 1u);   // PV_w(j-1) has been added
+      // ---- rescale this thread's 48 columns of O_w when a row's reference moved (warp-uniform decision: the tensor-memory
+      //      accesses are collective; both halves of a row see the same maxima and decide alike)
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        wait_bar(&bars->o_done[w], (j - 1) & 1u);   // PV_w(j-1) has been added
         fence_after();
-#pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(sO + 32 * c, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
-          tmem_st32(sO + 32 * c, v);
-        }
-      }
-      // ---- pass 2: p = exp2(s scale - max), row sum, dropout, bf16 pairs back into tensor memory over the consumed S columns
-#pragma unroll
-      for (int c = 0; c < BK / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(sS + 32 * c, v);
+        uint32_t ov[32], ow[16];
+        tmem_ld32(sO, ov);
+        tmem_ld16(sO + 32, ow);
         tmem_wait_ld();
-        float pe[32];
-        if (open) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) pe[e] = ex2(fmaf(__uint_as_float(v[e]), p.scale_log2, -mu));
-        } else {
+        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * corr);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int jj = kb + 32 * c + e;
-            pe[e] = (jj < klen && (!p.causal || jj <= i)) ? ex2(fmaf(__uint_as_float(v[e]), p.scale_log2, -mu)) : 0.f;
-          }
-        }
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          s0 += pe[e];
-          s1 += pe[e + 1];
-        }
-        l += s0 + s1;
-        if (drop) {
-          const uint32_t bits = keep_bits32(p, blk_row + (unsigned)((kb >> 4) + 2 * c), i, lane);
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (!((bits >> e) & 1u)) pe[e] = 0.f;
+        for (int e = 0; e < 16; ++e) ow[e] = __float_as_uint(__uint_as_float(ow[e]) * corr);
+        tmem_st32(sO, ov);
+        tmem_st16(sO + 32, ow);
+      }
+      // ---- pass 2: p = exp2(s scale - reference), row sum, dropout, bf16 pairs back into tensor memory over the S columns
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(sS + 32 * c, sv);
+        uint32_t bits = 0xffffffffu;
+        if (drop) {   // the Philox calls run while the logits travel
+          bits = keep_bits32(p, blk_row + (unsigned)((kb >> 4) + 2 * c), i, lane);
           const int kw = (kb >> 5) + c;
           if (p.keep_mask != nullptr && i < p.Tq && kw < p.n_kw) p.keep_mask[(bh * p.n_kw + kw) * p.Tq + i] = bits;
         }
-        uint32_t pw[16];
+        tmem_wait_ld();
+        if (!open) {
+          const int lim = min(klen, p.causal ? i + 1 : klen) - (kb + 32 * c);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) pw[e] = pack_bf16(pe[2 * e], pe[2 * e + 1]);
-        tmem_st16(sS + 16 * c, pw);   // words 16 c .. 16 c + 15 = keys 32 c .. 32 c + 31: k-steps 2 c, 2 c + 1 of P_w V_j
+          for (int e = 0; e < 32; ++e)
+            if (e >= lim) sv[e] = 0xff800000u;   // -inf: exp2 gives 0
+        }
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {   // 16 weights at a time: few live registers
+          float pe[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pe[e] = ex2(fmaf(__uint_as_float(sv[16 * hc + e]), p.scale_log2, -mu));
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 16; ++e) s4[e & 3] += pe[e];
+          l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          if (drop) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (!((bits >> (16 * hc + e)) & 1u)) pe[e] = 0.f;
+          }
+          uint32_t pw[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pw[e] = pack_bf16(pe[2 * e], pe[2 * e + 1]);
+          tmem_st8(sP + 16 * c + 8 * hc, pw);   // columns 64 half + 16 c + 8 hc ..: k-step 4 half + 2 c + hc of P_w V_j
+        }
       }
       tmem_wait_st();
       fence_before();
@@ -308,39 +353,43 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       if (lane == 0) mbar_arrive(&bars->p_full[w]);
     }
     // ---- epilogue: O_w / l (and the 1 / (1 - p) of the dropout) -> bf16 context, log2-domain log-sum-exp
+    {
+      float* xb = xch + (n_it & 1) * 256;   // the buffer the last tile did not use
+      xb[half * 128 + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+      l += xb[(half ^ 1) * 128 + r];
+    }
     if (n_it > 0) {
-      mbar_wait(&bars->o_done[w], (n_it - 1) & 1u);
+      wait_bar(&bars->o_done[w], (n_it - 1) & 1u);
       fence_after();
     }
     const float inv = l > 0.f ? p.drop_scale / l : 0.f;
-    __nv_bfloat16* op = p.o + ((long long)b * p.Tq + i) * p.ldo + h * DH;
+    __nv_bfloat16* op = p.o + ((long long)b * p.Tq + i) * p.ldo + h * DH + half * (DH / 2);
+    uint32_t v[48];
+    if (n_it > 0) {
+      tmem_ld32(sO, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld16(sO + 32, *reinterpret_cast<uint32_t(*)[16]>(&v[32]));
+      tmem_wait_ld();
+    } else {
 #pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
-      uint32_t v[32];
-      if (n_it > 0) {
-        tmem_ld32(sO + 32 * c, v);
-        tmem_wait_ld();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0u;
-      }
-      if (i < p.Tq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + 32 * c + 8 * q) = o;
-        }
-      }
+      for (int e = 0; e < 48; ++e) v[e] = 0u;
     }
-    if (i < p.Tq && p.lse != nullptr) p.lse[bh * p.Tq + i] = m + log2f(l);
+    if (i < p.Tq) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+        *reinterpret_cast<uint4*>(op + 8 * q) = o;
+      }
+      if (half == 0 && p.lse != nullptr) p.lse[bh * p.Tq + i] = m + log2f(l);
+    }
   }
   fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace tcf

@@ -854,7 +854,7 @@ extern "C" int tts_attn_train_fwd(const TtsAttnTrain* t, void* stream) {
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // head_dim 96 (the decoder's self- and cross-attention): the tcgen05 kernel (TTS_ATTN_FWD_TC=0: the mma.sync kernel)
-  static const bool tc_on = getenv("TTS_ATTN_FWD_TC") != nullptr && atoi(getenv("TTS_ATTN_FWD_TC")) != 0;   // opt-in until verified on hardware
+  static const bool tc_on = !(getenv("TTS_ATTN_FWD_TC") != nullptr && atoi(getenv("TTS_ATTN_FWD_TC")) == 0);
   if (tc_on && t->head_dim == 96) return attn::launch_fwd_tc(a, s);
   switch (t->head_dim) {
     case 32: return attn::launch_fwd<32>(a, s);
