@@ -152,6 +152,20 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    if (n_max > 0) {
+      // Q and the first K / V tiles are requested before the CTA-wide sync: their latency overlaps the tensor-memory allocation
+      mbar_expect_tx(&bars->q_full, 65536u);
+      mbar_expect_tx(&bars->k_full[0], 32768u);
+      tma_2d(sbase + oQf, &tmQ, h * DH, b * p.Tq + q0, &bars->q_full);
+      tma_2d(sbase + oQf + 16384, &tmQ, h * DH + 64, b * p.Tq + q0, &bars->q_full);
+      tma_2d(sbase + oKf, &tmK, h * DH, b * p.Tk, &bars->k_full[0]);
+      tma_2d(sbase + oKf + 16384, &tmK, h * DH + 64, b * p.Tk, &bars->k_full[0]);
+      tma_2d(sbase + oQf + 32768, &tmQ, h * DH, b * p.Tq + q0 + BQ, &bars->q_full);
+      tma_2d(sbase + oQf + 32768 + 16384, &tmQ, h * DH + 64, b * p.Tq + q0 + BQ, &bars->q_full);
+      mbar_expect_tx(&bars->v_full[0], 32768u);
+      tma_2d(sbase + oVf, &tmV, h * DH, b * p.Tk, &bars->v_full[0]);
+      tma_2d(sbase + oVf + 16384, &tmV, h * DH + 64, b * p.Tk, &bars->v_full[0]);
+    }
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
@@ -170,13 +184,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
   if (warp == kTmaWarp) {
     // ================= producer: both Q tiles once, then K / V tiles through two-stage rings =================
     if (lane == 0 && n_max > 0) {
-      mbar_expect_tx(&bars->q_full, 65536u);
-#pragma unroll
-      for (int w = 0; w < kTiles; ++w) {
-        tma_2d(sbase + oQf + w * 32768, &tmQ, h * DH, b * p.Tq + q0 + BQ * w, &bars->q_full);
-        tma_2d(sbase + oQf + w * 32768 + 16384, &tmQ, h * DH + 64, b * p.Tq + q0 + BQ * w, &bars->q_full);
-      }
-      for (int j = 0; j < n_max; ++j) {
+      // tile 0 was requested in the prologue
+      for (int j = 1; j < n_max; ++j) {
         const int s = j & 1;
         const uint32_t par = ((j >> 1) & 1u) ^ 1u;
         wait_bar(&bars->k_empty[s], par);
@@ -410,6 +419,11 @@ static int launch_fwd_tc(const Args& a, cudaStream_t s) {
   p.key_len = a.key_len; p.lse = a.lse; p.keep_mask = a.keep_mask; p.o = a.o; p.ldo = a.ldo;
   static bool attr = false;
   if (!attr) {
+    // setmaxnreg redistributes the registers the CTA was launched with: 16 softmax warps x 104 + 4 helper warps x 64
+    cudaFuncAttributes fa;
+    TTS_CHECK_CUDA(cudaFuncGetAttributes(&fa, tcf::attn_fwd_tc_kernel));
+    TTS_REQUIRE((long long)fa.numRegs * tcf::kThreadsF >= 512LL * 104 + 128LL * 64,
+                "attn_fwd_tc: built with %d registers per thread, the kernel's setmaxnreg budget needs 96", fa.numRegs);
     TTS_CHECK_CUDA(cudaFuncSetAttribute(tcf::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcf::kSmemF));
     attr = true;
   }

@@ -444,12 +444,14 @@ __device__ __forceinline__ void gemm_bf16_body(const CUtensorMap& tmA, const CUt
         if (p.drop_thresh != 0u) {   // nn.Dropout on the product (before the residual add: modules.py:132,138,141)
           const unsigned long long e0 = (unsigned long long)orow * (unsigned long long)p.N + (unsigned long long)n;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 rw = dropout_words_linear(p.seed, p.stream, (e0 >> 2) + q);
-            x[4 * q + 0] = rw.x >= p.drop_thresh ? x[4 * q + 0] * p.drop_scale : 0.f;
-            x[4 * q + 1] = rw.y >= p.drop_thresh ? x[4 * q + 1] * p.drop_scale : 0.f;
-            x[4 * q + 2] = rw.z >= p.drop_thresh ? x[4 * q + 2] * p.drop_scale : 0.f;
-            x[4 * q + 3] = rw.w >= p.drop_thresh ? x[4 * q + 3] * p.drop_scale : 0.f;
+          for (int q = 0; q < 4; ++q) {   // one Philox call per 8 outputs: 16-bit lanes (philox.cuh)
+            const uint4 rw = dropout_words_linear(p.seed, p.stream, (e0 >> 3) + q);
+            const uint32_t ws[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              x[8 * q + 2 * e] = (ws[e] & 0xffffu) >= p.drop_thresh ? x[8 * q + 2 * e] * p.drop_scale : 0.f;
+              x[8 * q + 2 * e + 1] = (ws[e] >> 16) >= p.drop_thresh ? x[8 * q + 2 * e + 1] * p.drop_scale : 0.f;
+            }
           }
         }
         if (p.residual != nullptr) {
@@ -672,8 +674,8 @@ extern "C" int tts_gemm_bf16(const TtsGemmBf16* g, void* stream) {
   p.bias = g->bias; p.act = g->act; p.alpha = g->alpha == 0.f ? 1.f : g->alpha;
   p.residual = g->residual; p.ldr = g->ldr;
   if (g->drop_p > 0.f) {
-    TTS_REQUIRE(g->drop_p < 1.f && g->N % 4 == 0, "gemm_bf16: dropout needs p < 1 and N %% 4 == 0");
-    p.drop_thresh = drop_threshold(g->drop_p);
+    TTS_REQUIRE(g->drop_p < 1.f && g->N % 8 == 0, "gemm_bf16: dropout needs p < 1 and N %% 8 == 0");
+    p.drop_thresh = drop_threshold16(g->drop_p);
     p.drop_scale = 1.f / (1.f - g->drop_p);
     p.seed = g->seed; p.stream = g->rng_stream;
   }

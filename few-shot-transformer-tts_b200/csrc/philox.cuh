@@ -31,9 +31,16 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
   return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
 }
 
-// Row-major tensors (GEMM epilogues, element-wise kernels): the four elements 4*g .. 4*g+3 share one call.
+// Row-major tensors of the TRAINING path (GEMM epilogues, element-wise kernels): the eight elements 8*g .. 8*g+7 share one
+// call, 16 random bits each: element e uses half (e & 1) of word (e & 7) >> 1 and is KEPT iff its 16 bits >= p * 65536
+// (drop_threshold16).  (The decode kernel's train()-mode dropout, pipelined.cu drop1, keeps 32-bit lanes: four elements
+// per call.)
 __device__ __forceinline__ uint4 dropout_words_linear(unsigned long long seed, uint32_t stream, unsigned long long group) {
   return philox4x32(seed, group, stream);
+}
+__device__ __forceinline__ uint32_t dropout_lane16(const uint4& w, int lane) {   // lane = e & 7
+  const uint32_t word = (lane >> 1) == 0 ? w.x : ((lane >> 1) == 1 ? w.y : ((lane >> 1) == 2 ? w.z : w.w));
+  return (lane & 1) ? (word >> 16) : (word & 0xffffu);
 }
 
 // Attention weights [bh][i][j]: one call covers the 2 x 4 elements {i0, i0+8} x {j0, j0+1, j0+8, j0+9} of a 16 x 16 block

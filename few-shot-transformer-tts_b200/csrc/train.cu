@@ -29,16 +29,15 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {   // blockDim.x
   return t;
 }
 __device__ __forceinline__ bool keep1(unsigned long long seed, uint32_t stream, unsigned long long e, uint32_t thresh) {
-  const uint4 w = philox4x32(seed, e >> 2, stream);
-  const uint32_t r = (e & 3) == 0 ? w.x : ((e & 3) == 1 ? w.y : ((e & 3) == 2 ? w.z : w.w));
-  return r >= thresh;
+  const uint4 w = dropout_words_linear(seed, stream, e >> 3);
+  return dropout_lane16(w, (int)(e & 7)) >= thresh;
 }
 struct Drop {
   uint32_t thresh; float scale; unsigned long long seed; uint32_t stream;
 };
 static Drop make_drop(float p, unsigned long long seed, uint32_t stream) {
   Drop d;
-  d.thresh = p > 0.f ? drop_threshold(p) : 0u;
+  d.thresh = p > 0.f ? drop_threshold16(p) : 0u;
   d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   d.seed = seed;
   d.stream = stream;
@@ -47,11 +46,12 @@ static Drop make_drop(float p, unsigned long long seed, uint32_t stream) {
 // 4 consecutive elements starting at e (e % 4 == 0)
 __device__ __forceinline__ void drop4(const Drop& d, unsigned long long e, float4& v) {
   if (d.thresh == 0u) return;
-  const uint4 w = philox4x32(d.seed, e >> 2, d.stream);
-  v.x = w.x >= d.thresh ? v.x * d.scale : 0.f;
-  v.y = w.y >= d.thresh ? v.y * d.scale : 0.f;
-  v.z = w.z >= d.thresh ? v.z * d.scale : 0.f;
-  v.w = w.w >= d.thresh ? v.w * d.scale : 0.f;
+  const uint4 w = dropout_words_linear(d.seed, d.stream, e >> 3);   // 16-bit lanes: this half of the call's eight
+  const uint32_t a = (e & 4) ? w.z : w.x, b = (e & 4) ? w.w : w.y;
+  v.x = (a & 0xffffu) >= d.thresh ? v.x * d.scale : 0.f;
+  v.y = (a >> 16) >= d.thresh ? v.y * d.scale : 0.f;
+  v.z = (b & 0xffffu) >= d.thresh ? v.z * d.scale : 0.f;
+  v.w = (b >> 16) >= d.thresh ? v.w * d.scale : 0.f;
 }
 __device__ __forceinline__ uint2 pack4(float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);

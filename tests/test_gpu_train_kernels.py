@@ -143,9 +143,11 @@ def keep_linear(seed, stream, rows, cols, p):
     """keep mask [rows, cols] of a row-major tensor (GEMM epilogues, element-wise kernels)."""
     import numpy as np
     e = np.arange(rows * cols, dtype=np.uint64)
-    w = _philox(seed, e >> np.uint64(2), stream)
-    r = np.take_along_axis(w, (e & np.uint64(3)).astype(np.int64)[:, None], axis=1)[:, 0]
-    return torch.from_numpy((r >= np.uint64(_thresh(p))).reshape(rows, cols))
+    w = _philox(seed, e >> np.uint64(3), stream)   # eight elements per call, 16-bit lanes (philox.cuh)
+    lane = (e & np.uint64(7)).astype(np.int64)
+    word = np.take_along_axis(w, (lane >> 1)[:, None], axis=1)[:, 0]
+    r = np.where(lane & 1, word >> np.uint64(16), word & np.uint64(0xffff))
+    return torch.from_numpy((r >= np.uint64(min(int(p * 65536.0), 65535))).reshape(rows, cols))
 
 
 def keep_attn(seed, stream, BH, Tq, Tk, p):
