@@ -274,8 +274,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       // ---- pass 1: maximum of the half row (rolled loops over the two 32-key chunks keep the code small: the unrolled
       //      version was ~80 KB of instructions and the warps starved on instruction fetch), exchanged with the partner
       float mx = -CUDART_INF_F;
+      // keys this WARP's 32 rows can see at all (causal diagonal tiles / the last key tile): chunks past it are skipped
+      const int warp_lim = min(klen, p.causal ? q0 + BQ * w + quad * 32 + 32 : klen);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
+        if (kb + 32 * c >= warp_lim) break;   // warp-uniform
         uint32_t sv[32];
         tmem_ld32(sS + 32 * c, sv);
         tmem_wait_ld();
@@ -321,6 +324,13 @@ __global__ void __launch_bounds__(kThreadsF, 1) attn_fwd_tc_kernel(const __grid_
       // ---- pass 2: p = exp2(s scale - reference), row sum, dropout, bf16 pairs back into tensor memory over the S columns
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
+        if (kb + 32 * c >= warp_lim) {   // nothing visible to any row of the warp: P = 0 (no Philox, no exp2; the cached keep
+          uint32_t z[16];               // bits of masked weights are never read)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) z[e] = 0u;
+          tmem_st16(sP + 16 * c, z);
+          continue;
+        }
         uint32_t sv[32];
         tmem_ld32(sS + 32 * c, sv);
         uint32_t bits = 0xffffffffu;
