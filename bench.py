@@ -518,6 +518,26 @@ def run_train_step(args, dev, rank, world):
     m.to(dev).train()
     B, S, T = args.tf_batch, args.text_len, args.frames
     host = O.synth_batch(cfg, batch=B, text_len=S, n_frames=T, seed=100 + rank)
+    cfg4 = getattr(args, "cfg4", False)
+    if cfg4:
+        # BASELINE configs[3]: 38-language / 128-speaker mixed RAGGED batch, global 128 = 16 per GPU at 8 GPUs: text lengths
+        # U[32, 258], mel lengths U[240, 800], padded to the longest (dataloader.py:419-439), one language / speaker per row
+        B, S, T = 16, 258, 800
+        g = torch.Generator().manual_seed(400 + rank)
+        host = O.synth_batch(cfg, batch=B, text_len=S, n_frames=T, seed=100 + rank)
+        in_len = torch.randint(32, S + 1, (B,), generator=g)
+        tg_len = torch.randint(240, T + 1, (B,), generator=g)
+        in_len[0], in_len[1], tg_len[0], tg_len[1] = 32, S, T, 240
+        pos = torch.arange(S)[None, :]
+        ids = host["inputs"]
+        ids = torch.where(pos == (in_len[:, None] - 1), torch.ones_like(ids), ids)
+        host["inputs"] = torch.where(pos < in_len[:, None], ids, torch.zeros_like(ids))
+        host["mel_targets"] = (host["mel_targets"] * (torch.arange(T)[None, :, None] < tg_len[:, None, None])).contiguous()
+        host["input_lengths"], host["target_lengths"] = in_len, tg_len
+        host["input_spk_ids"] = (torch.arange(B) * 37 + 5 + 16 * rank) % 128
+        lang = torch.zeros(B, cfg.max_num_language)
+        lang[torch.arange(B), (torch.arange(B) * 7 + rank) % 38] = 1.0
+        host["input_language_vecs"] = lang
     keys = ("inputs", "input_lengths", "mel_targets", "target_lengths", "input_spk_ids", "input_language_vecs")
     # the feeder's side of the boundary (dataloader.py:419-439): pageable host arrays, the language as an id; the stager
     # (tts_b200/staging.py) moves them through pinned arenas on a copy stream and expands the one-hot on the device
@@ -589,18 +609,24 @@ def run_train_step(args, dev, rank, world):
     host_issue_ms = 1e3 * (time.perf_counter() - t_h0)
     barrier()
     flops = train_flops(S, T, B)
+    valid_frames = B * T
+    if cfg4:   # algorithmic FLOPs of the VALID tokens / frames (the padded rows a kernel also touches earn nothing)
+        flops = sum(train_flops(int(s_), int(t_), 1) for s_, t_ in zip(host["input_lengths"], host["target_lengths"]))
+        valid_frames = int(host["target_lengths"].sum())
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     ar = [a.elapsed_time(b) for a, b in ar_ms]
     n_params = sum(p.numel() for p in m.parameters())
     return {"metric": "teacher-forced train step ms", "value": ms, "unit": "ms", "higher_is_better": False, "n_gpus": world,
             "steps": args.steps, "scaling": "weak", "dtype": "bf16 (fp32 accumulate, fp32 master weights and optimizer state)",
-            "config": {"workload": "teacher-forced train step, per-GPU batch=%d x %d mel frames, %d text tokens, dropout on "
-                                   "(BASELINE.json configs[2])" % (B, T, S), "global_batch": B * world,
+            "config": {"workload": ("multilingual mixed ragged train step, per-GPU batch=%d (38 languages, 128 speakers, text U[32,%d], "
+                                    "mel U[240,%d], padded to the longest), dropout on (BASELINE.json configs[3])" % (B, S, T)) if cfg4 else
+                                   ("teacher-forced train step, per-GPU batch=%d x %d mel frames, %d text tokens, dropout on "
+                                    "(BASELINE.json configs[2])" % (B, T, S)), "global_batch": B * world,
                        "parallelism": "dp%d (%s)" % (world, "single GPU" if world == 1 else
                                                      ("DistributedDataParallel" if ddp is not None else
                                                       "bucketed NCCL all-reduce overlapped with backward, 64 MB buckets"))},
-            "frames_per_s": B * T * world / (ms / 1e3), "loss": float(loss_host),
+            "frames_per_s": valid_frames * world / (ms / 1e3), "loss": float(loss_host),
             "h2d_bytes_per_step": stager.h2d_bytes // (max(args.warmup, 3) + args.steps + 1), "d2h_bytes_per_step": 4,
             "gpu_launches_per_step": launches, "host_issue_ms_per_step": host_issue_ms,
             "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
@@ -697,6 +723,7 @@ def main():
     ap.add_argument("--module-api-frames", type=int, default=300)
     ap.add_argument("--dp", default="buckets", choices=["buckets", "buckets-late", "ddp"], help="gradient exchange of the train step at N > 1")
     ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")
+    ap.add_argument("--cfg4", action="store_true", help="--workload train on the BASELINE configs[3] share: ragged mixed-language batch of 16 per GPU")
     args = ap.parse_args()
     if args.workload == "forward":
         return run_forward(args)
