@@ -126,7 +126,7 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // default semantics (.release at CTA scope): the explicit .release.cluster form compiled to an ERRBAR that held the warp
-  // until its global stores of the tile had drained (16 % of the kernel's stall samples, profiles/r2_gemm_relu_drop_*)
+  // until its global stores of the tile had drained (16 % of the kernel's stall samples, profiles/r2_gemm_relu_drop_sass_top.txt)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
