@@ -51,6 +51,15 @@ class AttnTrain(C.Structure):
                 ("lddv", C.c_int64), ("dq_acc", C.c_void_p), ("keep_mask", C.c_void_p)]
 
 
+class GriffinLim(C.Structure):
+    _fields_ = [("mel", C.c_void_p), ("lengths", C.c_void_p), ("inv_basis_t", C.c_void_p), ("window", C.c_void_p),
+                ("twiddle", C.c_void_p), ("batch", C.c_int32), ("frames_max", C.c_int32), ("min_frames", C.c_int32),
+                ("n_mels", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32), ("win_length", C.c_int32),
+                ("n_iter", C.c_int32), ("max_abs", C.c_float), ("max_db", C.c_float), ("ref_db", C.c_float),
+                ("power", C.c_float), ("preemphasis", C.c_float), ("mag", C.c_void_p), ("frames", C.c_void_p),
+                ("y", C.c_void_p), ("ldy", C.c_int64), ("wav", C.c_void_p), ("ldw", C.c_int64)]
+
+
 class DecLayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln_self_g", "ln_self_b", "w_qkv", "w_self_out", "ln_cross_g", "ln_cross_b", "w_cross_q", "w_cross_kv",
@@ -86,6 +95,7 @@ _EXPORTS = {
     "tts_gemm_use_tensor_cores": (C.c_int, [C.c_int]),
     "tts_gemm_bf16": (C.c_int, [C.POINTER(GemmBf16), C.c_void_p]),
     "tts_gemm_bf16_status": (C.c_int, []),
+    "tts_griffin_lim": (C.c_int, [C.POINTER(GriffinLim), C.c_void_p]),
     "tts_attn_train_fwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
     "tts_attn_train_bwd": (C.c_int, [C.POINTER(AttnTrain), C.c_void_p]),
     "tts_attn_keep_words": (C.c_int32, [C.c_int32]),

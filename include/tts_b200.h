@@ -243,6 +243,32 @@ int tts_sumsq_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, 
 int tts_adam_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, float lr, float beta1, float beta2,
                    float eps, int64_t step, float reg_weight, float grad_scale, void* stream);
 
+/* ---- mel -> waveform ------------------------------------------------------ */
+
+/* utils/audio.py:53-99 of the reference: mel2wav = de-normalise, dB -> amplitude, mel_to_linear (pseudo-inverse of
+ * librosa.filters.mel, clamp 1e-10), ^power, griffin_lim (n_iter x {librosa.istft, librosa.stft, phase of the estimate on
+ * the target magnitude} + a last istft; librosa 0.6.0: Hann window of win_length centred in n_fft, centre = True with
+ * reflect padding, window-sum-of-squares normalisation), scipy.signal.lfilter([1], [1, -preemphasis]).  A whole batch at
+ * once; utterance b has lengths[b] frames and hop_length * (lengths[b] - 1) output samples.  Host-computed constants:
+ * inv_basis_t [n_mels][n_fft/2+1] = pinv(mel basis) transposed, window [win_length] (periodic Hann), twiddle [n_fft/2]
+ * complex = exp(-2 pi i k / n_fft).  Scratch: mag [batch][frames_max][n_fft/2+1], frames [batch][frames_max][win_length],
+ * y [batch][ldy]; output wav [batch][ldw].  Built for n_fft 2048 / hop 200 / win 800 (hyperparams.py:7-15). */
+typedef struct TtsGriffinLim {
+  const float* mel;           /* [batch][frames_max][n_mels], the model's normalised mel (synthesize.py:82) */
+  const int32_t* lengths;     /* [batch] frames per utterance, each >= 7 */
+  const float* inv_basis_t;
+  const float* window;
+  const float* twiddle;       /* [n_fft/2][2] (re, im) */
+  int32_t batch, frames_max, min_frames, n_mels;
+  int32_t n_fft, hop_length, win_length, n_iter;
+  float max_abs, max_db, ref_db, power, preemphasis;
+  float* mag;
+  float* frames;
+  float* y; int64_t ldy;
+  float* wav; int64_t ldw;
+} TtsGriffinLim;
+int tts_griffin_lim(const TtsGriffinLim* g, void* stream);
+
 /* ---- autoregressive decode (the hot path) ------------------------------------------------ */
 
 typedef struct TtsDecLayerWeights {
