@@ -216,6 +216,30 @@ def cpu_reference_sample(batch_size, text_len, horizon, repeats=1):
     return frames / min(times), times, frames
 
 
+def run_vocoder(args, dev):
+    """utils/audio.py:60-79 (mel2wav, one utterance per CPU worker in synthesize.py:82,99) as ONE batched GPU call of
+    tts_b200.vocoder on the shape the synthesis produces (B utterances x `frames` mel frames, synthetic mels in the model's range)."""
+    from tts_b200 import vocoder as V
+    g = torch.Generator().manual_seed(7)
+    mels = (torch.randn(args.batch, args.frames, 80, generator=g) * 0.6 + torch.linspace(1.5, -2.5, 80)).clamp_(-4, 4).to(dev)
+    eng = V.GriffinLim(dev)
+    lens = [args.frames] * args.batch
+    for _ in range(2):
+        eng(mels, lens)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        eng(mels, lens)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 3
+    audio_s = args.batch * 200 * (args.frames - 1) / 16000.0
+    return {"stage": "mel2wav: Griffin-Lim, 60 iterations, n_fft 2048 / hop 200 / win 800 (hyperparams.py:7-18)", "ms": ms,
+            "frames_per_s": args.batch * args.frames / (ms / 1e3), "audio_seconds": audio_s,
+            "realtime_factor": audio_s / (ms / 1e3), "gpu_launches": 2 * 61 + 2}
+
+
 def run_module_api_loop(args, dev, params, dev_batch):
     """frames/s of the reference's own loop shape (synthesize.py:35-56) driving transformer.tacotron.Tacotron: encoder once,
     then per frame torch.cat + Decoder.forward(leave_one=True) + stop bookkeeping + `torch.all(finished)` (a host sync)."""
@@ -452,6 +476,13 @@ def run_ours(args):
             module_api = run_module_api_loop(args, dev, params, dev_batch)
         except Exception as exc:
             module_api = {"error": repr(exc)[:300]}
+    # ---- the stage after the path: mel -> waveform, 60 Griffin-Lim iterations on the synthesised batch shape
+    vocoder = None
+    if not args.no_vocoder and rank == 0:
+        try:
+            vocoder = run_vocoder(args, dev)
+        except Exception as exc:
+            vocoder = {"error": repr(exc)[:300]}
     train = None
     if not args.no_train:
         try:
@@ -480,7 +511,7 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager, "decode_impl": args.decode_impl, "module_api_loop": module_api,
-                "train_step": train}
+                "train_step": train, "mel2wav": vocoder}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
@@ -720,6 +751,7 @@ def main():
                          "training step (BASELINE metric 2); forward = teacher-forced forward pass only")
     ap.add_argument("--no-train", action="store_true", help="skip the train_step measurement of the default run")
     ap.add_argument("--no-module-api", action="store_true", help="skip the per-frame module-API loop measurement")
+    ap.add_argument("--no-vocoder", action="store_true", help="skip the mel -> waveform (Griffin-Lim) measurement")
     ap.add_argument("--module-api-frames", type=int, default=300)
     ap.add_argument("--dp", default="buckets", choices=["buckets", "buckets-late", "ddp"], help="gradient exchange of the train step at N > 1")
     ap.add_argument("--tf-batch", type=int, default=64, help="batch of the --workload forward run")

@@ -7,9 +7,9 @@
 //                       the complex spectrogram never leaves shared memory (the reference materialises it twice per iteration)
 //   gl_ola_kernel       overlap-add of the windowed frames, normalised by the window's sum of squares, centre trimmed
 //                       (librosa.istft, librosa.filters.window_sumsquare); a gather over <= 4 frames per sample: deterministic
-//   deemphasis_kernel   scipy.signal.lfilter([1], [1, -preemphasis])                                 (audio.py:75-76)
-// FFT: radix-2 decimation-in-time in shared memory (bit-reversed load, 11 stages of 1024 butterflies, twiddles from a
-// host-computed fp64 -> fp32 table), 256 threads per frame.  fp32 throughout (the reference keeps the waveform in float32 and
+//   deemphasis_kernel   scipy.signal.lfilter([1], [1, -preemphasis]) as a blocked scan of affine maps   (audio.py:75-76)
+// FFT: each 2048-point real transform as a 1024-point complex Stockham radix-4 FFT in shared memory (five passes, one butterfly
+// per thread and pass, 256 threads per frame, twiddles from a host-computed fp64 -> fp32 table) plus the split / merge step.  fp32 throughout (the reference keeps the waveform in float32 and
 // the estimate in complex64; its float64 magnitudes are rounded once here).
 #include <stdlib.h>
 #include <string.h>
@@ -22,28 +22,39 @@ namespace voc {
 constexpr int kFft = 2048, kBins = kFft / 2 + 1, kHop = 200, kWin = 800, kLo = (kFft - kWin) / 2, kHi = kLo + kWin;
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ int brev11(int i) { return (int)(__brev((unsigned)i) >> 21); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
 
-// buf: 2048 complex values in BIT-REVERSED order -> natural-order DFT (forward: e^{-2 pi i jk / N}; inverse: conjugate twiddles,
-// unscaled).  tw[k] = e^{-2 pi i k / 2048}, k < 1024.  Ends with a CTA-wide sync.
+// 1024-point complex DFT, Stockham autosort, radix 4: five passes, one butterfly per thread and pass (256 threads), ping-pong
+// between two shared-memory buffers, no bit reversal.  Pass with sub-transform size Ns: thread j reads a[j + 256 r], multiplies by
+// e^{-+ 2 pi i r k / (4 Ns)} (k = j mod Ns; tw = e^{-2 pi i m / 2048}, m = r k 512 / Ns < 1536), radix-4 butterfly, writes
+// b[4 (j - k) + k + r Ns].  INVERSE: conjugate twiddles, unscaled.  Returns the buffer that holds the result (natural order).
 template <bool INVERSE>
-__device__ __forceinline__ void fft2048(float2* buf, const float2* tw) {
-#pragma unroll 1
-  for (int s = 0; s < 11; ++s) {
-    const int half = 1 << s;
+__device__ __forceinline__ float2* fft1024(float2* a, float2* b, const float2* tw) {
+  const int j = threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < kFft / 2 / kThreads; ++q) {
-      const int j = threadIdx.x + q * kThreads;
-      const int pos = j & (half - 1), i0 = ((j >> s) << (s + 1)) + pos, i1 = i0 + half;
-      float2 w = tw[pos << (10 - s)];
-      if (INVERSE) w.y = -w.y;
-      const float2 a = buf[i0], b = buf[i1];
-      const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-      buf[i0] = make_float2(a.x + t.x, a.y + t.y);
-      buf[i1] = make_float2(a.x - t.x, a.y - t.y);
+  for (int ls = 0; ls < 10; ls += 2) {
+    const int Ns = 1 << ls, k = j & (Ns - 1), m = k << (9 - ls);
+    const float2 v0 = a[j];
+    float2 v1 = a[j + 256], v2 = a[j + 512], v3 = a[j + 768];
+    if (ls > 0) {
+      v1 = INVERSE ? cmulc(v1, tw[m]) : cmul(v1, tw[m]);
+      v2 = INVERSE ? cmulc(v2, tw[2 * m]) : cmul(v2, tw[2 * m]);
+      v3 = INVERSE ? cmulc(v3, tw[3 * m]) : cmul(v3, tw[3 * m]);
     }
+    const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+    const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const float2 t3 = INVERSE ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);   // (v1 - v3) * (+-i)
+    float2* o = b + ((j - k) << 2) + k;
+    o[0] = make_float2(t0.x + t2.x, t0.y + t2.y);
+    o[Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
+    o[2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
+    o[3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
     __syncthreads();
+    float2* t = a; a = b; b = t;
   }
+  return a;
 }
 
 // mag[b][t][k] = max(1e-10, sum_m inv_t[m][k] * amp[m]) ^ power,  amp = 10 ^ (0.05 * (clip((mel + max_abs) / (2 max_abs), 0, 1) * max_db - max_db + ref_db))
@@ -70,71 +81,102 @@ __global__ void __launch_bounds__(kThreads) mel_to_mag_kernel(const float* __res
 
 // One Griffin-Lim half-iteration of one frame.  FIRST: X = magnitude (zero phase).  Otherwise X = magnitude * E / max(1e-8, |E|)
 // with E the STFT frame of the current waveform estimate y.  Output: the Hann-windowed inverse transform of X (its 800
-// samples under the window), to be overlap-added.
+// samples under the window), to be overlap-added.  Both 2048-point REAL transforms run as 1024-point complex ones
+// (z[n] = x[2n] + i x[2n+1]) with the usual O(N) split / merge step; the spectrum lives in shared memory only.
 template <bool FIRST>
 __global__ void __launch_bounds__(kThreads) gl_frame_kernel(const float* __restrict__ mag, const int32_t* __restrict__ len,
                                                             const float* __restrict__ window, const float2* __restrict__ twiddle,
                                                             const float* __restrict__ y, long long ldy, int frames_max,
                                                             float* __restrict__ frames) {
-  __shared__ float2 buf[kFft];
-  __shared__ float2 tw[kFft / 2];
+  constexpr int H = kFft / 2;   // 1024
+  __shared__ float2 bufA[H];
+  __shared__ float2 bufB[H];
+  __shared__ float2 tw[kFft];   // e^{-2 pi i m / 2048}, full circle
+  __shared__ float x_nyq;       // X[1024] (real)
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int T = len[b];
   if (t >= T) return;
-  for (int i = tid; i < kFft / 2; i += kThreads) tw[i] = twiddle[i];
+  for (int i = tid; i < kFft; i += kThreads) tw[i] = twiddle[i];
   const float* S = mag + ((size_t)b * frames_max + t) * kBins;
-  constexpr int kPer = (kBins + kThreads - 1) / kThreads;   // 5: bins tid + 256 q (the last one only for tid == 0)
-  float2 X[kPer];
+  float sk[H / kThreads];   // the target magnitudes of this thread's bins, requested before the forward transform hides them
+#pragma unroll
+  for (int q = 0; q < H / kThreads; ++q) sk[q] = S[tid + q * kThreads];
+  const float s_nyq = tid == 0 ? S[H] : 0.f;
+  float2* xp = bufB;   // X'[0..1023] = target magnitude with the estimate's phase
   if (!FIRST) {
     const int L = kHop * (T - 1);
     const float* yb = y + (size_t)b * ldy;
-    for (int i = tid; i < kFft; i += kThreads) {
-      float v = 0.f;
-      if (i >= kLo && i < kHi) {   // np.pad(y, n_fft / 2, mode='reflect'), frame t, times the centred window
-        int idx = t * kHop + i - kFft / 2;
-        if (idx < 0) idx = -idx;
-        if (idx >= L) idx = 2 * (L - 1) - idx;
-        v = yb[idx] * window[i - kLo];
-      }
-      buf[brev11(i)] = make_float2(v, 0.f);
-    }
-    __syncthreads();
-    fft2048<false>(buf, tw);
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int k = tid + q * kThreads;
-      if (k < kBins) {
-        const float2 e = buf[k];
-        const float s = S[k] / fmaxf(1e-8f, sqrtf(e.x * e.x + e.y * e.y));   // audio.py:87-88
-        X[q] = make_float2(e.x * s, e.y * s);
+    for (int q = 0; q < H / kThreads; ++q) {
+      const int n = tid + q * kThreads;
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * n + e;
+        if (i >= kLo && i < kHi) {   // np.pad(y, n_fft / 2, mode='reflect'), frame t, times the centred window
+          int idx = t * kHop + i - kFft / 2;
+          if (idx < 0) idx = -idx;
+          if (idx >= L) idx = 2 * (L - 1) - idx;
+          v[e] = yb[idx] * window[i - kLo];
+        }
       }
+      bufA[n] = make_float2(v[0], v[1]);
     }
     __syncthreads();
+    float2* Z = fft1024<false>(bufA, bufB, tw);   // five passes: the result is in bufB
+    xp = Z == bufA ? bufB : bufA;
+    // split: E = (Z[k] + conj Z[-k]) / 2 (even samples), O = (Z[k] - conj Z[-k]) / 2i (odd samples), X[k] = E + e^{-2 pi i k / N} O
+#pragma unroll
+    for (int q = 0; q < H / kThreads; ++q) {
+      const int k = tid + q * kThreads;
+      const float2 zk = Z[k], zc = Z[(H - k) & (H - 1)];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+      const float2 to = cmul(tw[k], o);
+      float2 X = make_float2(e.x + to.x, e.y + to.y);
+      if (k == 0) {
+        const float xn = zk.x - zk.y;   // X[1024] = E[0] - O[0] (real); its phase is its sign
+        x_nyq = s_nyq * xn / fmaxf(1e-8f, fabsf(xn));
+        X.y = 0.f;
+      }
+      const float sc = sk[q] / fmaxf(1e-8f, sqrtf(X.x * X.x + X.y * X.y));   // audio.py:87-88
+      xp[k] = make_float2(X.x * sc, X.y * sc);
+    }
   } else {
-    __syncthreads();   // twiddles loaded
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
+    for (int q = 0; q < H / kThreads; ++q) {
       const int k = tid + q * kThreads;
-      if (k < kBins) X[q] = make_float2(S[k], 0.f);
+      xp[k] = make_float2(sk[q], 0.f);
     }
-  }
-  // Hermitian extension (librosa.istft: spec | conj(spec[-2:0:-1])); the imaginary parts of DC / Nyquist drop out of .real
-#pragma unroll
-  for (int q = 0; q < kPer; ++q) {
-    const int k = tid + q * kThreads;
-    if (k < kBins) {
-      if (k == 0 || k == kFft / 2) {
-        buf[brev11(k)] = make_float2(X[q].x, 0.f);
-      } else {
-        buf[brev11(k)] = X[q];
-        buf[brev11(kFft - k)] = make_float2(X[q].x, -X[q].y);
-      }
-    }
+    if (tid == 0) x_nyq = s_nyq;
   }
   __syncthreads();
-  fft2048<true>(buf, tw);
+  // merge (Hermitian input; the imaginary parts of DC / Nyquist drop out of librosa's ifft(...).real):
+  // E = (X[k] + conj X[N/2 - k]) / 2, O = (X[k] - conj X[N/2 - k]) / 2 * e^{+2 pi i k / N}, Z[k] = E + i O
+  float2* zin = xp == bufA ? bufB : bufA;
+#pragma unroll
+  for (int q = 0; q < H / kThreads; ++q) {
+    const int k = tid + q * kThreads;
+    float2 xk = xp[k];
+    float2 xm;
+    if (k == 0) {
+      xk.y = 0.f;
+      xm = make_float2(x_nyq, 0.f);
+    } else {
+      const float2 r = xp[H - k];
+      xm = make_float2(r.x, -r.y);
+    }
+    const float2 e = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y + xm.y));
+    const float2 o = cmulc(make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y - xm.y)), tw[k]);
+    zin[k] = make_float2(e.x - o.y, e.y + o.x);
+  }
+  __syncthreads();
+  const float2* z = fft1024<true>(zin, xp, tw);   // z[n] = 1024 (x[2n] + i x[2n+1])
   float* out = frames + ((size_t)b * frames_max + t) * kWin;
-  for (int i = tid; i < kWin; i += kThreads) out[i] = window[i] * buf[kLo + i].x * (1.f / kFft);
+  for (int n = tid; n < kWin / 2; n += kThreads) {
+    const float2 v = z[kLo / 2 + n];
+    *reinterpret_cast<float2*>(out + 2 * n) = make_float2(window[2 * n] * v.x * (1.f / H), window[2 * n + 1] * v.y * (1.f / H));
+  }
 }
 
 // y[b][n] = sum_t frames[b][t][n + 1024 - 200 t - 624] / sum_t window^2[...]   (n < 200 (T - 1): the centre-trimmed ISTFT)
@@ -158,18 +200,56 @@ __global__ void __launch_bounds__(256) gl_ola_kernel(const float* __restrict__ f
   y[(size_t)b * ldy + n] = wss > 1.17549435e-38f ? acc / wss : acc;
 }
 
-// wav[n] = y[n] + c * wav[n - 1]: a first-order recurrence, one thread per utterance (0.5 ms for 200 k samples)
-__global__ void deemphasis_rows_kernel(const float* __restrict__ y, long long ldy, const int32_t* __restrict__ len, int batch,
-                                       float c, float* __restrict__ wav, long long ldw) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
+// wav[n] = y[n] + c * wav[n - 1] (scipy.signal.lfilter([1], [1, -c])): a first-order recurrence = a scan of affine maps
+// s -> a s + b.  One CTA per utterance walks tiles of 2048 samples: every thread folds 8 consecutive samples into (c^8, b),
+// a shuffle scan + eight warp totals give each thread the state it starts from, and it replays its 8 samples from there.
+// (A single thread per utterance took 13 ms of the stage: 200 k dependent, uncoalesced steps.)
+__global__ void __launch_bounds__(256) deemphasis_kernel(const float* __restrict__ y, long long ldy, const int32_t* __restrict__ len,
+                                                         float c, float* __restrict__ wav, long long ldw) {
+  __shared__ float sa[8], sb[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = kHop * (len[b] - 1);
   const float* src = y + (size_t)b * ldy;
   float* dst = wav + (size_t)b * ldw;
-  float prev = 0.f;
-  for (int n = 0; n < L; ++n) {
-    prev = fmaf(c, prev, src[n]);
-    dst[n] = prev;
+  const float c2 = c * c, c4 = c2 * c2, c8 = c4 * c4;
+  float carry = 0.f;
+  for (int base = 0; base < L; base += 2048) {
+    const int n0 = base + 8 * tid;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = n0 + e < L ? src[n0 + e] : 0.f;
+    float bb = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bb = fmaf(c, bb, x[e]);
+    float a = c8;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {   // inclusive scan: (a, bb) o (ap, bp) = (a ap, a bp + bb)
+      const float ap = __shfl_up_sync(0xffffffffu, a, d), bp = __shfl_up_sync(0xffffffffu, bb, d);
+      if (lane >= d) {
+        bb = fmaf(a, bp, bb);
+        a *= ap;
+      }
+    }
+    if (lane == 31) {
+      sa[warp] = a;
+      sb[warp] = bb;
+    }
+    __syncthreads();
+    float st = carry, tot = carry;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) st = fmaf(sa[w], st, sb[w]);
+      tot = fmaf(sa[w], tot, sb[w]);
+    }
+    const float ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, bb, 1);
+    float prev = lane == 0 ? st : fmaf(ae, st, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      prev = fmaf(c, prev, x[e]);
+      if (n0 + e < L) dst[n0 + e] = prev;
+    }
+    __syncthreads();   // sa / sb are rewritten by the next tile
+    carry = tot;
   }
 }
 
@@ -207,7 +287,7 @@ extern "C" int tts_griffin_lim(const TtsGriffinLim* g, void* stream) {
     voc::gl_ola_kernel<<<og, 256, 0, s>>>(g->frames, g->lengths, g->window, g->frames_max, g->y, g->ldy);
     TTS_CHECK_LAUNCH();
   }
-  voc::deemphasis_rows_kernel<<<ceil_div(g->batch, 32), 32, 0, s>>>(g->y, g->ldy, g->lengths, g->batch, g->preemphasis, g->wav, g->ldw);
+  voc::deemphasis_kernel<<<g->batch, 256, 0, s>>>(g->y, g->ldy, g->lengths, g->preemphasis, g->wav, g->ldw);
   TTS_CHECK_LAUNCH();
   return 0;
 }

@@ -55,7 +55,7 @@ class GriffinLim:
         self.inv_t = torch.from_numpy(np.ascontiguousarray(inv.T).astype(np.float32)).to(self.device)
         n = np.arange(hp.win_length, dtype=np.float64)
         self.window = torch.from_numpy((0.5 - 0.5 * np.cos(2.0 * np.pi * n / hp.win_length)).astype(np.float32)).to(self.device)
-        k = np.arange(hp.n_fft // 2, dtype=np.float64)
+        k = np.arange(hp.n_fft, dtype=np.float64)                       # full circle: e^{-2 pi i k / n_fft}
         tw = np.stack([np.cos(2.0 * np.pi * k / hp.n_fft), -np.sin(2.0 * np.pi * k / hp.n_fft)], axis=1)
         self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device)
         self._scratch = None

@@ -250,7 +250,7 @@ int tts_adam_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, f
  * the target magnitude} + a last istft; librosa 0.6.0: Hann window of win_length centred in n_fft, centre = True with
  * reflect padding, window-sum-of-squares normalisation), scipy.signal.lfilter([1], [1, -preemphasis]).  A whole batch at
  * once; utterance b has lengths[b] frames and hop_length * (lengths[b] - 1) output samples.  Host-computed constants:
- * inv_basis_t [n_mels][n_fft/2+1] = pinv(mel basis) transposed, window [win_length] (periodic Hann), twiddle [n_fft/2]
+ * inv_basis_t [n_mels][n_fft/2+1] = pinv(mel basis) transposed, window [win_length] (periodic Hann), twiddle [n_fft]
  * complex = exp(-2 pi i k / n_fft).  Scratch: mag [batch][frames_max][n_fft/2+1], frames [batch][frames_max][win_length],
  * y [batch][ldy]; output wav [batch][ldw].  Built for n_fft 2048 / hop 200 / win 800 (hyperparams.py:7-15). */
 typedef struct TtsGriffinLim {
@@ -258,7 +258,7 @@ typedef struct TtsGriffinLim {
   const int32_t* lengths;     /* [batch] frames per utterance, each >= 7 */
   const float* inv_basis_t;
   const float* window;
-  const float* twiddle;       /* [n_fft/2][2] (re, im) */
+  const float* twiddle;       /* [n_fft][2] (re, im) */
   int32_t batch, frames_max, min_frames, n_mels;
   int32_t n_fft, hop_length, win_length, n_iter;
   float max_abs, max_db, ref_db, power, preemphasis;
