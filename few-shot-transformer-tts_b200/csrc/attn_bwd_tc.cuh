@@ -507,10 +507,13 @@ static int launch_bwd_tc(const Args& a, cudaStream_t s) {
   p.dk = a.dk; p.dv = a.dv; p.lddk = a.lddk; p.lddv = a.lddv; p.dq_acc = a.dq_acc;
   static const bool trace_on = getenv("TTS_ATTN_TC_TRACE") != nullptr && atoi(getenv("TTS_ATTN_TC_TRACE")) != 0;
   p.trace = trace_on ? atoi(getenv("TTS_ATTN_TC_TRACE")) : 0;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<unsigned long long> attr{0ull};   // per device: cudaFuncSetAttribute applies to the current device only
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long dev_bit = 1ull << (dev & 63);
+  if (!(attr.load(std::memory_order_acquire) & dev_bit)) {
     TTS_CHECK_CUDA(cudaFuncSetAttribute(tc::attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmem));
-    attr = true;
+    attr.fetch_or(dev_bit, std::memory_order_release);
   }
   const long long n = (long long)a.B * a.Tq * a.H;
   TTS_CHECK_CUDA(cudaMemsetAsync(a.dq_acc, 0, (size_t)n * DH * sizeof(float), s));

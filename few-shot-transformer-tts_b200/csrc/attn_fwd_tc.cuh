@@ -427,15 +427,18 @@ static int launch_fwd_tc(const Args& a, cudaStream_t s) {
   p.B = a.B; p.H = a.H; p.Tq = a.Tq; p.Tk = a.Tk; p.causal = a.causal; p.n_kw = a.n_kw;
   p.scale_log2 = a.scale_log2; p.drop_scale = a.drop_scale; p.drop_thresh = a.drop_thresh; p.stream = a.stream; p.seed = a.seed;
   p.key_len = a.key_len; p.lse = a.lse; p.keep_mask = a.keep_mask; p.o = a.o; p.ldo = a.ldo;
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<unsigned long long> attr{0ull};   // per device: cudaFuncSetAttribute applies to the current device only
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long dev_bit = 1ull << (dev & 63);
+  if (!(attr.load(std::memory_order_acquire) & dev_bit)) {
     // setmaxnreg redistributes the registers the CTA was launched with: 16 softmax warps x 104 + 4 helper warps x 64
     cudaFuncAttributes fa;
     TTS_CHECK_CUDA(cudaFuncGetAttributes(&fa, tcf::attn_fwd_tc_kernel));
     TTS_REQUIRE((long long)fa.numRegs * tcf::kThreadsF >= 512LL * 104 + 128LL * 64,
                 "attn_fwd_tc: built with %d registers per thread, the kernel's setmaxnreg budget needs 96", fa.numRegs);
     TTS_CHECK_CUDA(cudaFuncSetAttribute(tcf::attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcf::kSmemF));
-    attr = true;
+    attr.fetch_or(dev_bit, std::memory_order_release);
   }
   tcf::attn_fwd_tc_kernel<<<dim3(ceil_div(a.Tq, tcf::kTiles * tcf::BQ), a.H, a.B), tcf::kThreadsF, tcf::kSmemF, s>>>(mq, mk, mv, p);
   TTS_CHECK_LAUNCH();

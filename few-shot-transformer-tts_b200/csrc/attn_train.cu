@@ -20,6 +20,8 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <atomic>
+
 #include "philox.cuh"
 
 namespace tts {

@@ -454,7 +454,7 @@ class TtsEngine:
         return DecodeSession(self, batch, mem_len, t_max, record_align)
 
     def generate(self, batch, max_frames=None, record_align="encdec", chunk=32, impl=0, session=None,
-                 memory=None, dropout=None, compact=None):
+                 memory=None, dropout=None, compact=None, waveform=False):
         """The whole of synthesize.eval_batch (synthesize.py:17-72) as one call: encoder, K/V-cached decode loop with the
         stop bookkeeping on the device (one 4-byte D2H poll per `chunk` steps), Postnet.
 
@@ -465,7 +465,10 @@ class TtsEngine:
         stop logits are scattered back at the end.  Per-row results do not depend on the batch composition (the
         K/V streams of a batch of <= 16 rows are split across SMs, so sums may differ in the last bits).  Default
         (None): on when no attention rows are recorded and dropout is off - alignment rows of a finished sample
-        beyond its stop would stay zero, and the dropout masks are indexed by batch row."""
+        beyond its stop would stay zero, and the dropout masks are indexed by batch row.
+
+        waveform: also run the stage after the path (synthesize.py:82: mel2wav of every utterance's mel_aft[:length]) as one
+        batched Griffin-Lim call on the device (tts_b200/vocoder.py): out["wav"] [B, 200 (T - 1)] and out["wav_lengths"]."""
         cfg = self.cfg
         max_frames = cfg.max_generation_frames if max_frames is None else max_frames
         if memory is None:
@@ -522,6 +525,15 @@ class TtsEngine:
         out = {"mel_pre": mels, "mel_aft": mel_aft, "generated_lengths": lengths, "memory": memory,
                "stop_logits": top.stop_logits[:, :t_gen], "alignments": top.alignments(t_gen), "session": top,
                "compactions": compactions}
+        if waveform:
+            from .vocoder import GriffinLim
+            if getattr(self, "_vocoder", None) is None:
+                self._vocoder = GriffinLim(self.device)
+            lens_host = [int(v) for v in lengths.tolist()]
+            # an utterance shorter than one reflection of the STFT pad (7 frames) is converted with its zero frames up to 7
+            wav, _ = self._vocoder(mel_aft, [min(max(n, 7), t_gen) for n in lens_host])
+            out["wav"] = wav
+            out["wav_lengths"] = [200 * max(n - 1, 0) for n in lens_host]
         return out
 
     def _compact_session(self, sess, rows, n_live, t):

@@ -78,3 +78,21 @@ def test_reference_signature_and_errors(built):
         V.mel2wav(mel[:5])                                # fewer frames than one reflection of the STFT pad needs
     with pytest.raises(RuntimeError):
         V.mel2wav_batch(mel[None], [30], device="cpu")    # no CPU fallback
+
+
+def test_generate_returns_waveforms(built, tiny_params):
+    """synthesize.py:56,82 end to end on the device: generate(waveform=True) = eval_batch + mel2wav of every utterance."""
+    from oracle import tts_oracle as O
+    from tts_b200.engine import TtsEngine
+    cfg, params = tiny_params
+    eng = TtsEngine.from_state_dict(dict(params), cfg, DEV)
+    batch = O.synth_batch(cfg, batch=3, text_len=12, n_frames=4, seed=3)
+    out = eng.generate(batch, max_frames=24, record_align="none", waveform=True)
+    lens = [int(v) for v in out["generated_lengths"].tolist()]
+    assert out["wav"].shape[0] == 3 and out["wav_lengths"] == [200 * max(n - 1, 0) for n in lens]
+    mel = out["mel_aft"].cpu().numpy()
+    for b, n in enumerate(lens):
+        if n >= 7:
+            want = A.mel2wav(mel[b, :n])
+            got = out["wav"][b, :out["wav_lengths"][b]].cpu().numpy()
+            assert np.abs(got - want).max() < 2e-3 * max(np.abs(want).max(), 1e-6)
