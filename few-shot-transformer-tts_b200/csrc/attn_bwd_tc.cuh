@@ -373,17 +373,26 @@ __global__ void __launch_bounds__(kThreads, 1) attn_bwd_tc_kernel(const __grid_c
       mbar_wait(&bars->s_full[s], (it >> 1) & 1u);
       fence_after();
       TC_STAMP(0, 2);
-      uint32_t sv[CPT], dv[CPT];
-      tmem_ld16(lane_addr + cS + s * BQT + cg * CPT, sv);
-      tmem_ld16(lane_addr + cDP + s * BQT + cg * CPT, dv);
-      tmem_wait_ld();
-      TC_STAMP(0, 3);
-      const uint32_t stl = sbase + oStat + qst * kStatBytes + cg * CPT * 4;
-      // interior tiles: every query exists and sees every key of the tile
-      const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
       uint32_t pw[CPT / 2], dw[CPT / 2];
-      if (open) soft_block<true>(p, sv, dv, stl, quad, lane, 0, 0, 0, pw, dw);
-      else soft_block<false>(p, sv, dv, stl, quad, lane, qb + cg * CPT, j, klen, pw, dw);
+      // a warp whose 32 key rows no query of this block can see (beyond the sample's key length - two valid keys in the
+      // last 128-key block of the 258-token cross-attention - or above the causal diagonal) hands over zeros without
+      // reading the logits: the kernel is bound by these warps' instruction issue
+      const bool dead_warp = j0 + quad * 32 >= klen || (p.causal && j0 + quad * 32 > qb + BQT - 1);
+      if (dead_warp) {
+#pragma unroll
+        for (int e = 0; e < CPT / 2; ++e) pw[e] = dw[e] = 0u;
+      } else {
+        uint32_t sv[CPT], dv[CPT];
+        tmem_ld16(lane_addr + cS + s * BQT + cg * CPT, sv);
+        tmem_ld16(lane_addr + cDP + s * BQT + cg * CPT, dv);
+        tmem_wait_ld();
+        TC_STAMP(0, 3);
+        const uint32_t stl = sbase + oStat + qst * kStatBytes + cg * CPT * 4;
+        // interior tiles: every query exists and sees every key of the tile
+        const bool open = qb + BQT <= p.Tq && j0 + BKT <= klen && (!p.causal || j0 + BKT - 1 <= qb);
+        if (open) soft_block<true>(p, sv, dv, stl, quad, lane, 0, 0, 0, pw, dw);
+        else soft_block<false>(p, sv, dv, stl, quad, lane, qb + cg * CPT, j, klen, pw, dw);
+      }
       TC_STAMP(0, 4);
       // P^T goes back into tensor memory, over this thread's own (already loaded) S^T columns: columns 16 cg .. 16 cg + 7 of the
       // buffer hold queries 16 cg .. 16 cg + 15 as bf16 pairs = the A operand of k-step cg of dV += P^T dO.  dS^T goes to
