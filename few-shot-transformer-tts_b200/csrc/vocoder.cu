@@ -25,32 +25,40 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
 
+// Shared-memory index swizzle of the two FFT buffers: bits 5:4 of the index are XORed into bits 1:0 and 3:2.  Sixteen
+// consecutive indices still map to sixteen different 8-byte banks, and so do the strided stores of the first two Stockham
+// passes (4 j + r and 16 (j / 4) + j % 4 + 4 r), which were 4-way bank conflicts.
+__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 4) & 3) * 5); }
+
 // 1024-point complex DFT, Stockham autosort, radix 4: five passes, one butterfly per thread and pass (256 threads), ping-pong
 // between two shared-memory buffers, no bit reversal.  Pass with sub-transform size Ns: thread j reads a[j + 256 r], multiplies by
-// e^{-+ 2 pi i r k / (4 Ns)} (k = j mod Ns; tw = e^{-2 pi i m / 2048}, m = r k 512 / Ns < 1536), radix-4 butterfly, writes
-// b[4 (j - k) + k + r Ns].  INVERSE: conjugate twiddles, unscaled.  Returns the buffer that holds the result (natural order).
+// e^{-+ 2 pi i r k / (4 Ns)} (k = j mod Ns), radix-4 butterfly, writes b[4 (j - k) + k + r Ns].  The twiddles of a pass are
+// stored per pass as [r - 1][k] (consecutive lanes read consecutive entries; indexing one 2048-entry circle was a 16-way bank
+// conflict in the middle passes): ptw = {Ns = 4 | 16 | 64 | 256}, 3 Ns entries each.  INVERSE: conjugate twiddles, unscaled.
+// Returns the buffer that holds the result (natural order, swizzled).
 template <bool INVERSE>
-__device__ __forceinline__ float2* fft1024(float2* a, float2* b, const float2* tw) {
+__device__ __forceinline__ float2* fft1024(float2* a, float2* b, const float2* ptw) {
   const int j = threadIdx.x;
 #pragma unroll
   for (int ls = 0; ls < 10; ls += 2) {
-    const int Ns = 1 << ls, k = j & (Ns - 1), m = k << (9 - ls);
-    const float2 v0 = a[j];
-    float2 v1 = a[j + 256], v2 = a[j + 512], v3 = a[j + 768];
+    const int Ns = 1 << ls, k = j & (Ns - 1);
+    const float2 v0 = a[swz(j)];
+    float2 v1 = a[swz(j + 256)], v2 = a[swz(j + 512)], v3 = a[swz(j + 768)];
     if (ls > 0) {
-      v1 = INVERSE ? cmulc(v1, tw[m]) : cmul(v1, tw[m]);
-      v2 = INVERSE ? cmulc(v2, tw[2 * m]) : cmul(v2, tw[2 * m]);
-      v3 = INVERSE ? cmulc(v3, tw[3 * m]) : cmul(v3, tw[3 * m]);
+      const float2* t = ptw + (Ns - 4) + k;   // 3 (4 + 16 + ...) = Ns - 4 entries precede this pass
+      v1 = INVERSE ? cmulc(v1, t[0]) : cmul(v1, t[0]);
+      v2 = INVERSE ? cmulc(v2, t[Ns]) : cmul(v2, t[Ns]);
+      v3 = INVERSE ? cmulc(v3, t[2 * Ns]) : cmul(v3, t[2 * Ns]);
     }
     const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y), t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
     const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
     const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
     const float2 t3 = INVERSE ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);   // (v1 - v3) * (+-i)
-    float2* o = b + ((j - k) << 2) + k;
-    o[0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-    o[Ns] = make_float2(t1.x + t3.x, t1.y + t3.y);
-    o[2 * Ns] = make_float2(t0.x - t2.x, t0.y - t2.y);
-    o[3 * Ns] = make_float2(t1.x - t3.x, t1.y - t3.y);
+    const int o = ((j - k) << 2) + k;
+    b[swz(o)] = make_float2(t0.x + t2.x, t0.y + t2.y);
+    b[swz(o + Ns)] = make_float2(t1.x + t3.x, t1.y + t3.y);
+    b[swz(o + 2 * Ns)] = make_float2(t0.x - t2.x, t0.y - t2.y);
+    b[swz(o + 3 * Ns)] = make_float2(t1.x - t3.x, t1.y - t3.y);
     __syncthreads();
     float2* t = a; a = b; b = t;
   }
@@ -91,12 +99,16 @@ __global__ void __launch_bounds__(kThreads) gl_frame_kernel(const float* __restr
   constexpr int H = kFft / 2;   // 1024
   __shared__ float2 bufA[H];
   __shared__ float2 bufB[H];
-  __shared__ float2 tw[kFft];   // e^{-2 pi i m / 2048}, full circle
+  __shared__ float2 tw[H];        // e^{-2 pi i k / 2048}, k < 1024: the split / merge step
+  __shared__ float2 ptw[H];       // per-pass twiddles of the 1024-point transform (1020 entries)
   __shared__ float x_nyq;       // X[1024] (real)
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int T = len[b];
   if (t >= T) return;
-  for (int i = tid; i < kFft; i += kThreads) tw[i] = twiddle[i];
+  for (int i = tid; i < H; i += kThreads) {
+    tw[i] = twiddle[i];
+    ptw[i] = twiddle[H + i];
+  }
   const float* S = mag + ((size_t)b * frames_max + t) * kBins;
   float sk[H / kThreads];   // the target magnitudes of this thread's bins, requested before the forward transform hides them
 #pragma unroll
@@ -120,16 +132,16 @@ __global__ void __launch_bounds__(kThreads) gl_frame_kernel(const float* __restr
           v[e] = yb[idx] * window[i - kLo];
         }
       }
-      bufA[n] = make_float2(v[0], v[1]);
+      bufA[swz(n)] = make_float2(v[0], v[1]);
     }
     __syncthreads();
-    float2* Z = fft1024<false>(bufA, bufB, tw);   // five passes: the result is in bufB
+    float2* Z = fft1024<false>(bufA, bufB, ptw);   // five passes: the result is in bufB
     xp = Z == bufA ? bufB : bufA;
     // split: E = (Z[k] + conj Z[-k]) / 2 (even samples), O = (Z[k] - conj Z[-k]) / 2i (odd samples), X[k] = E + e^{-2 pi i k / N} O
 #pragma unroll
     for (int q = 0; q < H / kThreads; ++q) {
       const int k = tid + q * kThreads;
-      const float2 zk = Z[k], zc = Z[(H - k) & (H - 1)];
+      const float2 zk = Z[swz(k)], zc = Z[swz((H - k) & (H - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
       const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
       const float2 to = cmul(tw[k], o);
@@ -140,13 +152,13 @@ __global__ void __launch_bounds__(kThreads) gl_frame_kernel(const float* __restr
         X.y = 0.f;
       }
       const float sc = sk[q] / fmaxf(1e-8f, sqrtf(X.x * X.x + X.y * X.y));   // audio.py:87-88
-      xp[k] = make_float2(X.x * sc, X.y * sc);
+      xp[swz(k)] = make_float2(X.x * sc, X.y * sc);
     }
   } else {
 #pragma unroll
     for (int q = 0; q < H / kThreads; ++q) {
       const int k = tid + q * kThreads;
-      xp[k] = make_float2(sk[q], 0.f);
+      xp[swz(k)] = make_float2(sk[q], 0.f);
     }
     if (tid == 0) x_nyq = s_nyq;
   }
@@ -157,24 +169,24 @@ __global__ void __launch_bounds__(kThreads) gl_frame_kernel(const float* __restr
 #pragma unroll
   for (int q = 0; q < H / kThreads; ++q) {
     const int k = tid + q * kThreads;
-    float2 xk = xp[k];
+    float2 xk = xp[swz(k)];
     float2 xm;
     if (k == 0) {
       xk.y = 0.f;
       xm = make_float2(x_nyq, 0.f);
     } else {
-      const float2 r = xp[H - k];
+      const float2 r = xp[swz(H - k)];
       xm = make_float2(r.x, -r.y);
     }
     const float2 e = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y + xm.y));
     const float2 o = cmulc(make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y - xm.y)), tw[k]);
-    zin[k] = make_float2(e.x - o.y, e.y + o.x);
+    zin[swz(k)] = make_float2(e.x - o.y, e.y + o.x);
   }
   __syncthreads();
-  const float2* z = fft1024<true>(zin, xp, tw);   // z[n] = 1024 (x[2n] + i x[2n+1])
+  const float2* z = fft1024<true>(zin, xp, ptw);   // z[n] = 1024 (x[2n] + i x[2n+1])
   float* out = frames + ((size_t)b * frames_max + t) * kWin;
   for (int n = tid; n < kWin / 2; n += kThreads) {
-    const float2 v = z[kLo / 2 + n];
+    const float2 v = z[swz(kLo / 2 + n)];
     *reinterpret_cast<float2*>(out + 2 * n) = make_float2(window[2 * n] * v.x * (1.f / H), window[2 * n + 1] * v.y * (1.f / H));
   }
 }

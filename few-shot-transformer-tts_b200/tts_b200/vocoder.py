@@ -55,8 +55,17 @@ class GriffinLim:
         self.inv_t = torch.from_numpy(np.ascontiguousarray(inv.T).astype(np.float32)).to(self.device)
         n = np.arange(hp.win_length, dtype=np.float64)
         self.window = torch.from_numpy((0.5 - 0.5 * np.cos(2.0 * np.pi * n / hp.win_length)).astype(np.float32)).to(self.device)
-        k = np.arange(hp.n_fft, dtype=np.float64)                       # full circle: e^{-2 pi i k / n_fft}
-        tw = np.stack([np.cos(2.0 * np.pi * k / hp.n_fft), -np.sin(2.0 * np.pi * k / hp.n_fft)], axis=1)
+        # twiddle table [n_fft]: e^{-2 pi i k / n_fft} for k < n_fft / 2 (the real-transform split / merge), then the per-pass
+        # twiddles of the 1024-point radix-4 Stockham transform: for Ns in (4, 16, 64, 256): for r in (1, 2, 3): e^{-2 pi i r k / (4 Ns)}
+        half = hp.n_fft // 2
+        k = np.arange(half, dtype=np.float64)
+        ang = [2.0 * np.pi * k / hp.n_fft]
+        for ns in (4, 16, 64, 256):
+            kk = np.arange(ns, dtype=np.float64)
+            ang += [2.0 * np.pi * r * kk / (4 * ns) for r in (1, 2, 3)]
+        ang = np.concatenate(ang)
+        ang = np.concatenate([ang, np.zeros(hp.n_fft - ang.size)])
+        tw = np.stack([np.cos(ang), -np.sin(ang)], axis=1)
         self.twiddle = torch.from_numpy(tw.astype(np.float32)).to(self.device)
         self._scratch = None
 

@@ -251,7 +251,7 @@ int tts_adam_multi(const void* table_dev, int32_t n_entries, int64_t n_chunks, f
  * reflect padding, window-sum-of-squares normalisation), scipy.signal.lfilter([1], [1, -preemphasis]).  A whole batch at
  * once; utterance b has lengths[b] frames and hop_length * (lengths[b] - 1) output samples.  Host-computed constants:
  * inv_basis_t [n_mels][n_fft/2+1] = pinv(mel basis) transposed, window [win_length] (periodic Hann), twiddle [n_fft]
- * complex = exp(-2 pi i k / n_fft).  Scratch: mag [batch][frames_max][n_fft/2+1], frames [batch][frames_max][win_length],
+ * complex: exp(-2 pi i k / n_fft) for k < n_fft/2, then the per-pass radix-4 twiddles (tts_b200/vocoder.py).  Scratch: mag [batch][frames_max][n_fft/2+1], frames [batch][frames_max][win_length],
  * y [batch][ldy]; output wav [batch][ldw].  Built for n_fft 2048 / hop 200 / win 800 (hyperparams.py:7-15). */
 typedef struct TtsGriffinLim {
   const float* mel;           /* [batch][frames_max][n_mels], the model's normalised mel (synthesize.py:82) */
