@@ -528,6 +528,55 @@ def train_flops(S, T, B):
     return 3.0 * fwd
 
 
+def gpu_eager_train_sample(dev, B, S, T, autocast_bf16):
+    """SURVEY.md §8d(iii) for metric 2: the reference's training step as plain PyTorch eager on the SAME B200 - the oracle's
+    functional restatement of Tacotron.forward (batch-statistics BatchNorm; dropout off, which only helps it) + compute_loss
+    under torch autograd + torch.optim.Adam, cuBLAS / cuDNN kernels, materialised [B,H,T,T] attention as in the reference.
+    fp32 with TF32 off is the reference's own arithmetic; bf16 autocast is what a user would switch on first.  A reported
+    baseline like cpu_baseline, never the product."""
+    from oracle import tts_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cfg = O.ModelConfig()
+        params = {k: v.to(dev) for k, v in O.synth_params(cfg, seed=0).items()}
+        leaves = [v for k, v in params.items() if v.dtype.is_floating_point and "running_" not in k and "num_batches" not in k]
+        for v in leaves:
+            v.requires_grad_()
+        opt = torch.optim.Adam(leaves, lr=1e-4, eps=1e-6)
+        batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in O.synth_batch(cfg, batch=B, text_len=S, n_frames=T, seed=100).items()}
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
+                out = O.tacotron_forward(params, cfg, batch, batch_stats=True)
+                out = {k: (v.float() if torch.is_tensor(v) else v) for k, v in out.items()}
+            loss = O.compute_loss(params, cfg, batch["mel_targets"], batch["target_lengths"], out)["loss"]
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+
+        step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 2
+        for _ in range(n):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / n
+        return {"value": ms, "unit": "ms", "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                "kind": "torch eager on the same B200: oracle forward + compute_loss + autograd + torch.optim.Adam, %s, dropout off"
+                        % ("bf16 autocast" if autocast_bf16 else "fp32, TF32 off")}
+    except Exception as exc:   # a baseline must never take the benchmark down
+        return {"value": None, "unit": "ms", "error": repr(exc)[:300]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+
+
 def run_train_step(args, dev, rank, world):
     """BASELINE.json metric 2 / configs[2]: the teacher-forced TRAINING step (train.py:165-191: forward, compute_loss,
     backward, gradient all-reduce, Adam) at per-GPU batch 64 x 1000 mel frames, 258 text tokens, bf16 tensor-core
@@ -639,6 +688,10 @@ def run_train_step(args, dev, rank, world):
     step()
     host_issue_ms = 1e3 * (time.perf_counter() - t_h0)
     barrier()
+    eager = None
+    if world == 1 and not args.no_cpu_baseline and not cfg4:
+        torch.cuda.empty_cache()
+        eager = {"bf16_autocast": gpu_eager_train_sample(dev, B, S, T, True), "fp32": gpu_eager_train_sample(dev, B, S, T, False)}
     flops = train_flops(S, T, B)
     valid_frames = B * T
     if cfg4:   # algorithmic FLOPs of the VALID tokens / frames (the padded rows a kernel also touches earn nothing)
@@ -663,6 +716,7 @@ def run_train_step(args, dev, rank, world):
             "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (ms / 1e3) / 1e12 / peak, "traffic": None,
                          "flops_per_step_per_gpu": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "gpu_eager_baseline": eager,
             "allreduce": None if not ar else {"bytes": 4 * n_params, "ms_median": statistics.median(ar),
                                               "note": "exposed time after backward (CUDA events around finish()); the postnet and decoder groups start from "
                                                       "autograd hooks and run behind the rest of backward"}}

@@ -165,9 +165,9 @@ def decoder_forward(params: Params, cfg: ModelConfig, memory, input_lengths, tar
     tmask = _length_mask(target_lengths, T)
     x = x * tmask[..., None]                                                   # modules.py:114
     x = torch.cat([torch.zeros_like(x[:, :1]), x[:, :-1]], dim=1)              # modules.py:115-116
-    x = x + sinusoid_table(T, x.shape[-1], dt) * params["decoder.decoder.pe_scale"].to(dt)
+    x = x + sinusoid_table(T, x.shape[-1], dt).to(x.device) * params["decoder.decoder.pe_scale"].to(dt)
     enc_bias = ((~_length_mask(input_lengths, S)).to(dt) * NEG_BIAS)[:, None, None, :]
-    causal = torch.triu(torch.ones(T, T, dtype=dt), diagonal=1) * NEG_BIAS     # common.py:41-43
+    causal = torch.triu(torch.ones(T, T, dtype=dt, device=x.device), diagonal=1) * NEG_BIAS     # common.py:41-43
     causal = causal[None, None]
     p = "decoder.decoder."
     self_align, cross_align = [], []
@@ -249,9 +249,10 @@ def compute_loss(params: Params, cfg: ModelConfig, mel_targets, target_lengths, 
     aft = ((outputs["mel_aft"] - mel_targets) ** 2).mean(-1)
     aft_each = (aft * m).sum(-1) / target_lengths.to(dt)
     l2 = cfg.reg_weight * sum((params[n].to(dt) ** 2).sum() / 2 for n in l2_names(params))
-    stop_target = (torch.arange(T)[None, :] == (target_lengths[:, None] - 1)).to(dt)
+    dev = outputs["mel_bef"].device
+    stop_target = (torch.arange(T, device=dev)[None, :] == (target_lengths.to(dev)[:, None] - 1)).to(dt)
     ce = F.binary_cross_entropy_with_logits(outputs["stop_logits"], stop_target, reduction="none",
-                                            pos_weight=torch.tensor([5.0], dtype=dt))
+                                            pos_weight=torch.tensor([5.0], dtype=dt, device=dev))
     bef_l, aft_l, ce_l = masked_mean(bef), masked_mean(aft), masked_mean(ce)
     return {"loss": bef_l + aft_l + l2 + ce_l, "bef_loss": bef_l, "aft_loss": aft_l,
             "aft_losses": aft_each, "mse_loss": (bef_l + aft_l) / 2, "l2": l2, "stop_loss": ce_l}
