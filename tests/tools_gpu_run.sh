@@ -22,6 +22,8 @@ case $mode in
     cp /tmp/gl.txt gpurun_out/r2_gemm_log.txt; python tests/tools_gemm_join.py gpurun_out/r2_gemm_log.txt gpurun_out/r2_train_launches.csv > gpurun_out/r2_train_gemm_by_shape.txt 2>&1
     python tests/tools_launch_summary.py gpurun_out/r2_train_launches.csv > gpurun_out/r2_train_launches_summary.txt 2>&1; head -12 gpurun_out/r2_train_launches_summary.txt
     timeout 100 python tests/tools_attn_bench.py > gpurun_out/r2_attn_bench.txt 2>&1
+    timeout 100 python tests/tools_vocoder_bench.py 2> /dev/null | tail -1 > gpurun_out/r2_vocoder_bench.json; cut -c1-200 gpurun_out/r2_vocoder_bench.json
+    python bench.py --workload train --cfg4 --steps 5 --warmup 3 2> /dev/null | tail -1 > gpurun_out/r2_train_cfg4.json
     PIMPL=4 PT=475 PN=50 PTMAX=640 ncu --set full --clock-control none --import-source on -k regex:pipelined_decode_kernel -s 1 -c 1 -f -o gpurun_out/r2_pipe python tests/tools_ncu_target.py > /dev/null 2>&1
     ncu -i gpurun_out/r2_pipe.ncu-rep --page raw --csv > gpurun_out/r2_pipe_ncu_raw.csv
     PB=16 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 3 -f -o gpurun_out/r2_attn python tests/tools_attn_target.py > /dev/null 2>&1
