@@ -567,7 +567,7 @@ def gpu_eager_train_sample(dev, B, S, T, autocast_bf16):
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / n
-        return {"value": ms, "unit": "ms", "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+        return {"value": ms, "unit": "ms", "loss": float(loss.detach()), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                 "kind": "torch eager on the same B200: oracle forward + compute_loss + autograd + torch.optim.Adam, %s, dropout off"
                         % ("bf16 autocast" if autocast_bf16 else "fp32, TF32 off")}
     except Exception as exc:   # a baseline must never take the benchmark down

@@ -18,7 +18,7 @@ case $mode in
     python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; cut -c1-300 gpurun_out/r2_bench.json; tail -3 gpurun_out/r2_bench.err
     python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/r2_train_bench.json 2> gpurun_out/r2_train_bench.err; cut -c1-200 gpurun_out/r2_train_bench.json
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_bench_launches_decode.csv python bench.py --steps 1 --warmup 3 --no-train --no-module-api --no-cpu-baseline > /dev/null 2>&1
-    rm -f /tmp/gl.txt; TTS_GEMM_LOG=/tmp/gl.txt ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 > /dev/null 2>&1
+    rm -f /tmp/gl.txt; TTS_GEMM_LOG=/tmp/gl.txt ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_train_launches.csv python bench.py --workload train --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
     cp /tmp/gl.txt gpurun_out/r2_gemm_log.txt; python tests/tools_gemm_join.py gpurun_out/r2_gemm_log.txt gpurun_out/r2_train_launches.csv > gpurun_out/r2_train_gemm_by_shape.txt 2>&1
     python tests/tools_launch_summary.py gpurun_out/r2_train_launches.csv > gpurun_out/r2_train_launches_summary.txt 2>&1; head -12 gpurun_out/r2_train_launches_summary.txt
     timeout 100 python tests/tools_attn_bench.py > gpurun_out/r2_attn_bench.txt 2>&1
