@@ -62,14 +62,18 @@ class GradBuckets:
         with ctx:
             for bi in self.group_buckets[gi]:
                 flat, items = self.buckets[bi]
+                dsts, srcs = [], []
                 for p, off, n in items:
                     src = fresh.get(id(p))
                     if src is None:
                         src = p.grad
                     if src is not None:
-                        flat[off:off + n].copy_(src.reshape(-1))
+                        dsts.append(flat[off:off + n])
+                        srcs.append(src.reshape(-1))
                     else:
                         flat[off:off + n].zero_()
+                if dsts:   # one multi-tensor copy per bucket instead of one small kernel per parameter
+                    torch._foreach_copy_(dsts, srcs)
                 self._pending.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
         self._done_groups.add(gi)
 
@@ -88,9 +92,10 @@ class GradBuckets:
                 work.wait()
                 flat, items = self.buckets[bi]
                 flat.mul_(1.0 / self.world)
-                for p, off, n in items:
-                    if p.grad is not None:
-                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                dsts = [p.grad for p, off, n in items if p.grad is not None]
+                srcs = [flat[off:off + n].view_as(p.grad) for p, off, n in items if p.grad is not None]
+                if dsts:   # the scatter back is on the critical path (after backward): one multi-tensor copy per bucket
+                    torch._foreach_copy_(dsts, srcs)
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         self._pending = []
