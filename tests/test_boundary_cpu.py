@@ -44,14 +44,17 @@ def test_library_is_sm100a_with_packed_fp32_and_no_legacy_tensor_ops(built):
 def test_struct_layouts_match_the_header(built):
     """sizeof() of the ctypes mirrors equals what the C compiler lays out."""
     from tts_b200 import _native
-    src = '#include <stdio.h>\n#include "tts_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(TtsGemmEpilogue),' \
-          ' sizeof(TtsDecLayerWeights), sizeof(TtsDecoderWeights), sizeof(TtsDecodeState));return 0;}'
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "tts_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu", ' \
+          'sizeof(TtsGemmEpilogue), sizeof(TtsDecLayerWeights), sizeof(TtsDecoderWeights), sizeof(TtsDecodeState), ' \
+          'sizeof(TtsGemmBf16), sizeof(TtsAttnTrain), sizeof(TtsGriffinLim), offsetof(TtsGriffinLim, mag), ' \
+          'offsetof(TtsAttnTrain, keep_mask), offsetof(TtsGemmBf16, out_row_offset));return 0;}'
     exe = os.path.join(ROOT, "few-shot-transformer-tts_b200", "build", "sizes")
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
                    check=True)
     sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     mine = [ctypes.sizeof(c) for c in (_native.GemmEpilogue, _native.DecLayerWeights, _native.DecoderWeights,
-                                       _native.DecodeState)]
+                                       _native.DecodeState, _native.GemmBf16, _native.AttnTrain, _native.GriffinLim)]
+    mine += [_native.GriffinLim.mag.offset, _native.AttnTrain.keep_mask.offset, _native.GemmBf16.out_row_offset.offset]
     assert sizes == mine
 
 
