@@ -64,3 +64,14 @@ def test_griffin_lim_reduces_the_spectral_error():
     assert e20 < e0
     wav = A.mel2wav(mel, n_iter=3)
     assert wav.dtype == np.float32 and wav.shape == (A.HOP * 39,)
+
+
+def test_product_vocoder_refuses_the_cpu_and_never_imports_the_oracle():
+    """No CPU fallback in the product path (the oracle above is the only CPU implementation, and only tests import it)."""
+    import pytest
+    import torch
+    from tts_b200 import vocoder as V
+    with pytest.raises(RuntimeError):
+        V.mel2wav_batch(torch.zeros(1, 30, 80), [30], device="cpu")
+    src = open(V.__file__).read()
+    assert "oracle" not in src.replace("Oracle", "")
