@@ -10,8 +10,9 @@ dependency that is ABSENT from this image: **librosa==0.6.0** (reference ``requi
 PARITY UNPINNED against the reference itself: without librosa the reference's ``utils/audio.py`` cannot be imported
 here, and the reference ships no audio golden vectors.  What IS pinned (``tests/test_oracle_audio.py``): ``stft`` /
 ``istft`` against ``scipy.signal.stft`` / ``istft`` (independent implementation, same frames after rescaling), the
-mel filter bank's published properties (Slaney scale, area normalisation, triangle partition), ``lfilter`` is scipy's
-own.  Only ``tests/`` may import this file; the product path (``few-shot-transformer-tts_b200/``) never does.
+mel filter bank against ``transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")`` (a separate
+implementation written to reproduce ``librosa.filters.mel``; equal to 1e-16) and its published properties, the periodic
+Hann window likewise; ``lfilter`` is scipy's own.  Only ``tests/`` may import this file; the product path (``few-shot-transformer-tts_b200/``) never does.
 """
 from __future__ import annotations
 

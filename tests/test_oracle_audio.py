@@ -75,3 +75,15 @@ def test_product_vocoder_refuses_the_cpu_and_never_imports_the_oracle():
         V.mel2wav_batch(torch.zeros(1, 30, 80), [30], device="cpu")
     src = open(V.__file__).read()
     assert "oracle" not in src.replace("Oracle", "")
+
+
+def test_mel_basis_matches_an_independent_librosa_compatible_implementation():
+    """transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney") is a separate implementation written to
+    reproduce librosa.filters.mel; the periodic Hann window likewise."""
+    import pytest
+    au = pytest.importorskip("transformers.audio_utils")
+    fb = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0,
+                            sampling_rate=16000, norm="slaney", mel_scale="slaney")
+    assert fb.shape == (1025, 80) and np.abs(fb.T - A.mel_basis()).max() < 1e-12
+    w = au.window_function(800, "hann", periodic=True)
+    assert np.abs(w - A.padded_window()[624:1424]).max() < 1e-12
